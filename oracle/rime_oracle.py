@@ -1,0 +1,536 @@
+"""
+CPU oracle for the BayesLIM RIME hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+This file restates, in plain torch-on-CPU, the arithmetic of the reference's
+``rime_model.RIME.forward`` and the model components it calls.  It follows the
+reference's own formulation (a materialised (Nbl, Nfreq, Nsrc) complex fringe
+tensor that is exponentiated, multiplied with the perceived sky and summed), so
+
+  * torch autograd through it gives the reference's gradients, and
+  * timing it on host cores is a faithful stand-in for the reference's CPU path
+    (``bench.py``'s ``cpu_baseline`` / ``--impl reference`` leg).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg
+may import this module.  The product (``bayeslim_b200``) never does.
+
+Pinning: every function here is checked against outputs of the *unmodified*
+reference (imported in the build container through astropy/h5py/healpy stub
+modules, see ``tests/golden/make_golden.py``) stored under ``tests/golden/``.
+Two pieces cannot be pinned that way because the reference delegates them to
+third-party packages that are not installed (and not vendored):
+
+  * ``eq2top`` (astropy ICRS->AltAz; reference ``telescope_model.py:469-502``):
+    "parity unpinned".  The hot path consumes (zen, az), so tests and benches
+    feed both implementations the same angles from :func:`eq2top_synth`.
+  * HEALPix bilinear weights (``healpy.get_interp_weights``, called at
+    reference ``utils.py:765-769``): "parity unpinned"; restated from the
+    published HEALPix ring-interpolation algorithm in :func:`healpix_interp_weights`.
+
+Reference citations are ``file:line`` relative to ``/root/reference/bayeslim``.
+"""
+import math
+
+import numpy as np
+import torch
+
+C_LIGHT = 2.99792458e8          # telescope_model.py:355 (hard coded in the reference)
+D2R = math.pi / 180.0           # utils.py:46
+
+
+# --------------------------------------------------------------------------
+# geometry
+# --------------------------------------------------------------------------
+def make_hex(N, D=15.0):
+    """Hexagonal array of 3N^2-3N+1 antennas with spacing D [m].
+
+    Restates utils.py:1943-1962 (``_make_hex``): 2N-1 rows, row i has
+    N + min(i, 2N-2-i) antennas, rows offset by half a spacing, centred on the
+    mean position.  Returns (ants, antvecs[Nant,3] float64 numpy).
+    """
+    xs, ys = [], []
+    for i in range(2 * N - 1):
+        n_in_row = N + min(i, 2 * N - 2 - i)
+        start = -0.5 * min(i, 2 * N - 2 - i)
+        for j in range(n_in_row):
+            xs.append(start + j)
+            ys.append(i * math.sin(math.pi / 3))
+    xs = np.asarray(xs, dtype=np.float64)
+    ys = np.asarray(ys, dtype=np.float64)
+    xs -= xs.mean()
+    ys -= ys.mean()
+    vecs = np.stack([xs, ys, np.zeros_like(xs)], axis=1) * D
+    return list(range(len(xs))), vecs
+
+
+def hera350():
+    """Synthetic "HERA-350" of SURVEY section 8(d): hex core (N=11, D=14.6 m, 331 ants)
+    plus 19 outriggers at radius 320+12k m, angle 2*pi*k/19."""
+    ants, vecs = make_hex(11, D=14.6)
+    k = np.arange(19)
+    r = 320.0 + 12.0 * k
+    ang = 2 * np.pi * k / 19
+    out = np.stack([r * np.cos(ang), r * np.sin(ang), np.zeros(19)], axis=1)
+    vecs = np.concatenate([vecs, out], axis=0)
+    return list(range(len(vecs))), vecs
+
+
+def cross_baselines(ants):
+    """All (i, j) antenna pairs with i < j in list order."""
+    return [(ants[i], ants[j]) for i in range(len(ants)) for j in range(i + 1, len(ants))]
+
+
+def unique_baselines(ants, antvecs, tol=1.0):
+    """One representative (i, j) per redundant group of baseline vectors.
+
+    Simplified stand-in for ``telescope_model.build_reds`` (:693-942) that only
+    produces the representative list used to build test inputs: two baselines
+    are redundant if their vectors (or the negated vector) agree within tol.
+    """
+    reps, repvecs = [], []
+    vecs = np.asarray(antvecs)
+    for i in range(len(ants)):
+        for j in range(i + 1, len(ants)):
+            v = vecs[j] - vecs[i]
+            found = False
+            for rv in repvecs:
+                if np.linalg.norm(v - rv) < tol or np.linalg.norm(v + rv) < tol:
+                    found = True
+                    break
+            if not found:
+                reps.append((ants[i], ants[j]))
+                repvecs.append(v)
+    return reps
+
+
+def get_blvecs(antvecs, ants, bls):
+    """b = antvecs[j] - antvecs[i] for bl (i, j): telescope_model.py:221-239."""
+    idx = {a: k for k, a in enumerate(ants)}
+    i0 = torch.as_tensor([idx[b[0]] for b in bls], dtype=torch.long)
+    i1 = torch.as_tensor([idx[b[1]] for b in bls], dtype=torch.long)
+    antvecs = torch.as_tensor(antvecs)
+    return antvecs[i1] - antvecs[i0]
+
+
+def eq2top_synth(time, ra, dec, lat=-30.72148, t0=2458148.0, lst0=1.0):
+    """Deterministic stand-in for astropy's ICRS->AltAz.
+
+    Hour-angle rotation at latitude ``lat`` [deg]; ra/dec in degrees, returns
+    (zen, az) in degrees, az East of North.  NOT a restatement of astropy; both
+    the oracle and the CUDA path are fed the same output.
+    """
+    ra = np.asarray(ra, dtype=np.float64) * D2R
+    dec = np.asarray(dec, dtype=np.float64) * D2R
+    phi = lat * D2R
+    lst = 2 * np.pi * 1.0027379 * (float(time) - t0) + lst0
+    H = lst - ra
+    x = -np.cos(dec) * np.sin(H)
+    y = np.cos(phi) * np.sin(dec) - np.sin(phi) * np.cos(dec) * np.cos(H)
+    z = np.sin(phi) * np.sin(dec) + np.cos(phi) * np.cos(dec) * np.cos(H)
+    zen = np.arccos(np.clip(z, -1.0, 1.0)) / D2R
+    az = np.mod(np.arctan2(x, y), 2 * np.pi) / D2R
+    return zen, az
+
+
+def shat(zen, az, dtype=torch.float64):
+    """Unit pointing vectors (3, Ns) from zen/az in degrees: telescope_model.py:337-343."""
+    zen = torch.as_tensor(zen)
+    az = torch.as_tensor(az)
+    _zen = zen * D2R
+    _az = az * D2R
+    s = torch.zeros(3, len(zen), dtype=dtype)
+    s[0] = torch.sin(_zen) * torch.sin(_az)
+    s[1] = torch.sin(_zen) * torch.cos(_az)
+    s[2] = torch.cos(_zen)
+    return s
+
+
+def gen_fringe(blvecs, zen, az, freqs, conj=False, dtype=torch.float64):
+    """exp(+-2 pi i (b.s) nu / c) as an (Nbl, Nf, Ns) tensor: telescope_model.py:310-358."""
+    s = shat(zen, az, dtype=dtype)
+    sign = -2j if conj else 2j
+    const = torch.as_tensor(freqs, dtype=dtype)[:, None] * (sign * math.pi / C_LIGHT)
+    return ((blvecs.to(dtype) @ s)[:, None, :] * const).exp_()
+
+
+def fov_cut(zen, fov):
+    """Indices of sources with zen < fov/2 (strict); all if fov >= 360: beam_model.py:221-224."""
+    zen = torch.as_tensor(zen)
+    if fov < 360:
+        return torch.where(zen < fov / 2)[0]
+    return torch.arange(len(zen))
+
+
+# --------------------------------------------------------------------------
+# beams
+# --------------------------------------------------------------------------
+def airy_disk(zen, az, Dew, freqs, Dns=None, freq_ratio=1.0, square=True):
+    """(2 J1(x)/x)^(2|1) with x = pi nu D(az) sin(min(zen, 90deg)) / c, clipped at 1e-10.
+
+    zen, az in RADIANS (beam_model.py:1418-1482).  J1 = torch.special.bessel_j1
+    (special.py:535), which has no autograd formula: the gradient that reaches
+    Dew/Dns through this function is the truncated one, exactly as in the reference.
+    """
+    zen = torch.as_tensor(zen).clone()
+    az = torch.as_tensor(az)
+    zen[zen > math.pi / 2] = math.pi / 2
+    if Dns is None:
+        diameter = Dew
+    else:
+        diameter = Dns + torch.abs(torch.sin(az)) ** 2 * (Dew - Dns)
+    freqs = torch.as_tensor(freqs)
+    x = diameter * torch.sin(zen) * math.pi * freqs.reshape(-1, 1) * freq_ratio / C_LIGHT
+    x = x.clip(1e-10)
+    beam = 2.0 * torch.special.bessel_j1(x) / x
+    if square:
+        beam = beam ** 2
+    return beam
+
+
+def airy_response(params, zen, az, freqs, freq_ratio=1.0, powerbeam=True):
+    """AiryResponse.__call__ (beam_model.py:956-985): zen/az in DEGREES, params
+    (Npol, Nvec, Nmodel, 1, 1|2) -> beam (Npol, Nvec, Nmodel, Nf, Ns)."""
+    Dew = params[..., 0:1]
+    Dns = params[..., 1:2] if params.shape[-1] > 1 else None
+    zen = torch.as_tensor(zen)
+    az = torch.as_tensor(az)
+    return airy_disk(zen * D2R, az * D2R, Dew, freqs, Dns, freq_ratio, square=powerbeam)
+
+
+def gauss_response(params, zen, az, powerbeam=True):
+    """GaussResponse.__call__ (beam_model.py:886-899); zen/az degrees."""
+    zen_rad = torch.as_tensor(zen) * D2R
+    az_rad = torch.as_tensor(az) * D2R
+    srad = torch.sin(zen_rad)
+    srad = torch.where(zen_rad > math.pi / 2, torch.ones_like(srad), srad)
+    l = srad * torch.sin(az_rad)
+    m = srad * torch.cos(az_rad)
+    beam = torch.exp(-0.5 * ((l / params[..., 0:1]) ** 2 + (m / params[..., 1:2]) ** 2))
+    if not powerbeam:
+        beam = torch.sqrt(beam)
+    return beam
+
+
+_S2D = {'nearest': 0, 'linear': 1, 'quadratic': 2, 'cubic': 3}
+
+
+def _nearest_nodes(grid, xnew, n, wrap):
+    """Sorted indices of the n grid nodes nearest to each xnew, as the reference
+    picks them (argsort of |grid - x|, utils.py:1003-1004), plus the position of
+    xnew relative to the first picked node in units of the grid step."""
+    grid = torch.as_tensor(grid, dtype=torch.float64)
+    xnew = torch.as_tensor(xnew, dtype=torch.float64)
+    N = len(grid)
+    dx = grid[1] - grid[0]
+    if wrap:
+        ext = torch.cat([grid[-n:] - N * dx, grid, grid[:n] + N * dx])
+    else:
+        ext = grid
+    order = torch.argsort(torch.abs(ext - xnew[:, None]), dim=-1)[:, :n]
+    nn = torch.sort(order, dim=-1).values
+    rel = (xnew - ext[nn[:, 0]]) / dx
+    if wrap:
+        nn = (nn - n) % N
+    return nn, rel
+
+
+def _lagrange(rel, n):
+    """Weights of the degree-(n-1) polynomial through nodes 0..n-1 evaluated at rel.
+
+    The reference solves the monomial least-squares system (utils.py:1084-1116);
+    for a square, full-rank design matrix that is exact polynomial interpolation,
+    whose weights are the Lagrange basis polynomials."""
+    w = []
+    for i in range(n):
+        num = torch.ones_like(rel)
+        den = 1.0
+        for j in range(n):
+            if j != i:
+                num = num * (rel - j)
+                den *= (i - j)
+        w.append(num / den)
+    return torch.stack(w, dim=-1)
+
+
+def rect_interp_weights(theta_grid, phi_grid, zen, az, interp_mode='linear'):
+    """(inds, wgts), each (Ns, Nnn), for interpolation on a uniform (phi, theta) grid.
+
+    Restates PixInterp.get_interp 'rect' branch (utils.py:772-798) with
+    bipoly_grid_index (:949-1021, az wraps, zen does not) and
+    setup_bipoly_interp (:1024-1116).  Flat index = ix + Nphi*iy, neighbours
+    ordered with ix fastest.  zen, az, grids in degrees.
+    """
+    if ',' in interp_mode:
+        deg = [_S2D[s.strip()] for s in interp_mode.split(',')]
+    else:
+        deg = [_S2D[interp_mode]] * 2
+    nx, ny = deg[0] + 1, deg[1] + 1
+    xnn, xrel = _nearest_nodes(phi_grid, az, nx, wrap=True)
+    ynn, yrel = _nearest_nodes(theta_grid, zen, ny, wrap=False)
+    Nphi = len(phi_grid)
+    inds = (xnn[:, None, :] + Nphi * ynn[:, :, None]).reshape(len(xrel), -1)
+    wx = _lagrange(xrel, nx)
+    wy = _lagrange(yrel, ny)
+    wgts = (wy[:, :, None] * wx[:, None, :]).reshape(len(xrel), -1)
+    return inds, wgts
+
+
+def interp_map(m, inds, wgts):
+    """out[..., s] = sum_i m[..., inds[s, i]] * wgts[s, i]: utils.py:833-841."""
+    nearest = m.index_select(-1, inds.reshape(-1)).view(m.shape[:-1] + inds.shape)
+    return torch.einsum('...i,...i->...', nearest, wgts.to(nearest.dtype))
+
+
+# ---- HEALPix (RING) helpers: closed-form restatements of healpy calls -----
+def healpix_npix(nside):
+    return 12 * nside * nside
+
+
+def healpix_pixarea(nside):
+    return 4 * math.pi / healpix_npix(nside)
+
+
+def healpix_ring_info(nside):
+    """Per-ring (start pixel, n pixels, cos(theta), phi shift flag) for RING ordering."""
+    nring = 4 * nside - 1
+    start = np.zeros(nring, dtype=np.int64)
+    npr = np.zeros(nring, dtype=np.int64)
+    z = np.zeros(nring, dtype=np.float64)
+    shifted = np.zeros(nring, dtype=bool)
+    ncap = 2 * nside * (nside - 1)
+    npix = healpix_npix(nside)
+    for r in range(1, 4 * nside):
+        if r < nside:                       # north cap
+            npr[r - 1] = 4 * r
+            start[r - 1] = 2 * r * (r - 1)
+            z[r - 1] = 1.0 - r * r / (3.0 * nside * nside)
+            shifted[r - 1] = True
+        elif r <= 3 * nside:                # equatorial belt
+            npr[r - 1] = 4 * nside
+            start[r - 1] = ncap + (r - nside) * 4 * nside
+            z[r - 1] = (2 * nside - r) * 2.0 / (3.0 * nside)
+            shifted[r - 1] = ((r - nside) % 2 == 0)
+        else:                               # south cap
+            rr = 4 * nside - r
+            npr[r - 1] = 4 * rr
+            start[r - 1] = npix - 2 * rr * (rr + 1)
+            z[r - 1] = -1.0 + rr * rr / (3.0 * nside * nside)
+            shifted[r - 1] = True
+    return start, npr, z, shifted
+
+
+def healpix_pix2ang(nside):
+    """(theta, phi) [rad] of all RING-ordered pixel centres (healpy.pix2ang)."""
+    start, npr, z, shifted = healpix_ring_info(nside)
+    theta = np.zeros(healpix_npix(nside))
+    phi = np.zeros(healpix_npix(nside))
+    for r in range(len(start)):
+        j = np.arange(npr[r])
+        shift = 0.5 if shifted[r] else 0.0
+        theta[start[r]:start[r] + npr[r]] = math.acos(z[r])
+        phi[start[r]:start[r] + npr[r]] = (j + shift) * 2 * np.pi / npr[r]
+    return theta, phi
+
+
+def healpix_interp_weights(nside, theta, phi):
+    """Bilinear RING interpolation: (inds, wgts) of shape (Ns, 4).
+
+    Restates the published HEALPix ``get_interpol`` algorithm that
+    ``healpy.get_interp_weights`` wraps (reference call site utils.py:765-769):
+    pick the rings above/below theta; in each ring interpolate linearly in phi
+    between the two bracketing pixels; combine the rings linearly in theta.
+    Beyond the first/last ring, blend the ring pair with the mean of the four
+    polar pixels.  theta, phi in radians.  PARITY UNPINNED (healpy absent).
+    """
+    start, npr, z, shifted = healpix_ring_info(nside)
+    ring_theta = np.arccos(z)
+    theta = np.asarray(theta, dtype=np.float64)
+    phi = np.mod(np.asarray(phi, dtype=np.float64), 2 * np.pi)
+    ns = len(theta)
+    inds = np.zeros((ns, 4), dtype=np.int64)
+    wgts = np.zeros((ns, 4), dtype=np.float64)
+    nring = len(start)
+    npix = healpix_npix(nside)
+    # ring index (0-based) of the last ring with ring_theta <= theta; -1 if above the first ring
+    ir1 = np.searchsorted(ring_theta, theta, side='right') - 1
+
+    def ring_pair(r, ph):
+        n = npr[r]
+        dphi = 2 * np.pi / n
+        shift = 0.5 if shifted[r] else 0.0
+        t = ph / dphi - shift
+        i1 = np.floor(t).astype(np.int64)
+        w = t - i1
+        i2 = i1 + 1
+        i1 = np.mod(i1, n)
+        i2 = np.mod(i2, n)
+        return start[r] + i1, start[r] + i2, 1.0 - w, w
+
+    for k in range(ns):
+        r1 = ir1[k]
+        ph = phi[k]
+        if r1 < 0:                           # north polar cap above ring 1
+            p1, p2, w1, w2 = ring_pair(0, ph)
+            wt = theta[k] / ring_theta[0]
+            inds[k] = [0, 1, 2, 3]
+            wgts[k] = (1 - wt) * 0.25
+            # the ring-1 pair pixels are among (0..3): add their weights
+            wgts[k, p1] += wt * w1
+            wgts[k, p2] += wt * w2
+        elif r1 >= nring - 1:                # south polar cap below last ring
+            p1, p2, w1, w2 = ring_pair(nring - 1, ph)
+            wt = (theta[k] - ring_theta[-1]) / (math.pi - ring_theta[-1])
+            base = npix - 4
+            inds[k] = [base, base + 1, base + 2, base + 3]
+            wgts[k] = wt * 0.25
+            wgts[k, p1 - base] += (1 - wt) * w1
+            wgts[k, p2 - base] += (1 - wt) * w2
+        else:
+            a1, a2, wa1, wa2 = ring_pair(r1, ph)
+            b1, b2, wb1, wb2 = ring_pair(r1 + 1, ph)
+            wt = (theta[k] - ring_theta[r1]) / (ring_theta[r1 + 1] - ring_theta[r1])
+            inds[k] = [a1, a2, b1, b2]
+            wgts[k] = [(1 - wt) * wa1, (1 - wt) * wa2, wt * wb1, wt * wb2]
+    return torch.as_tensor(inds), torch.as_tensor(wgts)
+
+
+def pixel_response_forward(params, powerbeam=True, realbeam=True, log=False, beam0=None,
+                           comp_params=False):
+    """PixelResponse.forward for freq_mode='channel', no LM/taper/norm: beam_model.py:750-793."""
+    p = params
+    if comp_params and not torch.is_complex(p):
+        p = torch.view_as_complex(p)
+    if powerbeam or realbeam:
+        p = p.real
+    if log:
+        p = torch.exp(p)
+    elif powerbeam:
+        p = torch.abs(p)
+    if beam0 is not None:
+        p = p + beam0
+    return p
+
+
+# --------------------------------------------------------------------------
+# sky
+# --------------------------------------------------------------------------
+def point_sky_response(params, freqs, freq_mode='channel', f0=None, log=False):
+    """PointSkyResponse.__call__ (sky_model.py:340-366), modes 'channel' and 'powerlaw'."""
+    if freq_mode == 'channel':
+        out = params
+        if log:
+            out = torch.exp(out)
+        return out
+    if freq_mode == 'powerlaw':
+        amp = params[..., 0:1, :]
+        if log:
+            amp = torch.exp(amp)
+        return amp * (torch.as_tensor(freqs)[:, None] / f0) ** params[..., 1:2, :]
+    raise NotImplementedError(freq_mode)
+
+
+def stokes_to_coherency(sky):
+    """Stokes2Coherency.forward for a (Nstokes, 1, Nf, Ns) input holding
+    [I, fQ, fU(, fV)] with Q = I*fQ etc. (sky_model.py:1284-1313)."""
+    I = sky[0, 0]
+    n = len(sky)
+    if n == 1:
+        return sky
+    Q = I * sky[1, 0]
+    U = I * sky[2, 0] if n > 2 else torch.zeros_like(I)
+    has_v = n > 3
+    dtype = torch.complex128 if (has_v and I.dtype == torch.float64) else (
+        torch.complex64 if has_v else I.dtype)
+    B = torch.zeros(2, 2, *sky.shape[2:], dtype=dtype)
+    B[0, 0] = I + Q
+    B[0, 1] = U
+    B[1, 0] = U
+    B[1, 1] = I - Q
+    if has_v:
+        V = I * sky[3, 0]
+        B[0, 1] = B[0, 1] - 1j * V
+        B[1, 0] = B[1, 0] + 1j * V
+    return B
+
+
+# --------------------------------------------------------------------------
+# RIME
+# --------------------------------------------------------------------------
+def apply_beam(beam, sky, bls, powerbeam=True, ant2beam=None):
+    """Perceived sky (Npol, Npol, Nbl, Nf, Ns): beam_model.py:273-372.
+
+    beam (Npol, Nvec, Nmodel, Nf, Ns); sky (Nvec, Nvec, Nf, Ns); ant2beam maps
+    antenna number -> model index (None: all 0).  Operands of the polarised
+    einsum are promoted to a common dtype first (the reference raises a dtype
+    error otherwise in torch 2.11 -- SURVEY section 9 item 7; promotion does not
+    change the arithmetic).
+    """
+    Npol, Nvec = beam.shape[0], beam.shape[1]
+    a2b = (lambda a: 0) if ant2beam is None else (lambda a: ant2beam[a])
+    bl2mp = {bl: (a2b(bl[0]), a2b(bl[1])) for bl in bls}
+    modelpairs = sorted(set(bl2mp.values()))
+    i1 = torch.as_tensor([mp[0] for mp in modelpairs])
+    i2 = torch.as_tensor([mp[1] for mp in modelpairs])
+    beam1 = torch.index_select(beam, 2, i1)
+    beam2 = torch.index_select(beam, 2, i2)
+    sky = sky[:, :, None]
+    if Npol == 1 and Nvec == 1:
+        if powerbeam:
+            psky = beam1 * sky
+        else:
+            psky = (beam1 * beam2.conj()) * sky
+    elif Npol == 2 and powerbeam:
+        psky = torch.zeros(2, 1, *torch.broadcast_shapes(beam1.shape[2:], sky.shape[2:]),
+                           dtype=torch.result_type(beam1, sky))
+        psky[0] = beam1[0, 0] * sky[0, 0]
+        psky[1] = beam1[1, 0] * sky[0, 0]
+    else:
+        dt = torch.result_type(beam1, sky)
+        psky = torch.einsum("ab...,bc...,dc...->ad...", beam1.to(dt), sky.to(dt),
+                            beam2.conj().to(dt))
+    mp_idx = torch.as_tensor([modelpairs.index(bl2mp[bl]) for bl in bls])
+    return torch.index_select(psky, 2, mp_idx)
+
+
+def prod_and_sum(beam, cut_sky, bls, blvecs, zen, az, freqs, powerbeam=True,
+                 ant2beam=None, conj=False, bl_chunk=None):
+    """sum_s fringe * psky -> (Npol, Npol, Nbl, Nf): rime_model.py:391-440.
+
+    bl_chunk bounds the materialised (Nbl, Nf, Ns) tensor (the reference's own
+    remedy is baseline minibatching, rime_model.py:55-57); the arithmetic per
+    baseline is unchanged.
+    """
+    Nbl = len(bls)
+    bl_chunk = bl_chunk or Nbl
+    out = []
+    for b0 in range(0, Nbl, bl_chunk):
+        sl = slice(b0, min(b0 + bl_chunk, Nbl))
+        psky = apply_beam(beam, cut_sky, bls[sl], powerbeam=powerbeam, ant2beam=ant2beam)
+        fringe = gen_fringe(blvecs[sl], zen, az, freqs, conj=conj,
+                            dtype=blvecs.dtype)
+        out.append(torch.sum(fringe * psky, dim=-1))
+    return torch.cat(out, dim=2)
+
+
+def rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=180.0, powerbeam=True,
+                 ant2beam=None, sim2data=None, bl_chunk=None):
+    """The reference time loop (rime_model.py:326-368) for one sky component.
+
+    sky      : (Nvec, Nvec, Nf, Npix) coherency / (1,1,Nf,Npix) Stokes-I tensor
+    zenaz    : list over times of (zen, az) [deg] for all Npix sources
+    beam_fn  : callable (zen_cut, az_cut) -> (Npol, Nvec, Nmodel, Nf, Ns) beam
+    returns V: (Npol, Npol, Nbl|Ndata, Nt, Nf)
+    """
+    vis = []
+    for zen, az in zenaz:
+        zen = torch.as_tensor(zen)
+        az = torch.as_tensor(az)
+        cut = fov_cut(zen, fov)
+        zc, ac = zen[cut], az[cut]
+        beam = beam_fn(zc, ac)
+        cut_sky = sky.index_select(-1, cut)
+        v = prod_and_sum(beam, cut_sky, bls, blvecs, zc, ac, freqs, powerbeam=powerbeam,
+                         ant2beam=ant2beam, bl_chunk=bl_chunk)
+        if sim2data is not None:
+            v = torch.index_select(v, 2, sim2data)
+        vis.append(v)
+    return torch.stack(vis, dim=3)
