@@ -1,0 +1,86 @@
+"""
+ctypes binding of libb200rime.so (the C-ABI CUDA library declared in include/b200rime.h).
+
+There is no fallback: if the library has not been built, importing this module raises.
+Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C bayeslim_b200/csrc``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200rime.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "bayeslim_b200: %s not found. The CUDA library is the product; there is no CPU or "
+        "PyTorch fallback. Build it with `make -C %s`." % (LIB_PATH, os.path.dirname(LIB_PATH)))
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_P, _I, _L, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double
+
+lib.b200rime_version.restype = ctypes.c_char_p
+lib.b200rime_last_error.restype = ctypes.c_char_p
+lib.b200rime_device_info.argtypes = [_I] + [ctypes.POINTER(_I)] * 4
+lib.b200rime_kc.argtypes = [_I]
+lib.b200rime_microbench.argtypes = [_I, _I, ctypes.POINTER(_D), ctypes.POINTER(_D)]
+lib.b200rime_airy_bwd_blocks.argtypes = [_I, _I]
+
+_SIGS = {
+    "fringe_sum_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _I, _P, _P],
+    "reduce_units": [_P, _P, _I, _I, _I, _P, _L, _L, _L, _D, _D, _I, _P],
+    "fringe_sum_bwd_sky": [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _I, _P, _P],
+    "fringe_sum_bwd_bl": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _I, _I, _P, _P],
+    "pack": [_P, _L, _I, _I, _I, _L, _L, _P, _P],
+    "unpack": [_P, _L, _I, _I, _L, _L, _P, _P],
+    "build_interp": [_P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P],
+    "build_interp_bwd": [_P, _P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _L, _L, _P, _P, _L, _P],
+    "interp_transpose": [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P],
+    "build_airy": [_D, _D, _D, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P, _L, _P],
+    "build_airy_bwd": [_P, _D, _D, _D, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _L, _L, _P, _P, _P],
+}
+for _name, _sig in _SIGS.items():
+    for _suffix in ("f32", "f64"):
+        _fn = getattr(lib, "b200rime_%s_%s" % (_name, _suffix))
+        _fn.argtypes = _sig
+        _fn.restype = _I
+
+
+class B200RimeError(RuntimeError):
+    pass
+
+
+def call(name, suffix, *args):
+    """Invoke b200rime_<name>_<suffix>; raise B200RimeError with the library's message on failure."""
+    rc = getattr(lib, "b200rime_%s_%s" % (name, suffix))(*args)
+    if rc != 0:
+        raise B200RimeError("b200rime_%s_%s failed (%d): %s" % (
+            name, suffix, rc, lib.b200rime_last_error().decode()))
+
+
+def version():
+    return lib.b200rime_version().decode()
+
+
+SRC_PAD = lib.b200rime_src_pad()
+SRC_TILE = lib.b200rime_src_tile()
+KC = {"f32": lib.b200rime_kc(0), "f64": lib.b200rime_kc(1)}
+
+
+def device_info(device=0):
+    vals = [_I() for _ in range(4)]
+    rc = lib.b200rime_device_info(device, *[ctypes.byref(v) for v in vals])
+    if rc != 0:
+        raise B200RimeError(lib.b200rime_last_error().decode())
+    return dict(sm_count=vals[0].value, clock_khz=vals[1].value,
+                cc=(vals[2].value, vals[3].value))
+
+
+def microbench(kind, iters=4096):
+    """kind: 'fp32' | 'fp64' | 'mufu' -> (Gop/s, ms). FMA counted as 2 flop."""
+    k = {"fp32": 0, "fp64": 1, "mufu": 2}[kind]
+    g, ms = _D(), _D()
+    rc = lib.b200rime_microbench(k, iters, ctypes.byref(g), ctypes.byref(ms))
+    if rc != 0:
+        raise B200RimeError(lib.b200rime_last_error().decode())
+    return g.value, ms.value

@@ -1,0 +1,124 @@
+// Library identification, error text, device query and the peak-rate microbenchmarks.
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+#include "internal.h"
+#include "../../include/b200rime.h"
+
+namespace b200rime {
+static thread_local char g_err[512] = "";
+
+int set_error(const char* msg) {
+    std::snprintf(g_err, sizeof(g_err), "%s", msg);
+    return 1;
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        std::snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return 2;
+    }
+    return 0;
+}
+
+// ---- peak-rate microbenchmarks -------------------------------------------------------
+// 8 independent dependent-chains per thread, 1024 threads per SM-resident block set.
+__global__ void __launch_bounds__(256) peak_ffma_kernel(int iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f,
+          a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456f) sink[0] = r;
+}
+__global__ void __launch_bounds__(256) peak_dfma_kernel(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4.,
+           a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double m = 0.999, c = 1e-3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
+}
+__global__ void __launch_bounds__(256) peak_mufu_kernel(int iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 0.1f, a2 = a0 + 0.2f, a3 = a0 + 0.3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a0 = __sinf(a0); a1 = __cosf(a1); a2 = __sinf(a2); a3 = __cosf(a3);
+        }
+    }
+    float r = a0 + a1 + a2 + a3;
+    if (r == 123.456f) sink[0] = r;
+}
+}  // namespace b200rime
+
+using namespace b200rime;
+
+extern "C" {
+
+const char* b200rime_version(void) { return "b200rime 0.1.0 (sm_100a)"; }
+const char* b200rime_last_error(void) { return g_err; }
+int b200rime_src_pad(void) { return SRC_PAD; }
+int b200rime_src_tile(void) { return SRC_TILE; }
+int b200rime_kc(int is_f64) { return is_f64 ? Cfg<double>::KC : Cfg<float>::KC; }
+
+int b200rime_device_info(int device, int* sm_count, int* clock_khz, int* cc_major, int* cc_minor) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    int clk = 0;
+    cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, device);
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (clock_khz) *clock_khz = clk;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return 0;
+}
+
+int b200rime_microbench(int kind, int iters, double* gops, double* ms) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    void* sink = nullptr;
+    if (cudaMalloc(&sink, 64) != cudaSuccess) return set_error("microbench: cudaMalloc failed");
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        if (kind == 0) peak_ffma_kernel<<<blocks, threads>>>(iters, (float*)sink);
+        else if (kind == 1) peak_dfma_kernel<<<blocks, threads>>>(iters, (double*)sink);
+        else peak_mufu_kernel<<<blocks, threads>>>(iters, (float*)sink);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (rep > 0 && t < best) best = t;
+    }
+    int rc = check_launch("microbench");
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (rc) return rc;
+    const double per_thread = (kind == 2) ? 32.0 * iters : 64.0 * iters * 2.0;
+    const double total = per_thread * (double)blocks * threads;
+    if (ms) *ms = best;
+    if (gops) *gops = total / (best * 1e-3) / 1e9;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,441 @@
+"""
+B200-native drop-in for the reference's ``rime_model.RIME`` (bayeslim/rime_model.py:13-482).
+
+Same constructor, attributes, minibatch API and ``VisData`` output; the arithmetic of
+``forward`` -- beam evaluation at the source directions, FOV cut, beam x sky product, fringe
+generation and the sum over sources (rime_model.py:326-440) -- runs in the sm_100a CUDA
+kernels of libb200rime.so through ``ops``:
+
+    reference (per time, torch)                         here (per time group, CUDA)
+    ------------------------------------------------    --------------------------------------
+    beam.gen_beam -> R(params, zen, az)   :354          ops.build_airy / ops.build_interp
+    cut_sky_fov(sky, cut)                 :360            (fused: beam, cut gather, beam*sky,
+    beam.apply_beam(beam, bls, cut_sky)   :423             write tiled layout)   or, for other
+                                                           responses, torch + ops.pack_planes
+    array.gen_fringe(blvecs, zen, az)     :426          ops.fringe_sum (fringe generated on
+    torch.sum(fringe * psky, -1)          :429             the fly, never materialised)
+    torch.stack(skyvis, dim=3)            :368          written in place into (.., Nbl, Nt, Nf)
+
+Gradients reach sky.params, beam.params and array.antvecs through torch.autograd Functions
+whose backward passes are CUDA kernels as well.  There is no CPU path: tensors must be on a
+CUDA device, otherwise forward() raises.
+"""
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from . import utils, dataset, beam_model, ops
+from .dataset import VisData
+
+
+class _GeometryRecord:
+    """Per (sky component, time group) device tables, built once and reused by every forward."""
+
+    def __init__(self):
+        self.src_ids = None
+        self.geom = None
+        self.cuts = None      # per-time int64 index tensors (or None when the FOV keeps all)
+        self.zen = None       # per-time cut zen/az [deg], float64, device
+        self.az = None
+        self.airy = {}        # dtype -> [AiryRecord]
+        self.interp = {}      # (id(R), dtype) -> [InterpRecord]
+
+
+class RIME(utils.Module):
+    """Radio interferometric measurement equation,
+    V_pq(t, nu) = sum_s A_p(s, nu) I(s, nu) A_q(s, nu)^H exp(2 pi i b_pq . s nu / c)."""
+
+    def __init__(self, sky, telescope, beam, array, sim_bls, times, freqs, data_bls=None,
+                 device=None, cache_eq2top=True, name=None, verbose=False):
+        super().__init__(name=name)
+        self.sky = sky
+        self.telescope = telescope
+        self.beam = beam
+        self.array = array
+        self.device = device
+        self.cache_eq2top = cache_eq2top
+        self.verbose = verbose
+        self._geom_cache = {}
+        self._freq_cache = {}
+        self.setup_freqs(freqs)
+        self.setup_sim_bls(sim_bls, data_bls)
+        self.setup_sim_times(times=times)
+
+    # ------------------------------------------------------------------ bookkeeping
+    def push(self, device):
+        dtype = isinstance(device, torch.dtype)
+        self.sim_blvec_groups = {k: v.to(device) for k, v in self.sim_blvec_groups.items()}
+        if not dtype:
+            self.device = device
+            for k, v in self._sim2data.items():
+                if v is not None:
+                    self._sim2data[k] = utils.push(v, device)
+            self.clear_geometry_cache()
+
+    def clear_geometry_cache(self):
+        self._geom_cache = {}
+        self._freq_cache = {}
+
+    @property
+    def Ntimes_all(self):
+        return len(self.all_sim_times)
+
+    @property
+    def Nbls_all(self):
+        return len(self.all_sim_bls)
+
+    def setup_freqs(self, freqs):
+        self.freqs = freqs
+        self.Nfreqs = len(freqs)
+
+    def setup_sim_bls(self, sim_bls, data_bls=None):
+        """Group the simulated baselines and build the sim->data redundancy index
+        (rime_model.py:148-226)."""
+        self.bl_group_id = 0
+        if not isinstance(sim_bls, dict):
+            ints = (int, np.integer)
+            assert isinstance(sim_bls[0][0], ints) or isinstance(sim_bls[0][0][0], ints), \
+                "sim_bls must be list of 2-tuples or list of list of 2-tuples"
+            if isinstance(sim_bls[0], tuple) or isinstance(sim_bls[0][0], ints):
+                sim_bl_groups = {0: list(sim_bls)}
+            else:
+                sim_bl_groups = {i: list(g) for i, g in enumerate(sim_bls)}
+        else:
+            sim_bl_groups = {k: list(v) for k, v in sim_bls.items()}
+        for k in sim_bl_groups:
+            sim_bl_groups[k] = [tuple(int(a) for a in bl) for bl in sim_bl_groups[k]]
+        if data_bls is not None:
+            data_bls = [tuple(int(a) for a in bl) for bl in data_bls]
+        self.sim_bl_groups = sim_bl_groups
+        self.all_sim_bls = [bl for g in sim_bl_groups.values() for bl in g]
+        self.Nbl_groups = len(sim_bl_groups)
+        self.sim_blvec_groups = {k: self.array.get_blvecs(v) for k, v in sim_bl_groups.items()}
+        self._bl_meta = {}
+        if data_bls is None:
+            self.data_bl_groups = self.sim_bl_groups
+            self._sim2data = {k: None for k in sim_bl_groups}
+        else:
+            self._sim2data, self.data_bl_groups = {}, {}
+            bl2red = self.array.bl2red
+            for k, grp in sim_bl_groups.items():
+                sim_red = [bl2red[bl] for bl in grp]
+                keep = set(sim_red)
+                dbls = [bl for bl in data_bls if bl2red[bl] in keep]
+                data_red = [bl2red[bl] for bl in dbls]
+                assert set(sim_red) == set(data_red), \
+                    "non-overlapping bl type(s) in data_bls and sim_bls"
+                assert len(np.where(np.diff(data_red) != 0)[0]) == len(grp) - 1
+                lookup = {r: i for i, r in enumerate(sim_red)}
+                self.data_bl_groups[k] = dbls
+                self._sim2data[k] = torch.as_tensor([lookup[r] for r in data_red],
+                                                    device=self.device)
+        self._set_group()
+
+    def setup_sim_times(self, times):
+        self.time_group_id = 0
+        if not isinstance(times, dict):
+            if isinstance(times, list) or (isinstance(times, (np.ndarray, torch.Tensor))
+                                           and times.ndim > 1):
+                times = {k: np.asarray(t) for k, t in enumerate(times)}
+            else:
+                times = {0: np.asarray(times)}
+        self.sim_time_groups = times
+        self.all_sim_times = np.asarray([t for g in times.values() for t in np.atleast_1d(g)])
+        self.Ntime_groups = len(times)
+        self._set_group()
+
+    @property
+    def Nbatch(self):
+        if hasattr(self, 'sim_bl_groups') and hasattr(self, 'sim_time_groups'):
+            return len(self.sim_bl_groups) * len(self.sim_time_groups)
+        return None
+
+    @property
+    def batch_idx(self):
+        if hasattr(self, 'bl_group_id') and hasattr(self, 'time_group_id'):
+            return self.time_group_id * len(self.sim_bl_groups) + self.bl_group_id
+        return None
+
+    @batch_idx.setter
+    def batch_idx(self, val):
+        assert 0 <= val < self.Nbatch
+        self.time_group_id = int(val // len(self.sim_bl_groups))
+        self.bl_group_id = int(val % len(self.sim_bl_groups))
+        self._set_group()
+
+    def _set_group(self):
+        if hasattr(self, 'sim_bl_groups'):
+            keys = list(self.sim_bl_groups.keys())
+            k = keys[self.bl_group_id] if self.bl_group_id not in self.sim_bl_groups \
+                else self.bl_group_id
+            self._bl_key = k
+            self.sim_bls = self.sim_bl_groups[k]
+            self.sim_blvecs = self.sim_blvec_groups[k]
+            self.Nsim_bls = len(self.sim_bls)
+            self.data_bls = self.data_bl_groups[k]
+            self.Ndata_bls = len(self.data_bls)
+        if hasattr(self, 'sim_time_groups'):
+            keys = list(self.sim_time_groups.keys())
+            k = keys[self.time_group_id] if self.time_group_id not in self.sim_time_groups \
+                else self.time_group_id
+            self.sim_times = self.sim_time_groups[k]
+            self.Ntimes = len(self.sim_times)
+
+    # ------------------------------------------------------------------ device state
+    def _compute_device(self, sky_data):
+        dev = self.device if self.device is not None else sky_data.device
+        dev = torch.device(dev)
+        if dev.type != 'cuda':
+            raise RuntimeError(
+                "bayeslim_b200.RIME runs on CUDA devices only (got %s): the B200 kernels are the "
+                "implementation, there is no CPU path. Push the model to 'cuda'." % dev)
+        return dev if dev.index is not None else torch.device('cuda', torch.cuda.current_device())
+
+    def _freqs64(self, obj, dev):
+        """float64 device copy of obj.freqs (with its optional _freq_idx), cached by identity."""
+        f = obj.freqs
+        idx = getattr(obj, '_freq_idx', None)
+        key = (id(f), str(idx), dev)
+        if key not in self._freq_cache:
+            ff = torch.as_tensor(f)
+            if idx is not None:
+                ff = ff[idx]
+            self._freq_cache[key] = (f, ff.detach().to(device=dev, dtype=torch.float64).contiguous())
+        return self._freq_cache[key][1]
+
+    def _baseline_meta(self, dev, dtype):
+        """(blvecs on the compute device, uniform-frequency flag) for the current group."""
+        if getattr(self.array.antvecs, 'requires_grad', False):
+            # follow the live parameter (fresh graph every forward)
+            blvecs = self.array.get_blvecs(self.sim_bls)
+        else:
+            blvecs = self.sim_blvecs
+        blvecs = blvecs.to(dev)
+        key = (self._bl_key, dev, dtype)
+        if key not in self._bl_meta:
+            blmax = float(blvecs.detach().double().norm(dim=1).max()) if len(blvecs) else 0.0
+            uniform = ops.freqs_uniform(self._freqs64(self.array, dev), blmax, dtype)
+            self._bl_meta[key] = uniform
+        return blvecs, self._bl_meta[key]
+
+    def _geometry(self, sky_comp, dev):
+        """Per-time zen/az -> FOV cut -> packed source axis; cached per (component, time group)."""
+        ra, dec = sky_comp.angs
+        key = (sky_comp.name, len(ra), tuple(float(t) for t in self.sim_times), float(self.beam.fov),
+               str(dev))
+        zenaz, ids = [], []
+        for time in self.sim_times:
+            tkey = (sky_comp.name, len(ra), time)
+            za = self.telescope.eq2top(time, ra, dec, store=self.cache_eq2top, key=tkey)
+            zenaz.append(za)
+            ids.append(id(za))
+        rec = self._geom_cache.get(key)
+        if rec is not None and self.cache_eq2top and rec.src_ids == tuple(ids):
+            return rec
+        rec = _GeometryRecord()
+        rec.src_ids = tuple(ids)
+        rec.cuts, rec.zen, rec.az = [], [], []
+        for time, za in zip(self.sim_times, zenaz):
+            zen = torch.as_tensor(za[0]).to(dev, torch.float64)
+            az = torch.as_tensor(za[1]).to(dev, torch.float64)
+            tkey = (sky_comp.name, len(ra), time)
+            zen._arr_hash = tkey
+            cut = self.beam.sky_cut(zen)
+            if isinstance(cut, slice):
+                cut = torch.arange(len(zen), device=dev)
+            cut = cut.to(dev)
+            zc, ac = zen[cut], az[cut]
+            zc._arr_hash = tkey
+            rec.cuts.append(cut)
+            rec.zen.append(zc)
+            rec.az.append(ac)
+        rec.geom = ops.Geometry(rec.zen, rec.az, dev)
+        self._geom_cache[key] = rec
+        return rec
+
+    # ------------------------------------------------------------------ perceived sky
+    def _fused_mode(self, sky):
+        """'airy' | 'interp' when the beam/sky combination has a fused CUDA builder, else None."""
+        b, R = self.beam, self.beam.R
+        if not (b.powerbeam and b.Nvec == 1 and b.Nmodel == 1 and sky.shape[:2] == (1, 1)):
+            return None
+        if sky.is_complex() or getattr(b, 'theta_x', 0) > 0 or getattr(b, 'theta_y', 0) > 0:
+            return None
+        rname = R.__class__.__name__
+        if rname == 'AiryResponse' and not getattr(R, 'brute_force', False) \
+                and getattr(R, 'taper_kwargs', None) is None:
+            return 'airy'
+        if rname == 'PixelResponse' and getattr(R, 'Rchi', None) is None:
+            return 'interp'
+        return None
+
+    def _build_airy(self, sky, rec, dev):
+        b, R = self.beam, self.beam.R
+        dtype = sky.dtype
+        if dtype not in rec.airy:
+            rec.airy[dtype] = [ops.AiryRecord(c, z, a, dtype, dev)
+                               for c, z, a in zip(rec.cuts, rec.zen, rec.az)]
+        p = b.total_params().to(dev)
+        f64 = self._freqs64(b, dev)
+        planes = [ops.build_airy(sky[0, 0], p[ipol, 0, 0, 0], rec.geom, rec.airy[dtype], f64,
+                                 freq_ratio=R.freq_ratio, square=True,
+                                 full_grad=getattr(R, 'full_grad', False))
+                  for ipol in range(b.Npol)]
+        return planes[0] if len(planes) == 1 else torch.cat(planes, dim=0)
+
+    def _build_interp(self, sky, rec, dev):
+        b, R = self.beam, self.beam.R
+        dtype = sky.dtype
+        if R.beam_cache is None:
+            R.set_beam_cache(b.total_params())
+        bmap = R.beam_cache.to(dev)
+        key = (id(R), R.interp_mode, dtype)
+        if key not in rec.interp:
+            recs = []
+            for c, z, a in zip(rec.cuts, rec.zen, rec.az):
+                inds, wgts = R.get_interp(z, a)
+                recs.append(ops.InterpRecord(c, inds, wgts, bmap.shape[-1], dtype, dev))
+            rec.interp[key] = recs
+        planes = [ops.build_interp(sky[0, 0], bmap[ipol, 0, 0], rec.geom, rec.interp[key])
+                  for ipol in range(b.Npol)]
+        return planes[0] if len(planes) == 1 else torch.cat(planes, dim=0)
+
+    def _generic_planes(self, sky, rec, dev):
+        """Any response function: beam and beam*sky*beam^H in torch on the device (cheap: not
+        multiplied by Nbl), then one real plane per (pol product, model pair, re|im)."""
+        b = self.beam
+        p = b.total_params()
+        modelpairs, mp_idx = b.model_pairs(self.sim_bls)
+        per_time = []
+        for cut, zen, az in zip(rec.cuts, rec.zen, rec.az):
+            beam = b.R(p, zen, az, b.freqs)
+            beam = torch.as_tensor(beam).to(dev)
+            cut_sky = sky.index_select(-1, cut)
+            per_time.append(beam_model.perceived_sky(beam, cut_sky, modelpairs, b.Npol, b.Nvec,
+                                                     b.powerbeam))
+        return per_time, modelpairs, mp_idx
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, *args, prior_cache=None, **kwargs):
+        """Simulate the visibilities of the current (time group, baseline group) batch.
+        Returns VisData with data of shape (Npol, Npol, Ndata_bls, Ntimes, Nfreqs)."""
+        self._set_group()
+        sky_components = self.sky.forward(prior_cache=prior_cache)
+        if not isinstance(sky_components, list):
+            sky_components = [sky_components]
+        Npol = self.beam.Npol
+        pol = "{}{}".format(self.beam.pol, self.beam.pol) if Npol == 1 else None
+        if hasattr(self.beam.R, 'clear_beam_cache'):
+            self.beam.R.clear_beam_cache()
+        self.beam.skycut_device = getattr(self.sky, 'device', None)
+
+        start = datetime.now().timestamp()
+        vis = None
+        for i, sky_comp in enumerate(sky_components):
+            sky = sky_comp.data
+            dev = self._compute_device(sky)
+            sky = sky.to(dev)
+            rdtype = ops._real(sky.dtype)
+            rec = self._geometry(sky_comp, dev)
+            blvecs, uniform = self._baseline_meta(dev, rdtype)
+            f64 = self._freqs64(self.array, dev)
+            nfreq = len(f64)
+            mode = self._fused_mode(sky)
+            if mode is not None:
+                A = self._build_airy(sky, rec, dev) if mode == 'airy' \
+                    else self._build_interp(sky, rec, dev)
+                V = ops.fringe_sum(A, blvecs, rec.geom, f64, nfreq, conj=False, uniform=uniform)
+                skyvis = V[:, None]                     # (Npol, 1, Nbl, Nt, Nf)
+            else:
+                skyvis = self._forward_generic(sky, rec, dev, blvecs, f64, nfreq, uniform)
+            if self.verbose:
+                log("sky model {}/{} | {} elapsed".format(i + 1, len(sky_components),
+                                                          elapsed_time(start)), verbose=True)
+            vis = skyvis if vis is None else vis + skyvis
+        self.beam.eval_prior(prior_cache)
+
+        sim2data = self._sim2data[self._bl_key]
+        if sim2data is not None:
+            vis = torch.index_select(vis, 2, sim2data.to(vis.device))
+
+        vd = VisData()
+        telescope = self.telescope.__class__(self.telescope.location,
+                                             tloc=getattr(self.telescope, 'tloc', None),
+                                             device=self.telescope.device)
+        vd.setup_meta(telescope, self.array.to_antpos())
+        vd.setup_data(self.data_bls, self.sim_times, self.freqs, pol=pol, data=vis, flags=None,
+                      cov=None, history=self._history())
+        return vd
+
+    def _forward_generic(self, sky, rec, dev, blvecs, f64, nfreq, uniform):
+        per_time, modelpairs, mp_idx = self._generic_planes(sky, rec, dev)
+        P, Q = per_time[0].shape[0], per_time[0].shape[1]
+        cplx = per_time[0].is_complex()
+        mp_idx_t = torch.as_tensor(mp_idx, device=dev)
+        out = None
+        for m in range(len(modelpairs)):
+            sel = torch.where(mp_idx_t == m)[0]
+            planes = []
+            for X in per_time:
+                Xm = X[:, :, m].reshape(P * Q, X.shape[-2], X.shape[-1])
+                planes.append(torch.cat([Xm.real, Xm.imag], dim=0) if cplx else Xm)
+            A = ops.pack_planes(rec.geom, [pl.contiguous() for pl in planes])
+            V = ops.fringe_sum(A, blvecs.index_select(0, sel), rec.geom, f64, nfreq, conj=False,
+                               uniform=uniform)
+            if cplx:
+                V = V[:P * Q] + 1j * V[P * Q:]
+            V = V.reshape(P, Q, len(sel), V.shape[-2], V.shape[-1])
+            if len(modelpairs) == 1:
+                return V
+            if out is None:
+                out = torch.zeros(P, Q, len(mp_idx), V.shape[-2], V.shape[-1], dtype=V.dtype,
+                                  device=dev)
+            out = out.index_copy(2, sel, V)
+        return out
+
+    def _history(self):
+        return "bayeslim_b200.RIME | sky={} beam={}({}) array={} Nbls={} Ntimes={} Nfreqs={}".format(
+            self.sky.__class__.__name__, self.beam.__class__.__name__,
+            self.beam.R.__class__.__name__, self.array.__class__.__name__, len(self.sim_bls),
+            self.Ntimes, self.Nfreqs)
+
+    def run_batches(self, concat=True):
+        """forward() for every minibatch, concatenated over baselines then times
+        (rime_model.py:442-482)."""
+        vis_times, vis_bls = [], []
+        for i in range(self.Nbatch):
+            self.batch_idx = i
+            vis = self.forward()
+            vis_bls.append(vis)
+            if self.Nbatch == 1:
+                vis_times.append(vis)
+            elif self.bl_group_id == self.Nbl_groups - 1:
+                if concat:
+                    vis_times.append(dataset.concat_VisData(vis_bls, 'bl'))
+                else:
+                    vis_times.extend(vis_bls)
+                vis_bls = []
+        out = dataset.concat_VisData(vis_times, 'time') if concat else vis_times
+        self.batch_idx = 0
+        return out
+
+
+def log(message, verbose=False, style=1):
+    if verbose:
+        if style == 1:
+            print("{}".format(message))
+        elif style == 2:
+            print("{}\n{}".format(message, '-' * 30))
+        else:
+            print("\n{}\n{}\n{}".format('-' * 30, message, '-' * 30))
+
+
+def elapsed_time(start):
+    t = datetime.now().timestamp() - start
+    unit = 'sec'
+    if t > 60000:
+        t, unit = t / 3600, 'hrs'
+    elif t > 1000:
+        t, unit = t / 60, 'min'
+    return "{:.3f} {}".format(t, unit)

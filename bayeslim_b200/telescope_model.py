@@ -1,0 +1,326 @@
+"""
+Host-side mirror of the reference's telescope_model (bayeslim/telescope_model.py):
+``TelescopeModel`` (sky -> topocentric angles, cached) and ``ArrayModel`` (antenna
+layout, baseline vectors, redundancy bookkeeping, fringe).
+
+Differences that matter:
+  * astropy is not a dependency.  ``TelescopeModel.eq2top`` answers from ``conv_cache``
+    (the reference's own cache, keyed exactly as rime_model.py:345 builds the key) and, on a
+    miss, from a built-in rigid sky rotation about the celestial pole (no precession /
+    nutation / aberration -- parity with astropy is unpinned); users who
+    need astropy's transformation inject its output into ``conv_cache`` or pass
+    ``eq2top_fn``.
+  * ``ArrayModel.gen_fringe`` keeps the reference signature and semantics for callers
+    outside the RIME (imaging), but ``rime_model.RIME`` never calls it: the fringe is
+    generated inside the CUDA kernels (ops.fringe_sum).
+"""
+import copy
+import itertools
+
+import numpy as np
+import torch
+
+from . import utils
+from .utils import _float, D2R
+
+
+class TelescopeModel:
+    """Telescope location + equatorial -> topocentric conversion cache
+    (telescope_model.py:20-137)."""
+
+    def __init__(self, location, tloc=None, device=None, dtype=None, eq2top_fn=None):
+        self.location = location
+        self.tloc = tloc
+        self.dtype = dtype
+        self.conv_cache = {}
+        self.device = device
+        self.eq2top_fn = eq2top_fn
+
+    def hash(self, time, ra):
+        return (time, len(ra))
+
+    def clear_cache(self, key=None):
+        if key is None:
+            self.conv_cache = {}
+        else:
+            del self.conv_cache[key]
+
+    def eq2top(self, time, ra, dec, store=False, key=None):
+        """(zen, az) [deg] stacked as a (2, Nsrc) tensor; az is East of North."""
+        key = key if key is not None else self.hash(time, ra)
+        if key in self.conv_cache:
+            return self.conv_cache[key]
+        ra_n, dec_n = utils.tensor2numpy(ra), utils.tensor2numpy(dec)
+        fn = self.eq2top_fn if self.eq2top_fn is not None else eq2top
+        angs = fn(self.location, time, ra_n, dec_n)
+        angs = torch.as_tensor(np.asarray(angs), device=self.device, dtype=self.dtype)
+        if store:
+            self.conv_cache[key] = angs
+        return angs
+
+    def push(self, device):
+        dtype = isinstance(device, torch.dtype)
+        if dtype:
+            self.dtype = device
+        else:
+            self.device = device
+        for k in self.conv_cache:
+            self.conv_cache[k] = utils.push(self.conv_cache[k], device)
+
+
+def JD2LST(jd, longitude):
+    """Approximate local (mean) sidereal time [rad] at east longitude [deg]: GMST polynomial
+    of the IAU 1982 model.  Stand-in for the astropy call of telescope_model.py:671-690."""
+    d = np.asarray(jd, dtype=np.float64) - 2451545.0
+    gmst_hours = 18.697374558 + 24.06570982441908 * d
+    return np.mod(gmst_hours * 15.0 + longitude, 360.0) * D2R
+
+
+def eq2top(location, time, ra, dec):
+    """Rigid rotation of (ra, dec) [deg] to (zen, az) [deg] at `location` (lon, lat[, alt]) and
+    Julian date `time`.  Not astropy's ICRS->AltAz (telescope_model.py:469-502): no precession,
+    nutation, aberration or refraction."""
+    lon, lat = location[0], location[1]
+    lst = JD2LST(time, lon)
+    ra = np.asarray(ra, dtype=np.float64) * D2R
+    dec = np.asarray(dec, dtype=np.float64) * D2R
+    phi = lat * D2R
+    H = lst - ra
+    x = -np.cos(dec) * np.sin(H)
+    y = np.cos(phi) * np.sin(dec) - np.sin(phi) * np.cos(dec) * np.cos(H)
+    z = np.sin(phi) * np.sin(dec) + np.cos(phi) * np.cos(dec) * np.cos(H)
+    zen = np.arccos(np.clip(z, -1, 1)) / D2R
+    az = np.mod(np.arctan2(x, y), 2 * np.pi) / D2R
+    return zen, az
+
+
+class ArrayModel(utils.Module, utils.AntposDict):
+    """Antenna layout, baseline vectors and the interferometric fringe
+    (telescope_model.py:140-466)."""
+
+    def __init__(self, antpos, freqs=None, device=None, cache_s=True, cache_depth=None,
+                 redtol=1.0, name=None, **kwargs):
+        utils.Module.__init__(self, name=name)
+        if isinstance(antpos, utils.AntposDict):
+            ants, antvecs = antpos.ants, antpos.antvecs
+        else:
+            ants, antvecs = list(antpos.keys()), list(antpos.values())
+        utils.AntposDict.__init__(self, ants, antvecs)
+        self.cache_s = cache_s
+        self.clear_cache()
+        self.redtol = redtol
+        self.device = device
+        self.cache_depth = cache_depth
+        self.set_freqs(freqs)
+        (self.reds, self.redvecs, self.bl2red, self.bls, self.redlens, self.redangs,
+         self.redtags) = build_reds(self, redtol=redtol, **kwargs)
+        if device:
+            self.push(device)
+
+    # nn.Module defines __getitem__-free attribute access; route dict-style access to AntposDict
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return utils.Module.__getitem__(self, key)
+        return utils.AntposDict.__getitem__(self, key)
+
+    def __setitem__(self, key, value):
+        if isinstance(key, str):
+            return utils.Module.__setitem__(self, key, value)
+        return utils.AntposDict.__setitem__(self, key, value)
+
+    def get_antpos(self, ant):
+        return utils.AntposDict.__getitem__(self, ant)
+
+    def get_blvecs(self, bls):
+        """Baseline vectors b = antvecs[j] - antvecs[i] (ENU, metres), differentiable w.r.t.
+        antvecs (telescope_model.py:221-239).  One gather + subtract instead of a per-baseline
+        Python stack."""
+        if isinstance(bls, tuple) or isinstance(bls[0], (int, np.integer)):
+            bls = [tuple(bls)]
+        i0 = torch.as_tensor([self._ant_idx[int(b[0])] for b in bls], dtype=torch.long,
+                             device=self.antvecs.device)
+        i1 = torch.as_tensor([self._ant_idx[int(b[1])] for b in bls], dtype=torch.long,
+                             device=self.antvecs.device)
+        return self.antvecs.index_select(0, i1) - self.antvecs.index_select(0, i0)
+
+    def set_freqs(self, freqs):
+        self.freqs = freqs
+        if self.freqs is not None:
+            self.freqs = torch.as_tensor(self.freqs, dtype=_float(), device=self.device)
+
+    def set_freq_index(self, idx=None):
+        self._freq_idx = idx
+
+    def clear_cache(self, depth=None):
+        if depth is None:
+            self.cache = {}
+        else:
+            utils.clear_cache_depth(self.cache, depth)
+
+    def gen_fringe(self, blvecs, zen, az, conj=False):
+        """Materialised fringe exp(+-2 pi i (b . s) nu / c) of shape (Nbls, Nfreqs, Npix);
+        zen, az in degrees (telescope_model.py:310-358).  API compatibility for callers
+        outside the RIME -- the RIME hot path generates the fringe inside its kernels."""
+        key = utils.arr_hash(zen)
+        if not self.cache_s or key not in self.cache:
+            _zen, _az = zen * D2R, az * D2R
+            s = torch.zeros(3, len(zen), dtype=_float(), device=self.device)
+            s[0] = torch.sin(_zen) * torch.sin(_az)
+            s[1] = torch.sin(_zen) * torch.cos(_az)
+            s[2] = torch.cos(_zen)
+            if self.cache_s:
+                self.cache[key] = s
+        else:
+            s = self.cache[key]
+        sign = -2j if conj else 2j
+        freqs = self.freqs
+        if getattr(self, '_freq_idx', None) is not None:
+            freqs = freqs[self._freq_idx]
+        const = freqs[:, None] * (sign * np.pi / 2.99792458e8)
+        return ((blvecs @ s)[:, None, :] * const).exp_()
+
+    def push(self, device):
+        dtype = isinstance(device, torch.dtype)
+        utils.AntposDict.push(self, device)
+        if self.freqs is not None:
+            self.freqs = self.freqs.to(device)
+        if not dtype:
+            self.device = device
+        for k in self.cache:
+            if isinstance(self.cache[k], torch.Tensor):
+                self.cache[k] = self.cache[k].to(device)
+
+    def get_bls(self, uniq_bls=False, keep_autos=True, min_len=None, max_len=None, min_EW=None,
+                max_EW=None, min_NS=None, max_NS=None, min_deg=None, max_deg=None, xants=None):
+        """All physical baselines (or one per redundant group), optionally selected on the
+        baseline vector (telescope_model.py:373-460)."""
+        lens = np.asarray(self.redlens, dtype=float)
+        angs = np.asarray(self.redangs, dtype=float)
+        vecs = np.abs(np.asarray([utils.tensor2numpy(v) for v in self.redvecs]).reshape(len(lens), -1))
+        keep = np.ones(len(lens), dtype=bool)
+        if not keep_autos:
+            autos = np.isclose(lens, 0, atol=self.redtol)
+            if autos.any():
+                keep[np.where(autos)[0][0]] = False
+        if min_len is not None:
+            keep &= lens >= min_len
+        if max_len is not None:
+            keep &= lens <= max_len
+        if min_EW is not None:
+            keep &= vecs[:, 0] >= min_EW
+        if max_EW is not None:
+            keep &= vecs[:, 0] <= max_EW
+        if min_NS is not None:
+            keep &= vecs[:, 1] >= min_NS
+        if max_NS is not None:
+            keep &= vecs[:, 1] <= max_NS
+        if min_deg is not None:
+            keep &= angs >= min_deg
+        if max_deg is not None:
+            keep &= angs <= max_deg
+        reds = [list(self.reds[i]) for i in np.where(keep)[0]]
+        if uniq_bls:
+            reds = [red[:1] for red in reds]
+        bls = [bl for red in reds for bl in red]
+        if xants is not None:
+            bls = [bl for bl in bls if bl[0] not in xants and bl[1] not in xants]
+        return bls
+
+    def to_antpos(self):
+        return utils.AntposDict(copy.deepcopy(self.ants), self.antvecs.detach().clone())
+
+
+def build_reds(antpos, bls=None, red_bls=None, redtol=1.0, min_len=None, max_len=None,
+               min_EW_len=None, exclude_reds=None, skip_reds=False, norm_vec=False,
+               use_blnums=False, use_2d=False, fcluster=False, red_info=None):
+    """Sort baselines into redundant groups (telescope_model.py:693-942).
+
+    Same outputs and ordering conventions as the reference: groups are formed greedily in
+    baseline order (first vector within `redtol` wins), then sorted by length + angle*redtol/180;
+    returns (reds, redvecs, bl2red, bls, redlens, redangs, redtags).  The group search is a
+    vectorised distance test per baseline instead of a Python double loop."""
+    if red_info is not None:
+        return red_info
+    if use_blnums or fcluster:
+        raise NotImplementedError("use_blnums / fcluster are not part of the RIME path")
+    ants = list(antpos.keys())
+    if bls is None:
+        bls = [(a, a) for a in ants] + list(itertools.combinations(ants, 2))
+    idx = {a: i for i, a in enumerate(ants)}
+    pos = utils.tensor2numpy(antpos.antvecs if hasattr(antpos, 'antvecs')
+                             else torch.as_tensor(np.asarray(list(antpos.values()))))
+    pos = np.asarray(pos, dtype=np.float64)
+    i0 = np.asarray([idx[b[0]] for b in bls])
+    i1 = np.asarray([idx[b[1]] for b in bls])
+    vec = pos[i1] - pos[i0]
+    if use_2d:
+        vec = vec[:, :2]
+    lens = np.linalg.norm(vec, axis=1)
+    if norm_vec:
+        vec = np.zeros_like(vec)
+        vec[:, 0] = lens
+    keep = np.ones(len(bls), dtype=bool)
+    if min_len is not None:
+        keep &= lens > min_len
+    if max_len is not None:
+        keep &= lens < max_len
+    if min_EW_len is not None:
+        keep &= np.abs(vec[:, 0]) > min_EW_len
+    if exclude_reds is not None:
+        ex = np.asarray([pos[idx[b[1]]] - pos[idx[b[0]]] for b in exclude_reds])
+        if use_2d:
+            ex = ex[:, :2]
+        for e in ex:
+            keep &= ~((np.linalg.norm(vec - e, axis=1) < redtol) |
+                      (np.linalg.norm(vec + e, axis=1) < redtol))
+    sel = np.where(keep)[0]
+    bls = [bls[i] for i in sel]
+    vec, lens = vec[sel], lens[sel]
+
+    if skip_reds:
+        group = np.arange(len(bls))
+        rvec = vec.copy()
+    else:
+        group = np.zeros(len(bls), dtype=np.int64)
+        rvec = np.zeros_like(vec)
+        ngroup = 0
+        for b in range(len(bls)):
+            g = -1
+            if ngroup:
+                hit = np.where(np.linalg.norm(rvec[:ngroup] - vec[b], axis=1) < redtol)[0]
+                if len(hit):
+                    g = hit[0]
+            if g < 0:
+                g = ngroup
+                rvec[g] = vec[b]
+                ngroup += 1
+            group[b] = g
+        rvec = rvec[:ngroup]
+    rlens = np.linalg.norm(rvec, axis=1)
+    rangs = np.degrees(np.arctan2(rvec[:, 1], rvec[:, 0]))
+    rangs = np.where(rvec[:, 1] < 0, rangs + 180.0, rangs)
+    rangs = np.where(np.abs(rvec[:, 1]) < redtol, 0.0, rangs)
+    members = [[] for _ in range(len(rvec))]
+    for b, g in enumerate(group):
+        members[g].append(bls[b])
+    if red_bls is not None:
+        order = []
+        for rbl in red_bls:
+            for i, red in enumerate(members):
+                if rbl in red or utils.conjbl(rbl) in red:
+                    order.append(i)
+                    break
+    else:
+        order = np.argsort(rlens + rangs * redtol / 180, kind='stable')
+    reds = [sorted(members[i]) for i in order]
+    redvecs = [torch.as_tensor(rvec[i]) for i in order]
+    redlens = [float(rlens[i]) for i in order]
+    redangs = [float(rangs[i]) for i in order]
+    redtags = ["{:03.0f}_{:03.0f}".format(rlens[i], rangs[i]) for i in order]
+    all_bls = [bl for red in reds for bl in red]
+    bl2red = {}
+    if not skip_reds:
+        for i, red in enumerate(reds):
+            for bl in red:
+                bl2red[bl] = i
+    return reds, redvecs, bl2red, all_bls, redlens, redangs, redtags

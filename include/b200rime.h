@@ -1,0 +1,204 @@
+/*
+ * b200rime.h -- C ABI of the B200-native RIME hot path.
+ *
+ * The reference (BayesLIM) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary these entry points replace is the chain of ATen calls made by
+ *   rime_model.RIME._prod_and_sum            (bayeslim/rime_model.py:391-440)
+ *   telescope_model.ArrayModel.gen_fringe    (bayeslim/telescope_model.py:310-358)
+ *   beam_model.PixelBeam.apply_beam          (bayeslim/beam_model.py:273-372)
+ *   utils.PixInterp.interp                   (bayeslim/utils.py:815-861)
+ *   beam_model.airy_disk                     (bayeslim/beam_model.py:1418-1482)
+ *   beam_model.cut_sky_fov                   (bayeslim/beam_model.py:1681-1698)
+ * and their autograd backward.  Each function below names the reference lines it
+ * stands in for.  INTEGRATION.md shows the ctypes binding a BayesLIM maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; no allocation happens
+ *     inside the library (workspaces are passed in); no torch types cross the boundary
+ *   - `stream` is a cudaStream_t (pass the caller's current stream, 0 = legacy default)
+ *   - all functions return 0 on success; nonzero -> b200rime_last_error() has the text
+ *   - suffix _f32 / _f64 selects the arithmetic of the kernel (complex64 / complex128
+ *     visibilities); geometry (shat, blvecs, freqs) is always float64
+ *   - complex arrays are interleaved (re, im) pairs of the real type
+ *
+ * Data layout ("tiled source layout")
+ *   Sources of all times of a time-group are packed along one axis: time t owns the
+ *   range [toff[t], toff[t+1]) whose length is Ns_t (sources inside the beam FOV at
+ *   that time) rounded up to a multiple of b200rime_src_pad() (=128); padding entries
+ *   carry zero intensity.  S = toff[Nt] is the packed length.  Frequencies are split
+ *   into chunks of KC = b200rime_kc(is_f64) channels (64 for f32, 32 for f64);
+ *   nchunk = ceil(Nf / KC), Nfp = nchunk*KC.
+ *     A     : real  [nchunk][S][KC]   perceived sky  B_p conj(B_q) I  (one real plane)
+ *     shat  : f64   [S][4]            unit vectors (x, y, z, 0), ENU
+ *     blv   : f64   [Nbl][4]          baseline vectors (x, y, z, 0) in metres
+ *     units : int32 [nunits][4]       {time index, s_begin, s_end, 0}; s_* are packed
+ *                                     indices, multiples of 64, inside one time's range
+ *     Vpart : cplx  [nunits][Nbl][Nfp] per-unit partial visibilities
+ *     Gp    : cplx  [Nbl][Nt][Nfp]    cotangent dL/dV, zero padded in frequency
+ */
+#ifndef B200RIME_H
+#define B200RIME_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200rime_stream_t;
+
+/* library identification / diagnostics */
+const char* b200rime_version(void);
+const char* b200rime_last_error(void);
+int b200rime_src_pad(void);
+int b200rime_src_tile(void);
+int b200rime_kc(int is_f64);
+/* host query: fills sm_count, sm_clock_khz (max), compute capability major/minor */
+int b200rime_device_info(int device, int* sm_count, int* clock_khz, int* cc_major, int* cc_minor);
+
+/* ---- fringe sum forward --------------------------------------------------------
+ * Vpart[u][b][f] = sum_{s in unit u} A[f][s] * exp(sgn * 2 pi i (blv[b] . shat[s]) freqs[f] / c)
+ * sgn = +1 (conj == 0, RIME) or -1 (conj != 0, imaging).  Replaces gen_fringe
+ * (telescope_model.py:351-356) + `fringe * psky` + torch.sum (rime_model.py:426-429);
+ * the (Nbl, Nf, Ns) fringe tensor is never formed.  uniform != 0 asserts that freqs is
+ * equally spaced inside every chunk (rotation recurrence); uniform == 0 evaluates every
+ * channel's phase directly.  freqs: f64 [Nf] device. */
+int b200rime_fringe_sum_fwd_f32(const float* A, const double* shat, const double* blv,
+                                const double* freqs, const int* units, int nunits, int nbl,
+                                int nfreq, long long S, int conj, int uniform, float* Vpart,
+                                b200rime_stream_t stream);
+int b200rime_fringe_sum_fwd_f64(const double* A, const double* shat, const double* blv,
+                                const double* freqs, const int* units, int nunits, int nbl,
+                                int nfreq, long long S, int conj, int uniform, double* Vpart,
+                                b200rime_stream_t stream);
+
+/* V[b*sb + t*st + f*sf] (+)= alpha * sum_{u in [ubeg[t], ubeg[t+1])} Vpart[u][b][f]
+ * (fixed order, float64 accumulation -> bitwise reproducible).  Strides in complex
+ * elements; alpha = (alpha_re, alpha_im); accumulate != 0 adds to V.  Stands in for
+ * torch.stack(skyvis, dim=3) (rime_model.py:368). ubeg: int32 [Nt+1] device. */
+int b200rime_reduce_units_f32(const float* Vpart, const int* ubeg, int nt, int nbl, int nfreq,
+                              float* V, long long sb, long long st, long long sf,
+                              double alpha_re, double alpha_im, int accumulate,
+                              b200rime_stream_t stream);
+int b200rime_reduce_units_f64(const double* Vpart, const int* ubeg, int nt, int nbl, int nfreq,
+                              double* V, long long sb, long long st, long long sf,
+                              double alpha_re, double alpha_im, int accumulate,
+                              b200rime_stream_t stream);
+
+/* ---- fringe sum backward to the perceived sky ----------------------------------
+ * dA[f][s] = sum_b Re( conj(F[b][f][s]) * Gp[b][t(s)][f] )   (autograd of rime_model.py:429
+ * w.r.t. psky, for a real plane).  tile_time: int32 [S/128] time index of each 128-source
+ * tile.  Baselines are summed in index order by the thread that owns (s, chunk): no atomics. */
+int b200rime_fringe_sum_bwd_sky_f32(const float* Gp, const double* shat, const double* blv,
+                                    const double* freqs, const int* tile_time, int nbl, int nt,
+                                    int nfreq, long long S, int conj, int uniform, float* dA,
+                                    b200rime_stream_t stream);
+int b200rime_fringe_sum_bwd_sky_f64(const double* Gp, const double* shat, const double* blv,
+                                    const double* freqs, const int* tile_time, int nbl, int nt,
+                                    int nfreq, long long S, int conj, int uniform, double* dA,
+                                    b200rime_stream_t stream);
+
+/* ---- fringe sum backward to the baseline vectors --------------------------------
+ * dblpart[u][chunk][b][0..2] = sum_{s in u} shat[s] * sgn*(2 pi / c) *
+ *                              sum_{f in chunk} freqs[f] A[f][s] Im( conj(F) Gp[b][t][f] )
+ * (autograd of telescope_model.py:356 w.r.t. blvecs); float64 [nunits][nchunk][Nbl][4]. */
+int b200rime_fringe_sum_bwd_bl_f32(const float* Gp, const float* A, const double* shat,
+                                   const double* blv, const double* freqs, const int* units,
+                                   int nunits, int nbl, int nt, int nfreq, long long S, int conj,
+                                   int uniform, double* dblpart, b200rime_stream_t stream);
+int b200rime_fringe_sum_bwd_bl_f64(const double* Gp, const double* A, const double* shat,
+                                   const double* blv, const double* freqs, const int* units,
+                                   int nunits, int nbl, int nt, int nfreq, long long S, int conj,
+                                   int uniform, double* dblpart, b200rime_stream_t stream);
+
+/* ---- layout conversion (generic beam responses) ---------------------------------
+ * pack:   A[chunk][soff + s][k] = X[(chunk*KC + k)*ldx + s]   for s < ns, f < Nf; 0 elsewhere
+ *         over the padded range [soff, soff + ns_pad).
+ * unpack: X[f*ldx + s] = A[...]                                (the adjoint / inverse)
+ * X is a row-major (Nf, ns) real plane, e.g. the perceived sky of beam_model.py:341. */
+int b200rime_pack_f32(const float* X, long long ldx, int nfreq, int ns, int ns_pad,
+                      long long soff, long long S, float* A, b200rime_stream_t stream);
+int b200rime_pack_f64(const double* X, long long ldx, int nfreq, int ns, int ns_pad,
+                      long long soff, long long S, double* A, b200rime_stream_t stream);
+int b200rime_unpack_f32(const float* A, long long ldx, int nfreq, int ns, long long soff,
+                        long long S, float* X, b200rime_stream_t stream);
+int b200rime_unpack_f64(const double* A, long long ldx, int nfreq, int ns, long long soff,
+                        long long S, double* X, b200rime_stream_t stream);
+
+/* ---- fused perceived-sky builders (1-pol power beam) ------------------------------
+ * Interpolated pixel beam (PixInterp.interp utils.py:833-841 + cut_sky_fov beam_model.py:1696
+ * + beam*sky beam_model.py:341):
+ *   A[f][soff+s] = ( sum_{i<nnn} bmap[f*ldb + inds[s][i]] * wgts[s][i] ) * sky[f*lds + cut[s]]
+ * inds int32 [ns][nnn], wgts real [ns][nnn], cut int32 [ns]. */
+int b200rime_build_interp_f32(const float* bmap, long long ldb, const int* inds,
+                              const float* wgts, int nnn, const float* sky, long long lds,
+                              const int* cut, int nfreq, int ns, int ns_pad, long long soff,
+                              long long S, float* A, b200rime_stream_t stream);
+int b200rime_build_interp_f64(const double* bmap, long long ldb, const int* inds,
+                              const double* wgts, int nnn, const double* sky, long long lds,
+                              const int* cut, int nfreq, int ns, int ns_pad, long long soff,
+                              long long S, double* A, b200rime_stream_t stream);
+/* backward of the above given dA: writes
+ *   dsky[f*lds + cut[s]] += B[f][s] * dA[f][s]            (cut indices are unique per time)
+ *   dBI[f*ldd + s]        = sky[f][cut[s]] * dA[f][s]      (row-major (Nf, ns) workspace)
+ * followed by b200rime_interp_transpose_* which gathers dBI into the beam map through the
+ * CSR transpose of (inds, wgts):  dbmap[f*ldb + p] += sum_{j in [rowptr[p], rowptr[p+1])}
+ * val[j] * dBI[f*ldd + col[j]]   -- one owner per (f, p), no atomics. */
+int b200rime_build_interp_bwd_f32(const float* dA, const float* bmap, long long ldb,
+                                  const int* inds, const float* wgts, int nnn, const float* sky,
+                                  long long lds, const int* cut, int nfreq, int ns, long long soff,
+                                  long long S, float* dsky, float* dBI, long long ldd,
+                                  b200rime_stream_t stream);
+int b200rime_build_interp_bwd_f64(const double* dA, const double* bmap, long long ldb,
+                                  const int* inds, const double* wgts, int nnn, const double* sky,
+                                  long long lds, const int* cut, int nfreq, int ns, long long soff,
+                                  long long S, double* dsky, double* dBI, long long ldd,
+                                  b200rime_stream_t stream);
+int b200rime_interp_transpose_f32(const float* dBI, long long ldd, const int* rowptr,
+                                  const int* col, const float* val, int npix, int nfreq,
+                                  float* dbmap, long long ldb, b200rime_stream_t stream);
+int b200rime_interp_transpose_f64(const double* dBI, long long ldd, const int* rowptr,
+                                  const int* col, const double* val, int npix, int nfreq,
+                                  double* dbmap, long long ldb, b200rime_stream_t stream);
+
+/* Airy power/voltage beam (beam_model.py:1464-1480, special.py:535):
+ *   x = max(D(s) * sinzen[s] * pi * freqs[f] * freq_ratio / c, 1e-10),
+ *   D(s) = Dns + sin2az[s] * (Dew - Dns),  B = (2 J1(x)/x)^(square ? 2 : 1)
+ *   A[f][soff+s] = B * sky[f*lds + cut[s]]
+ * sinzen = sin(min(zen, 90 deg)), sin2az = sin(az)^2: real [ns], precomputed per time.
+ * Bout (optional, may be NULL): row-major (Nf, ns) copy of B with row stride ldo. */
+int b200rime_build_airy_f32(double Dew, double Dns, double freq_ratio, int square,
+                            const float* sinzen, const float* sin2az, const double* freqs,
+                            const float* sky, long long lds, const int* cut, int nfreq, int ns,
+                            int ns_pad, long long soff, long long S, float* A, float* Bout,
+                            long long ldo, b200rime_stream_t stream);
+int b200rime_build_airy_f64(double Dew, double Dns, double freq_ratio, int square,
+                            const double* sinzen, const double* sin2az, const double* freqs,
+                            const double* sky, long long lds, const int* cut, int nfreq, int ns,
+                            int ns_pad, long long soff, long long S, double* A, double* Bout,
+                            long long ldo, b200rime_stream_t stream);
+/* backward: dsky[f*lds + cut[s]] += B * dA ; dD[block][0..1] partial sums of
+ * dL/dDew, dL/dDns (float64 [nblocks][2], nblocks = b200rime_airy_bwd_blocks(nfreq, ns)),
+ * summed by the caller in index order.  full_grad != 0 uses the analytic derivative
+ * d(2J1/x)/dx = 2 J0/x - 4 J1/x^2; full_grad == 0 reproduces the reference's autograd,
+ * which treats J1(x) as a constant (torch.special.bessel_j1 has no derivative formula). */
+int b200rime_airy_bwd_blocks(int nfreq, int ns);
+int b200rime_build_airy_bwd_f32(const float* dA, double Dew, double Dns, double freq_ratio,
+                                int square, int full_grad, const float* sinzen,
+                                const float* sin2az, const double* freqs, const float* sky,
+                                long long lds, const int* cut, int nfreq, int ns, long long soff,
+                                long long S, float* dsky, double* dD, b200rime_stream_t stream);
+int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, double freq_ratio,
+                                int square, int full_grad, const double* sinzen,
+                                const double* sin2az, const double* freqs, const double* sky,
+                                long long lds, const int* cut, int nfreq, int ns, long long soff,
+                                long long S, double* dsky, double* dD, b200rime_stream_t stream);
+
+/* ---- on-device peak measurements used as roofline denominators ---------------------
+ * kind: 0 = FP32 FFMA chains, 1 = FP64 DFMA chains, 2 = MUFU sin+cos.  Runs `iters`
+ * dependent-chain iterations on every SM and returns achieved Gop/s (FMA counted as 2 flop;
+ * MUFU as 1 op) in *gops and the kernel time in *ms.  Synchronises the device. */
+int b200rime_microbench(int kind, int iters, double* gops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RIME_H */

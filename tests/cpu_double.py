@@ -1,0 +1,194 @@
+"""
+TEST DOUBLE for libb200rime.so -- host-logic tests only.
+
+The product has no CPU path.  To exercise the *Python orchestration* of
+``bayeslim_b200`` (layouts, unit tables, strides, autograd wiring, minibatching, sharding)
+in the GPU-less build container, ``emulated_kernels()`` temporarily replaces
+``ops._call`` by a torch restatement of each C-ABI entry point's documented contract
+(include/b200rime.h) and lifts the CUDA-device checks.  Nothing here is importable from the
+package; the GPU parity tests (``-m gpu``) never use it.
+"""
+import contextlib
+import math
+
+import numpy as np
+import torch
+
+from bayeslim_b200 import ops, rime_model, _lib
+
+C = 2.99792458e8
+
+
+def _kc(sfx):
+    return _lib.KC[sfx]
+
+
+def _fringe(blv, shat, freqs, conj):
+    u = blv[:, :3].double() @ shat[:, :3].double().T            # (nbl, ns)
+    sgn = -1.0 if conj else 1.0
+    ph = 2 * math.pi * sgn * u[:, None, :] * freqs.double()[None, :, None] / C
+    return torch.complex(torch.cos(ph), torch.sin(ph))           # (nbl, nf, ns)
+
+
+def _A_rows(A, nfreq):
+    """tiled [nchunk][S][KC] -> (nfreq, S)"""
+    nchunk, S, kc = A.shape
+    return A.permute(0, 2, 1).reshape(nchunk * kc, S)[:nfreq]
+
+
+def fringe_sum_fwd(sfx, A, shat, blv, freqs, units, nunits, nbl, nfreq, S, conj, uniform, vpart):
+    Af = _A_rows(A, nfreq).double()
+    for u in range(nunits):
+        _, s0, s1, _ = [int(v) for v in units[u]]
+        F = _fringe(blv[:nbl], shat[s0:s1], freqs[:nfreq], conj)
+        V = (F * Af[None, :, s0:s1]).sum(-1)
+        vpart[u, :, :nfreq, 0] = V.real.to(vpart.dtype)
+        vpart[u, :, :nfreq, 1] = V.imag.to(vpart.dtype)
+        vpart[u, :, nfreq:] = 0
+
+
+def reduce_units(sfx, vpart, ubeg, nt, nbl, nfreq, V, sb, st, sf, are, aim, accumulate):
+    assert sf == 1 and st == nfreq
+    for t in range(nt):
+        u0, u1 = int(ubeg[t]), int(ubeg[t + 1])
+        acc = vpart[u0:u1, :, :nfreq].double().sum(0)
+        r = are * acc[..., 0] - aim * acc[..., 1]
+        i = are * acc[..., 1] + aim * acc[..., 0]
+        if accumulate:
+            r = r + V[:, t, :, 0].double()
+            i = i + V[:, t, :, 1].double()
+        V[:, t, :, 0] = r.to(V.dtype)
+        V[:, t, :, 1] = i.to(V.dtype)
+
+
+def fringe_sum_bwd_sky(sfx, Gp, shat, blv, freqs, tile_time, nbl, nt, nfreq, S, conj, uniform, dA):
+    kc = _kc(sfx)
+    pad = _lib.SRC_PAD
+    G = torch.complex(Gp[..., 0].double(), Gp[..., 1].double())   # (nbl, nt, nfp)
+    out = torch.zeros(dA.shape[0] * kc, S, dtype=torch.float64)
+    for tile in range(S // pad):
+        t = int(tile_time[tile])
+        sl = slice(tile * pad, (tile + 1) * pad)
+        F = _fringe(blv[:nbl], shat[sl], freqs[:nfreq], conj)
+        out[:nfreq, sl] = (F.conj() * G[:, t, :nfreq, None]).real.sum(0)
+    dA.copy_(out.reshape(dA.shape[0], kc, S).permute(0, 2, 1).to(dA.dtype))
+
+
+def fringe_sum_bwd_bl(sfx, Gp, A, shat, blv, freqs, units, nunits, nbl, nt, nfreq, S, conj, uniform,
+                      part):
+    kc = _kc(sfx)
+    Af = _A_rows(A, nfreq).double()
+    G = torch.complex(Gp[..., 0].double(), Gp[..., 1].double())
+    sgn = -1.0 if conj else 1.0
+    part.zero_()
+    nchunk = part.shape[1]
+    for u in range(nunits):
+        t, s0, s1, _ = [int(v) for v in units[u]]
+        F = _fringe(blv[:nbl], shat[s0:s1], freqs[:nfreq], conj)
+        w = (F.conj() * G[:, t, :nfreq, None]).imag * Af[None, :, s0:s1] * freqs.double()[None, :nfreq, None]
+        for c in range(nchunk):
+            du = w[:, c * kc:(c + 1) * kc].sum(1)                  # (nbl, ns)
+            part[u, c, :, :3] = sgn * 2 * math.pi / C * (du @ shat[s0:s1, :3].double())
+
+
+def pack(sfx, X, ldx, nfreq, ns, ns_pad, soff, S, A):
+    kc = _kc(sfx)
+    nchunk = A.shape[0]
+    full = torch.zeros(nchunk * kc, ns_pad, dtype=A.dtype)
+    full[:nfreq, :ns] = X.reshape(nfreq, ldx)[:, :ns]
+    A[:, soff:soff + ns_pad] = full.reshape(nchunk, kc, ns_pad).permute(0, 2, 1)
+
+
+def unpack(sfx, A, ldx, nfreq, ns, soff, S, X):
+    X.reshape(nfreq, ldx)[:, :ns] = _A_rows(A, nfreq)[:, soff:soff + ns]
+
+
+def _interp(bmap, inds, wgts):
+    return (bmap[:, inds.long()] * wgts[None]).sum(-1)            # (nf, ns)
+
+
+def build_interp(sfx, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, ns_pad, soff, S, A):
+    B = _interp(bmap, inds.reshape(ns, nnn), wgts.reshape(ns, nnn))
+    X = B * sky[:, cut.long()]
+    pack(sfx, X.contiguous(), ns, nfreq, ns, ns_pad, soff, S, A)
+
+
+def build_interp_bwd(sfx, dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky,
+                     dBI, ldd):
+    g = _A_rows(dA, nfreq)[:, soff:soff + ns]
+    B = _interp(bmap, inds.reshape(ns, nnn), wgts.reshape(ns, nnn))
+    if dsky is not None:
+        dsky[:, cut.long()] += B * g
+    if dBI is not None:
+        dBI[:, :ns] = sky[:, cut.long()] * g
+
+
+def interp_transpose(sfx, dBI, ldd, rowptr, col, val, npix, nfreq, dbmap, ldb):
+    counts = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(npix), counts)
+    contrib = dBI[:, col.long()] * val[None]
+    dbmap.index_add_(1, rows, contrib.to(dbmap.dtype))
+
+
+def _airy(Dew, Dns, ratio, square, sinzen, sin2az, freqs, nfreq, T):
+    e = sin2az.double() if sin2az is not None else torch.ones_like(sinzen.double())
+    D = Dns + e * (Dew - Dns) if sin2az is not None else torch.full_like(e, Dew)
+    g = sinzen.double()[None] * (math.pi * ratio / C) * freqs.double()[:nfreq, None]
+    xr = D[None] * g
+    x = xr.clamp(min=1e-10).to(T)
+    J1 = torch.special.bessel_j1(x)
+    h = 2 * J1 / x
+    dxdDew = e[None] * g
+    dxdDns = (1 - e)[None] * g if sin2az is not None else torch.zeros_like(g)
+    return xr, x, J1, h, dxdDew, dxdDns
+
+
+def build_airy(sfx, Dew, Dns, ratio, square, sinzen, sin2az, freqs, sky, lds, cut, nfreq, ns,
+               ns_pad, soff, S, A, Bout, ldo):
+    _, x, J1, h, _, _ = _airy(Dew, Dns, ratio, square, sinzen, sin2az, freqs, nfreq, sky.dtype)
+    B = h * h if square else h
+    pack(sfx, (B * sky[:, cut.long()]).contiguous(), ns, nfreq, ns, ns_pad, soff, S, A)
+
+
+def build_airy_bwd(sfx, dA, Dew, Dns, ratio, square, full_grad, sinzen, sin2az, freqs, sky, lds, cut,
+                   nfreq, ns, soff, S, dsky, dD):
+    g = _A_rows(dA, nfreq)[:, soff:soff + ns]
+    xr, x, J1, h, d1, d2 = _airy(Dew, Dns, ratio, square, sinzen, sin2az, freqs, nfreq, sky.dtype)
+    B = h * h if square else h
+    I = sky[:, cut.long()]
+    if dsky is not None:
+        dsky[:, cut.long()] += B * g
+    if dD is not None:
+        hp = (2 * torch.special.bessel_j0(x) / x - 4 * J1 / (x * x)) if full_grad else (-h / x)
+        dBdx = 2 * h * hp if square else hp
+        w = (I * g * dBdx).double() * (xr >= 1e-10)
+        dD.zero_()
+        dD[0, 0] = (w * d1).sum()
+        dD[0, 1] = (w * d2).sum()
+
+
+_TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
+              fringe_sum_bwd_sky=fringe_sum_bwd_sky, fringe_sum_bwd_bl=fringe_sum_bwd_bl,
+              pack=pack, unpack=unpack, build_interp=build_interp,
+              build_interp_bwd=build_interp_bwd, interp_transpose=interp_transpose,
+              build_airy=build_airy, build_airy_bwd=build_airy_bwd)
+
+
+@contextlib.contextmanager
+def emulated_kernels():
+    calls = []
+
+    def fake_call(name, sfx, *args):
+        calls.append(name)
+        with torch.no_grad():
+            _TABLE[name](sfx, *args)
+
+    saved = (ops._call, ops._need_cuda, ops.sm_count, rime_model.RIME._compute_device)
+    ops._call = fake_call
+    ops._need_cuda = lambda *a: None
+    ops.sm_count = lambda dev: 4
+    rime_model.RIME._compute_device = lambda self, sky: torch.device('cpu')
+    try:
+        yield calls
+    finally:
+        ops._call, ops._need_cuda, ops.sm_count, rime_model.RIME._compute_device = saved

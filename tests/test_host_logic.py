@@ -1,0 +1,193 @@
+"""
+Host-side logic of bayeslim_b200 (layouts, work units, strides, autograd wiring, API
+mirror) exercised in the GPU-less container.  The CUDA kernels are replaced by the torch
+TEST DOUBLE of tests/cpu_double.py (contract restatement of include/b200rime.h); the real
+kernels are checked against the same fixtures by tests/test_gpu_parity.py on the B200.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import bayeslim_b200 as ba
+from bayeslim_b200 import ops, _lib
+from tests import model_cases as mc
+from tests.cpu_double import emulated_kernels
+from tests.oracle_cases import load
+
+torch.set_default_dtype(torch.float64)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def relmax(a, b):
+    a = torch.as_tensor(a).detach().cpu()
+    b = torch.as_tensor(b).detach().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200rime.h")).read()
+    names = sorted(set(re.findall(r"\b(b200rime_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert _lib.SRC_PAD == 128 and _lib.SRC_TILE == 64 and _lib.KC == {"f32": 64, "f64": 32}
+    assert "sm_100a" in _lib.version()
+
+
+def test_no_cpu_path():
+    g = load("rime_point_airy")
+    rime, _ = mc.build_point_airy(g, 'cpu')
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rime()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.fringe_sum(torch.zeros(1, 1, 128, 32), torch.zeros(2, 3), None, torch.zeros(4), 4)
+
+
+@pytest.mark.parametrize("name", list(mc.CASES))
+def test_golden_cases_through_host_logic(name):
+    with emulated_kernels() as calls:
+        vd, grads, g, gkeys = mc.run_case(name, 'cpu')
+    assert tuple(vd.data.shape) == g["vis"].shape
+    assert relmax(vd.data, g["vis"]) < 1e-11
+    for k, gk in gkeys.items():
+        assert relmax(grads[k], g[gk]) < 1e-9, (k, gk)
+    assert "fringe_sum_fwd" in calls and "fringe_sum_bwd_sky" in calls
+    if name == "rime_point_airy":
+        assert "build_airy" in calls and "pack" not in calls
+    if name == "rime_pixel_interp":
+        assert "build_interp" in calls and "interp_transpose" in calls and "pack" not in calls
+    if name in ("rime_4pol", "rime_multimodel"):
+        assert "pack" in calls and "unpack" in calls
+
+
+def test_visdata_metadata():
+    g = load("rime_point_airy")
+    with emulated_kernels():
+        rime, _ = mc.build_point_airy(g, 'cpu')
+        vd = rime()
+    assert vd.pol == 'ee' and vd.Npol == 1
+    assert vd.bls == mc.bl_list(g["bls"])
+    assert np.allclose(vd.times.numpy(), g["times"]) and vd.Nfreqs == len(g["freqs"])
+    assert isinstance(vd.history, str) and vd.antpos.ants == [int(a) for a in g["ants"]]
+
+
+def test_minibatching_matches_single_shot():
+    # mirrors reference tests/test_rime.py:29-51
+    g = load("rime_batched")
+    with emulated_kernels():
+        rime, _ = mc.build_pixel_interp(g, 'cpu', params=(), interp_mode='quadratic')
+        with torch.no_grad():
+            vis = rime()
+        assert vis.data.shape == (1, 1, len(g["bls"]), len(g["times"]), len(g["freqs"]))
+        assert relmax(vis.data, g["vis"]) < 1e-9       # quadratic weights: reference pinv noise
+        rime.setup_sim_times(ba.utils.split_into_groups(torch.as_tensor(g["times"]), Nelem=2))
+        assert rime.Nbatch == int(np.ceil(len(g["times"]) / 2))
+        bls = mc.bl_list(g["bls"])
+        rime.setup_sim_bls([bls[:11], bls[11:]])
+        assert rime.Nbatch == 3 * 2
+        with torch.no_grad():
+            batched = rime.run_batches()
+    assert batched.data.shape == vis.data.shape
+    assert (batched.times == vis.times).all() and batched.bls == vis.bls
+    assert (vis.data - batched.data).abs().max() < 1e-10
+
+
+def test_unit_tables_cover_sources_exactly():
+    zen = [torch.rand(n) * 80 for n in (1, 127, 128, 129, 1000, 0)]
+    az = [torch.rand(len(z)) * 360 for z in zen]
+    geom = ops.Geometry(zen, az, 'cpu')
+    assert geom.ns_pad == [128, 128, 128, 256, 1024, 0] and geom.S == sum(geom.ns_pad)
+    assert (geom.shat[:, :3].norm(dim=1)[:1] - 1).abs() < 1e-12
+    for nbl, nchunk, sms in [(3, 1, 4), (700, 4, 148), (61075, 16, 148)]:
+        units, ubeg = geom.units(nbl, nchunk, sms)
+        u = units.numpy()
+        assert (u[:, 1] % 64 == 0).all() and (u[:, 2] % 64 == 0).all()
+        assert ((u[:, 2] - u[:, 1]) <= ops.UNIT_MAX_SRC).all()
+        for t in range(geom.nt):
+            seg = u[ubeg[t]:ubeg[t + 1]]
+            assert (seg[:, 0] == t).all()
+            if len(seg):
+                assert seg[0, 1] == geom.toff[t] and seg[-1, 2] == geom.toff[t + 1]
+                assert (seg[1:, 1] == seg[:-1, 2]).all()
+    # padded sources carry zero weight: shat rows beyond ns are zero
+    assert float(geom.shat[1:128].abs().max()) == 0.0
+
+
+def test_frequency_uniformity_check():
+    f = torch.linspace(100e6, 200e6, 1024, dtype=torch.float64)
+    assert ops.freqs_uniform(f, 1000.0, torch.float32)
+    assert ops.freqs_uniform(f[:1000], 1000.0, torch.float64)
+    f32grid = torch.linspace(100e6, 200e6, 1024, dtype=torch.float32).double()
+    assert not ops.freqs_uniform(f32grid, 1000.0, torch.float32)    # 8 Hz jitter matters at 1 km
+    jitter = f.clone()
+    jitter[10] += 5e3
+    assert not ops.freqs_uniform(jitter, 100.0, torch.float32)
+
+
+def test_module_api_mirror():
+    g = load("rime_point_airy")
+    rime, leaves = mc.build_point_airy(g, 'cpu')
+    assert set(rime.named_params) == {"sky.params", "beam.params", "array.antvecs"}
+    assert rime['sky.params'] is rime.sky.params
+    new = torch.ones_like(rime.sky.params.data)
+    rime.update(ba.ParamDict({'sky.params': new}))
+    assert isinstance(rime.sky.params, torch.nn.Parameter) and (rime.sky.params == 1).all()
+    rime.unset_param('beam.params')
+    assert not isinstance(rime.beam.params, torch.nn.Parameter)
+    rime.set_param('beam.params')
+    assert isinstance(rime.beam.params, torch.nn.Parameter)
+    cache = {}
+    rime.sky.set_priors(priors_inp_params=lambda p: (p ** 2).sum())
+    rime.sky.forward(prior_cache=cache)
+    assert rime.sky.name in cache and float(cache[rime.sky.name]) > 0
+
+
+def test_rect_weights_match_reference_golden():
+    g = load("rect_interp")
+    for mode, tol in [('nearest', 1e-13), ('linear', 1e-12), ('quadratic', 1e-8), ('cubic', 1e-4)]:
+        P = ba.utils.PixInterp('rect', interp_mode=mode, theta_grid=torch.as_tensor(g["theta_grid"]),
+                               phi_grid=torch.as_tensor(g["phi_grid"]))
+        out = P.interp(torch.as_tensor(g["m"]), torch.as_tensor(g["zen"]), torch.as_tensor(g["az"]))
+        assert (out - torch.as_tensor(g["interp_" + mode])).abs().max() < tol
+
+
+def test_healpix_weights_match_oracle_restatement():
+    from oracle import rime_oracle as orc
+    rng = np.random.default_rng(5)
+    th = np.concatenate([np.arccos(rng.uniform(-1, 1, 300)), [1e-4, np.pi - 1e-4, 0.02]])
+    ph = np.concatenate([rng.uniform(0, 2 * np.pi, 300), [0.3, 4.0, 6.2]])
+    for nside in (1, 4, 16):
+        i1, w1 = ba.healpix.get_interp_weights(nside, th, ph)
+        i2, w2 = orc.healpix_interp_weights(nside, th, ph)
+        m = torch.randn(ba.healpix.nside2npix(nside))
+        assert ((m[i1] * w1).sum(1) - (m[i2] * w2).sum(1)).abs().max() < 1e-12
+        t1, p1 = ba.healpix.pix2ang(nside)
+        t2, p2 = orc.healpix_pix2ang(nside)
+        assert np.abs(t1 - t2).max() < 1e-14 and np.abs(p1 - p2).max() < 1e-14
+
+
+def test_build_reds_matches_reference_counts():
+    # tests/test_telescope.py:41-50: 31 redundant groups for hex-19; (0,1) -> [15,0,0]
+    ants, vecs = ba.utils._make_hex(3, D=15)
+    arr = ba.telescope_model.ArrayModel(dict(zip(ants, vecs)), freqs=torch.linspace(1e8, 2e8, 4))
+    assert len(arr.reds) == 31
+    assert torch.allclose(arr.get_blvecs([(0, 1)]), torch.tensor([[15.0, 0, 0]]))
+    assert len(arr.get_bls(uniq_bls=True, keep_autos=False)) == 30
+    fr = arr.gen_fringe(arr.get_blvecs([(0, 1), (0, 5)]), torch.tensor([0.0, 30.0]),
+                        torch.tensor([0.0, 90.0]))
+    assert fr.shape == (2, 4, 2) and (fr[:, :, 0] - 1).abs().max() < 1e-12
+
+
+def test_shard_units_balanced_and_complete():
+    from bayeslim_b200 import parallel
+    w = np.random.default_rng(0).uniform(1, 2, 37)
+    for world in (1, 2, 4, 8):
+        got = [parallel.shard_units(37, r, world, w) for r in range(world)]
+        assert sorted(sum(got, [])) == list(range(37))
+        loads = [w[idx].sum() for idx in got]
+        assert max(loads) - min(loads) <= 2 * w.max() + 1e-9
