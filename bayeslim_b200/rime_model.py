@@ -380,7 +380,10 @@ class RIME(utils.Module):
             for X in per_time:
                 Xm = X[:, :, m].reshape(P * Q, X.shape[-2], X.shape[-1])
                 planes.append(torch.cat([Xm.real, Xm.imag], dim=0) if cplx else Xm)
-            A = ops.pack_planes(rec.geom, [pl.contiguous() for pl in planes])
+            # kernel precision follows the sky tensor (float64 frequency/angle inputs of a
+            # response function must not silently promote a float32 session)
+            rdtype = ops._real(sky.dtype)
+            A = ops.pack_planes(rec.geom, [pl.to(rdtype).contiguous() for pl in planes])
             V = ops.fringe_sum(A, blvecs.index_select(0, sel), rec.geom, f64, nfreq, conj=False,
                                uniform=uniform)
             if cplx:

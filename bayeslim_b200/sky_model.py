@@ -161,7 +161,8 @@ class PixelSky(SkyBase):
     def __init__(self, params, angs, px_area, R=None, name=None, parameter=True, p0=None):
         super().__init__(params, R=R, name=name, parameter=parameter, p0=p0)
         self.angs = angs
-        self.px_area = torch.as_tensor(px_area)
+        # scalars stay Python floats (exact in any session dtype); arrays become tensors
+        self.px_area = px_area if isinstance(px_area, (int, float)) else torch.as_tensor(px_area)
 
     def forward(self, params=None, prior_cache=None, **kwargs):
         sky = self._response(params)

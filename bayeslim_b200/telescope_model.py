@@ -144,9 +144,12 @@ class ArrayModel(utils.Module, utils.AntposDict):
         return self.antvecs.index_select(0, i1) - self.antvecs.index_select(0, i0)
 
     def set_freqs(self, freqs):
+        """Frequencies [Hz] of the fringe.  Kept in float64 whatever the session dtype: they are
+        geometry (the reference casts to _float(), telescope_model.py:301, which in float32
+        sessions jitters a 100-200 MHz grid by +-8 Hz -- 1e-4 rad of phase on a 1 km baseline)."""
         self.freqs = freqs
         if self.freqs is not None:
-            self.freqs = torch.as_tensor(self.freqs, dtype=_float(), device=self.device)
+            self.freqs = torch.as_tensor(self.freqs, device=self.device).to(torch.float64)
 
     def set_freq_index(self, idx=None):
         self._freq_idx = idx

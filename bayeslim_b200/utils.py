@@ -509,14 +509,13 @@ class PixInterp:
         inds = (xi[:, None, :] + nphi * yi[:, :, None]).reshape(len(zen), nx * ny)
         wx, wy = _lagrange_weights(xrel, nx), _lagrange_weights(yrel, ny)
         wgts = (wy[:, :, None] * wx[:, None, :]).reshape(len(zen), nx * ny)
-        return inds, wgts.to(_float())
+        return inds, wgts            # float64; cast to the map dtype at the point of use
 
     def _healpix_weights(self, zen, az):
         from .healpix import get_interp_weights
         theta = torch.as_tensor(zen, dtype=torch.float64) * D2R
         phi = torch.as_tensor(az, dtype=torch.float64) * D2R
-        inds, wgts = get_interp_weights(self.nside, theta, phi)
-        return inds, wgts.to(_float())
+        return get_interp_weights(self.nside, theta, phi)
 
     def get_interp(self, zen, az):
         h = arr_hash(zen)

@@ -1,0 +1,347 @@
+"""
+Parity of the CUDA path (through the C ABI of libb200rime.so) with the CPU oracle and with
+the golden vectors produced by the unmodified reference.
+
+Tolerances (BASELINE.json north star): relative max-norm 1e-5 for the float32/complex64
+kernels -- judged against the FLOAT64 oracle, because the reference's own complex64 path is
+only good to 1e-4 on 300 m baselines -- and 1e-10 for the
+float64/complex128 kernels.
+
+Set B200RIME_TEST_DOUBLE=1 to dry-run this file's logic on a CPU with the torch test double
+of the kernels (tests/cpu_double.py); that mode checks the tests, not the product.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bayeslim_b200 as ba
+from bayeslim_b200 import ops, _lib
+from oracle import rime_oracle as orc
+from tests import model_cases as mc
+from tests import oracle_cases as oc
+import workloads
+
+pytestmark = pytest.mark.gpu
+
+DOUBLE = os.environ.get("B200RIME_TEST_DOUBLE") == "1"
+DEV = 'cpu' if DOUBLE else 'cuda'
+TOL = {torch.float32: 1e-5, torch.float64: 1e-10}
+ERRLOG = {}
+
+
+@pytest.fixture(autouse=True)
+def _kernels():
+    if DOUBLE:
+        from tests.cpu_double import emulated_kernels
+        with emulated_kernels():
+            yield
+    else:
+        assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+        yield
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_errors():
+    yield
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.json"), "w") as f:
+            json.dump(ERRLOG, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def relmax(a, b, tag=None):
+    a = torch.as_tensor(a).detach().cpu()
+    b = torch.as_tensor(b).detach().cpu()
+    e = float((a.to(b.dtype) - b).abs().max() / b.abs().max())
+    if tag:
+        ERRLOG[tag] = e
+    return e
+
+
+def _rand_problem(nbl, nfreq, ns_list, dtype, seed=0, blmax=300.0, fmax=200e6):
+    g = torch.Generator().manual_seed(seed)
+    zen = [torch.rand(n, generator=g, dtype=torch.float64) * 89.0 for n in ns_list]
+    az = [torch.rand(n, generator=g, dtype=torch.float64) * 360.0 for n in ns_list]
+    geom = ops.Geometry([z.to(DEV) for z in zen], [a.to(DEV) for a in az], DEV)
+    blv = (torch.rand(nbl, 3, generator=g, dtype=torch.float64) - 0.5) * 2 * blmax
+    blv[:, 2] *= 0.01
+    if nbl > 2:
+        blv[1] = 0.0                                  # an autocorrelation baseline
+    freqs = torch.linspace(100e6, fmax, nfreq, dtype=torch.float64)
+    planes = [torch.rand(2, nfreq, n, generator=g, dtype=torch.float64) for n in ns_list]
+    return geom, zen, az, blv, freqs, planes
+
+
+def _oracle_fringe_sum(planes, zen, az, blv, freqs, conj=False):
+    out = []
+    for X, z, a in zip(planes, zen, az):
+        F = orc.gen_fringe(blv, z, a, freqs, conj=conj)            # (nbl, nf, ns) complex128
+        out.append(torch.einsum('bfs,pfs->pbf', F, X.to(F.dtype)))
+    return torch.stack(out, dim=2)                                 # (nplane, nbl, nt, nf)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("nbl,nfreq,ns_list,uniform", [
+    (5, 10, [1, 130], True),              # tiny, ragged, Nf < KC
+    (130, 100, [300, 0, 64], True),       # Nbl not a multiple of 128, empty time, Nf % KC != 0
+    (40, 70, [257], False),               # direct per-channel phases
+])
+def test_fringe_sum_forward_backward(dtype, nbl, nfreq, ns_list, uniform):
+    geom, zen, az, blv, freqs, planes = _rand_problem(nbl, nfreq, ns_list, dtype, seed=nbl)
+    if not uniform:
+        freqs = freqs + torch.linspace(0, 1, nfreq, dtype=torch.float64) ** 2 * 3e6
+    f64 = freqs.to(DEV)
+    X = [p.detach().clone().to(device=DEV, dtype=dtype).requires_grad_(True) for p in planes]
+    b = blv.detach().clone().to(DEV).requires_grad_(True)
+    for conj in (False, True):
+        A = ops.pack_planes(geom, X)
+        V = ops.fringe_sum(A, b, geom, f64, nfreq, conj=conj, uniform=uniform)
+        Xo = [p.detach().clone().requires_grad_(True) for p in planes]
+        bo = blv.detach().clone().requires_grad_(True)
+        Vo = _oracle_fringe_sum(Xo, zen, az, bo, freqs, conj=conj)
+        tag = "fringe_sum/%s/nbl%d/conj%d" % (str(dtype)[6:], nbl, conj)
+        assert V.shape == Vo.shape
+        assert relmax(V, Vo, tag + "/V") < TOL[dtype]
+        # zenith-free known answer: the autocorrelation row is the plain source sum
+        if nbl > 2:
+            auto = torch.stack([x.sum(-1) for x in planes], dim=1)      # (nplane, nt, nf)
+            assert relmax(V[:, 1].real, auto) < TOL[dtype]
+        gen = torch.Generator().manual_seed(7)
+        G = torch.complex(torch.randn(Vo.shape, generator=gen, dtype=torch.float64),
+                          torch.randn(Vo.shape, generator=gen, dtype=torch.float64))
+        oc.real_loss(Vo, G).backward()
+        Gd = G.to(device=DEV, dtype=V.dtype)
+        torch.sum(Gd.real * V.real + Gd.imag * V.imag).backward()
+        for t in range(len(ns_list)):
+            if ns_list[t]:
+                assert relmax(X[t].grad, Xo[t].grad, tag + "/dA%d" % t) < TOL[dtype] * 2
+        assert relmax(b.grad, bo.grad, tag + "/dbl") < TOL[dtype] * 2
+        for x in X:
+            x.grad = None
+        b.grad = None
+
+
+def test_forward_is_bitwise_reproducible():
+    geom, zen, az, blv, freqs, planes = _rand_problem(200, 128, [500, 700], torch.float32, seed=3)
+    X = [p.to(device=DEV, dtype=torch.float32) for p in planes]
+    f64 = freqs.to(DEV)
+    outs = []
+    for _ in range(3):
+        A = ops.pack_planes(geom, X)
+        outs.append(ops.fringe_sum(A, blv.to(DEV), geom, f64, 128))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_pack_unpack_roundtrip_exact(dtype):
+    geom, zen, az, blv, freqs, planes = _rand_problem(3, 77, [5, 200, 129], dtype, seed=11)
+    X = [p.detach().clone().to(device=DEV, dtype=dtype).requires_grad_(True) for p in planes]
+    A = ops.pack_planes(geom, X)
+    kc = _lib.KC[ops._sfx(dtype)]
+    assert A.shape == (2, (77 + kc - 1) // kc, geom.S, kc)
+    # padded sources / channels are exactly zero; payload is bit exact
+    rows = A.permute(0, 1, 3, 2).reshape(2, -1, geom.S)
+    for t, n in enumerate(geom.ns):
+        seg = rows[:, :, geom.toff[t]:geom.toff[t + 1]]
+        assert torch.equal(seg[:, :77, :n], X[t].detach())
+        assert float(seg[:, :77, n:].abs().max() if geom.ns_pad[t] > n else 0) == 0
+        assert float(seg[:, 77:].abs().max()) == 0
+    w = torch.rand_like(A)
+    (A * w).sum().backward()
+    wrows = w.permute(0, 1, 3, 2).reshape(2, -1, geom.S)
+    for t, n in enumerate(geom.ns):
+        assert torch.equal(X[t].grad, wrows[:, :77, geom.toff[t]:geom.toff[t] + n])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("name", list(mc.CASES))
+def test_golden_cases(name, dtype):
+    """Every golden fixture of the unmodified reference through the CUDA path."""
+    g = oc.load(name)
+    build, gkeys = mc.CASES[name]
+    rime, leaves = build(g, DEV, dtype)
+    vd = rime()
+    V = vd.data
+    assert tuple(V.shape) == g["vis"].shape
+    assert V.dtype == (torch.complex64 if dtype == torch.float32 else torch.complex128)
+    tag = "golden/%s/%s" % (name, str(dtype)[6:])
+    assert relmax(V, g["vis"], tag + "/V") < TOL[dtype]
+    G = torch.as_tensor(g["G"]).to(device=DEV, dtype=V.dtype)
+    torch.sum(G.real * V.real + G.imag * V.imag).backward()
+    for k, gk in gkeys.items():
+        tol = TOL[dtype] * (5 if dtype == torch.float32 else 10)
+        assert relmax(leaves[k].grad, g[gk], tag + "/" + gk) < tol, (k, gk)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_golden_batched_and_minibatch_invariance(dtype):
+    g = oc.load("rime_batched")
+    rime, _ = mc.build_pixel_interp(g, DEV, dtype, params=(), interp_mode='quadratic')
+    with torch.no_grad():
+        vis = rime()
+        assert relmax(vis.data, g["vis"], "golden/rime_batched/%s/V" % str(dtype)[6:]) < \
+            max(TOL[dtype], 1e-9)
+        rime.setup_sim_times(ba.utils.split_into_groups(torch.as_tensor(g["times"]), Nelem=2))
+        bls = mc.bl_list(g["bls"])
+        rime.setup_sim_bls([bls[:11], bls[11:]])
+        batched = rime.run_batches()
+    assert batched.data.shape == vis.data.shape
+    # same kernels, same per-(baseline, time) summation order -> identical to rounding of the
+    # unit split; reference asserts 1e-10 in float64 (tests/test_rime.py:51)
+    assert relmax(batched.data, vis.data) < (1e-10 if dtype == torch.float64 else 2e-6)
+
+
+def _oracle_of_workload(rime, kind, bl_sel, f_sel, dtype=torch.float64):
+    """fp64 oracle visibilities of a workloads.* model on a subset of baselines / channels."""
+    zenaz = [(za[0].cpu().double(), za[1].cpu().double()) for za in workloads.zenaz_of(rime)]
+    freqs = rime.array.freqs.detach().cpu().double()[f_sel]
+    bls = [rime.sim_bls[i] for i in bl_sel]
+    blvecs = rime.sim_blvecs.detach().cpu().double()[bl_sel]
+    with torch.no_grad():
+        sky = rime.sky.forward().data.detach().cpu().double()[:, :, f_sel]
+        if kind == 'airy':
+            p = rime.beam.params.detach().cpu().double()
+            beam_fn = lambda z, a: orc.airy_response(p, z, a, freqs, powerbeam=True)
+        else:
+            bmap = rime.beam.params.detach().cpu().double().abs()[:, :, :, f_sel]
+            tg, pg = rime.beam.R.theta_grid.cpu(), rime.beam.R.phi_grid.cpu()
+
+            def beam_fn(z, a):
+                inds, wgts = orc.rect_interp_weights(tg, pg, z, a, 'linear')
+                return orc.interp_map(bmap, inds, wgts)
+        return orc.rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=rime.beam.fov,
+                                bl_chunk=16)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_c2_reduced_vs_oracle(dtype):
+    """HERA-37 all cross baselines x 1500 sources x 96 freqs x 3 times, full oracle."""
+    rime = workloads.point_airy(1500, 96, 3, DEV, dtype)
+    vd = rime()
+    V = vd.data
+    Vo = _oracle_of_workload(rime, 'airy', list(range(len(rime.sim_bls))), slice(None))
+    assert relmax(V, Vo, "c2_reduced/%s/V" % str(dtype)[6:]) < TOL[dtype]
+    (V.abs() ** 2).sum().backward()
+    assert torch.isfinite(rime.sky.params.grad).all() and rime.sky.params.grad.abs().max() > 0
+
+
+def test_c2_full_size_properties():
+    """BASELINE config 2 at full size (666 bl x 10^4 src x 256 freqs x 60 times), complex64:
+    size-independent checks + oracle on a baseline/channel subset."""
+    if DOUBLE:
+        pytest.skip("full size needs the GPU")
+    rime = workloads.point_airy(10000, 256, 60, DEV, torch.float32)
+    with torch.no_grad():
+        V = rime().data
+    assert V.shape == (1, 1, 666, 60, 256)
+    evals = workloads.count_evals(rime)
+    assert 3e10 < evals < 1.1e11
+    # oracle on 12 baselines x 16 channels x all sources x 3 of the times
+    bl_sel = list(range(0, 666, 60))
+    f_sel = slice(0, 256, 16)
+    rime_t = workloads.point_airy(10000, 256, 60, DEV, torch.float32)
+    Vo = _oracle_of_workload(rime, 'airy', bl_sel, f_sel)
+    sub = V[:, :, bl_sel][..., f_sel]
+    assert relmax(sub[:, :, :, ::20], Vo[:, :, :, ::20], "c2_full/f32/V_subset") < 1e-5
+    # linearity in the sky: V(2.5 * I) = 2.5 * V(I)
+    with torch.no_grad():
+        rime.sky.params.data[0, 0, 0] *= 2.5
+        V2 = rime().data
+    assert relmax(V2, 2.5 * V) < 2e-6
+    # Hermitian symmetry: swapping the antennas of a baseline conjugates the visibility
+    rime_c = workloads.point_airy(10000, 256, 60, DEV, torch.float32)
+    rime_c.setup_sim_bls([(b[1], b[0]) for b in rime_c.sim_bls[:50]])
+    rime_c.setup_sim_times(rime_c.all_sim_times[:4])
+    with torch.no_grad():
+        Vc = rime_c().data
+    assert relmax(Vc, (V2 / 2.5)[:, :, :50, :4].conj()) < 2e-6
+    del rime_t
+
+
+def test_c3_full_size_subset_and_gradients():
+    """BASELINE config 3 shape at full source/frequency size on a baseline subset that the
+    fp64 oracle can follow: nside-128 PixelSky, rect-interpolated PixelBeam, 1024 freqs."""
+    if DOUBLE:
+        pytest.skip("full size needs the GPU")
+    rime = workloads.pixel_interp(128, 1024, 1, DEV, torch.float32, n_bl=256, antpos_param=True)
+    vd = rime()
+    V = vd.data
+    assert V.shape[2:] == (256, 1, 1024)
+    bl_sel = list(range(0, 256, 32))
+    f_sel = slice(0, 1024, 64)
+    Vo = _oracle_of_workload(rime, 'interp', bl_sel, f_sel)
+    assert relmax(V[:, :, bl_sel][..., f_sel], Vo, "c3_subset/f32/V") < 1e-5
+    (V.abs() ** 2).sum().backward()
+    for p in (rime.sky.params, rime.beam.params, rime.array.antvecs):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0
+    # sources below the horizon at this time receive exactly zero gradient
+    rec = list(rime._geom_cache.values())[0]
+    mask = torch.ones(rime.sky.params.shape[-1], dtype=torch.bool, device=V.device)
+    mask[rec.cuts[0]] = False
+    assert float(rime.sky.params.grad[..., mask].abs().max()) == 0.0
+
+
+def test_gradients_small_c3_vs_oracle_autograd():
+    """Gradients to sky, beam map and antenna positions of a C3-shaped model small enough for
+    the oracle's autograd (nside 8, HERA-37, 48 freqs, 2 times), float32 and float64."""
+    for dtype in (torch.float32, torch.float64):
+        rime = workloads.pixel_interp(8, 48, 2, DEV, dtype, n_bl=60, antpos_param=True,
+                                      layout='hera37', dgrid=5.0)
+        V = rime().data
+        gen = torch.Generator().manual_seed(1)
+        G = torch.complex(torch.randn(V.shape, generator=gen, dtype=torch.float64),
+                          torch.randn(V.shape, generator=gen, dtype=torch.float64))
+        Gd = G.to(device=DEV, dtype=V.dtype)
+        torch.sum(Gd.real * V.real + Gd.imag * V.imag).backward()
+        # oracle
+        zenaz = [(za[0].cpu().double(), za[1].cpu().double()) for za in workloads.zenaz_of(rime)]
+        freqs = rime.array.freqs.detach().cpu().double()
+        antvecs = rime.array.antvecs.detach().cpu().double().requires_grad_(True)
+        sp = rime.sky.params.detach().cpu().double().requires_grad_(True)
+        bp = rime.beam.params.detach().cpu().double().requires_grad_(True)
+        blvecs = orc.get_blvecs(antvecs, rime.array.ants, rime.sim_bls)
+        bmap = orc.pixel_response_forward(bp, powerbeam=True)
+        tg, pg = rime.beam.R.theta_grid.cpu(), rime.beam.R.phi_grid.cpu()
+
+        def beam_fn(z, a):
+            inds, wgts = orc.rect_interp_weights(tg, pg, z, a, 'linear')
+            return orc.interp_map(bmap, inds, wgts)
+
+        Vo = orc.rime_forward(sp * float(rime.sky.px_area), zenaz, beam_fn, rime.sim_bls, blvecs,
+                              freqs, fov=180.0)
+        oc.real_loss(Vo, G).backward()
+        tag = "small_c3/%s" % str(dtype)[6:]
+        tol = TOL[dtype]
+        assert relmax(V, Vo, tag + "/V") < tol
+        assert relmax(rime.sky.params.grad, sp.grad, tag + "/dsky") < 5 * tol
+        assert relmax(rime.beam.params.grad, bp.grad, tag + "/dbeam") < 5 * tol
+        assert relmax(rime.array.antvecs.grad, antvecs.grad, tag + "/dantvecs") < 5 * tol
+
+
+def test_airy_full_gradient_option_matches_finite_difference():
+    """full_grad=True uses d(2J1/x)/dx = 2J0/x - 4J1/x^2 (the reference's autograd drops the
+    J1' term); check against a central finite difference of the CUDA forward in float64."""
+    g = oc.load("rime_point_airy")
+    rime, leaves = mc.build_point_airy(g, DEV, torch.float64)
+    rime.beam.R.full_grad = True
+    G = torch.as_tensor(g["G"]).to(DEV)
+    V = rime().data
+    torch.sum(G.real * V.real + G.imag * V.imag).backward()
+    analytic = float(rime.beam.params.grad.reshape(-1)[0])
+    eps = 1e-5
+    vals = []
+    for s in (+1, -1):
+        with torch.no_grad():
+            rime.beam.params.data += s * eps
+            Vs = rime().data
+            vals.append(float(torch.sum(G.real * Vs.real + G.imag * Vs.imag)))
+            rime.beam.params.data -= s * eps
+    fd = (vals[0] - vals[1]) / (2 * eps)
+    ERRLOG["airy_full_grad/rel_err_vs_fd"] = abs(analytic - fd) / abs(fd)
+    assert abs(analytic - fd) / abs(fd) < 1e-6

@@ -1,0 +1,147 @@
+"""
+Synthetic workloads of BASELINE.json, built with bayeslim_b200's own
+classes exactly as a BayesLIM user would build them with the reference package.  Shared by
+bench.py, __graft_entry__.smoke() and the GPU parity tests.  No dataset is read: antenna
+layouts, skies and beams are generated from fixed seeds.
+
+  C1  HERA-37, 1k point sources (power law), Airy beam, 64 freqs, 10 times
+  C2  HERA-37, 10k point sources, 256 freqs, 60 times, grads to sky
+  C3  HERA-350, HEALPix nside-128 PixelSky, rect-grid interpolated PixelBeam, 1024 freqs,
+      grads to sky, beam (and optionally antenna positions)
+"""
+import itertools
+import math
+
+import numpy as np
+import torch
+
+import bayeslim_b200 as ba
+
+LOCATION = (21.42827, -30.72148, 1051.7)     # reference tests/test_telescope.py:13
+
+
+def hera37():
+    return ba.utils._make_hex(4, D=14.6)
+
+
+def hera350():
+    """Hex core (N=11, 331 antennas) + 19 outriggers at radius 320+12k m, angle 2 pi k/19."""
+    ants, vecs = ba.utils._make_hex(11, D=14.6)
+    k = np.arange(19)
+    r = 320.0 + 12.0 * k
+    ang = 2 * np.pi * k / 19
+    out = np.stack([r * np.cos(ang), r * np.sin(ang), np.zeros(19)], axis=1)
+    vecs = np.concatenate([vecs, out], axis=0)
+    return list(range(len(vecs))), vecs
+
+
+def all_cross_bls(ants):
+    return list(itertools.combinations(ants, 2))
+
+
+def make_array(ants, vecs, freqs, device, antpos_param=False):
+    antpos = ba.utils.AntposDict(ants, torch.as_tensor(vecs, dtype=torch.float64, device=device))
+    array = ba.telescope_model.ArrayModel(antpos, freqs=freqs, device=device, skip_reds=True)
+    if antpos_param:
+        array.set_param('antvecs')
+    return array
+
+
+def point_airy(n_src, n_freq, n_time, device, dtype=torch.float32, bls='all', seed=0,
+               sky_param=True, beam_param=False, antpos_param=False, layout='hera37'):
+    """C1 / C2 family."""
+    rng = np.random.default_rng(seed)
+    freqs = torch.linspace(100e6, 200e6, n_freq, dtype=torch.float64, device=device)
+    ants, vecs = hera37() if layout == 'hera37' else hera350()
+    array = make_array(ants, vecs, freqs, device, antpos_param)
+    if bls == 'all':
+        sim_bls = all_cross_bls(ants)
+    else:
+        full = ba.telescope_model.ArrayModel(dict(zip(ants, vecs)), freqs=freqs)
+        sim_bls = full.get_bls(uniq_bls=True, keep_autos=False)
+    ra = rng.uniform(0, 360, n_src)
+    dec = np.degrees(np.arcsin(rng.uniform(-1, math.sin(math.radians(29)), n_src)))
+    params = np.zeros((1, 1, 2, n_src))
+    params[0, 0, 0] = np.exp(rng.normal(size=n_src))
+    params[0, 0, 1] = rng.normal(-0.8, 0.2, n_src)
+    R = ba.sky_model.PointSkyResponse(freqs.to(dtype), freq_mode='powerlaw', f0=150e6, device=device)
+    sky = ba.sky_model.PointSky(torch.as_tensor(params, dtype=dtype, device=device),
+                                torch.as_tensor(np.stack([ra, dec]), device=device), R=R,
+                                parameter=sky_param)
+    beam = ba.beam_model.PixelBeam(torch.ones(1, 1, 1, 1, 1, dtype=dtype, device=device) * 14.0, freqs,
+                                   R=ba.beam_model.AiryResponse(powerbeam=True), pol='e',
+                                   powerbeam=True, fov=180, parameter=beam_param)
+    tel = ba.telescope_model.TelescopeModel(LOCATION, device=device)
+    times = np.linspace(2458148.15, 2458148.25, n_time)
+    rime = ba.RIME(sky, tel, beam, array, sim_bls, times, freqs, device=device)
+    return rime
+
+
+def healpix_sky_angles(nside, dec_max=59.27852):
+    theta, phi = ba.healpix.pix2ang(nside)
+    dec = np.pi / 2 - theta
+    keep = dec < math.radians(dec_max)
+    return np.degrees(phi[keep]), np.degrees(dec[keep])
+
+
+def rect_airy_map(freqs, dtheta=1.0, dphi=1.0, D=14.0, dtype=torch.float32, device='cpu'):
+    """Airy power beam sampled on a (phi, theta) grid -- construction of reference
+    tests/test_beam.py:13-32."""
+    theta = torch.arange(0, 90.0 + 1e-6, dtheta, dtype=torch.float64, device=device)
+    phi = torch.arange(0, 360.0 - 1e-6, dphi, dtype=torch.float64, device=device)
+    b_phi, b_theta = torch.meshgrid(phi, theta, indexing='xy')
+    airy = ba.beam_model.airy_disk(b_theta.ravel() * ba.D2R, b_phi.ravel() * ba.D2R, D,
+                                   freqs.double(), square=True)
+    return theta, phi, airy.to(dtype)
+
+
+def pixel_interp(nside, n_freq, n_time, device, dtype=torch.float32, n_bl=None, seed=0,
+                 sky_param=True, beam_param=True, antpos_param=False, layout='hera350',
+                 dgrid=1.0):
+    """C3 family."""
+    gen = torch.Generator(device='cpu').manual_seed(seed)
+    freqs = torch.linspace(100e6, 200e6, n_freq, dtype=torch.float64, device=device)
+    ants, vecs = hera350() if layout == 'hera350' else hera37()
+    array = make_array(ants, vecs, freqs, device, antpos_param)
+    sim_bls = all_cross_bls(ants)
+    if n_bl is not None:
+        step = max(1, len(sim_bls) // n_bl)
+        sim_bls = sim_bls[::step][:n_bl]
+    ra, dec = healpix_sky_angles(nside)
+    npix = len(ra)
+    spec = (freqs / 150e6) ** -2.5
+    base = torch.randn(npix, generator=gen).abs()
+    params = (spec[:, None].cpu() * base[None, :]).to(dtype)[None, None].to(device)
+    sky = ba.sky_model.PixelSky(params, torch.as_tensor(np.stack([ra, dec]), device=device),
+                                ba.healpix.nside2pixarea(nside),
+                                R=ba.sky_model.PixelSkyResponse(freqs.to(dtype), device=device),
+                                parameter=sky_param)
+    theta, phi, airy = rect_airy_map(freqs, dgrid, dgrid, 14.0, dtype, device)
+    R = ba.beam_model.PixelResponse(freqs, 'rect', interp_mode='linear', theta_grid=theta,
+                                    phi_grid=phi, freq_mode='channel', powerbeam=True,
+                                    realbeam=True, log=False, device=device)
+    beam = ba.beam_model.PixelBeam(airy[None, None, None].contiguous(), freqs, R=R, pol='e',
+                                   powerbeam=True, fov=180, parameter=beam_param)
+    tel = ba.telescope_model.TelescopeModel(LOCATION, device=device)
+    times = np.linspace(2458148.15, 2458148.25, n_time)
+    rime = ba.RIME(sky, tel, beam, array, sim_bls, times, freqs, device=device)
+    return rime
+
+
+def count_evals(rime):
+    """source x baseline x freq x time evaluations of the current batch, sources counted after
+    the FOV cut.  Requires one forward to have populated the geometry cache."""
+    total = 0
+    for rec in rime._geom_cache.values():
+        total += sum(rec.geom.ns)
+    return total * len(rime.sim_bls) * len(rime.array.freqs)
+
+
+def zenaz_of(rime, sky_name=None):
+    """Per-time (zen, az) [deg] tensors of the current time group, from the telescope cache."""
+    out = []
+    name = sky_name if sky_name is not None else rime.sky.name
+    npix = rime.sky.angs.shape[1] if isinstance(rime.sky.angs, torch.Tensor) else len(rime.sky.angs[0])
+    for t in rime.sim_times:
+        out.append(rime.telescope.conv_cache[(name, npix, t)])
+    return out
