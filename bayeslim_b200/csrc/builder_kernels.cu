@@ -15,12 +15,61 @@ namespace b200rime {
 constexpr int TS = 32;            // sources per builder tile
 constexpr int BUILD_THREADS = 256;
 
-template <typename T> __device__ __forceinline__ T j1_dev(T x);
-template <> __device__ __forceinline__ float j1_dev<float>(float x) { return j1f(x); }
-template <> __device__ __forceinline__ double j1_dev<double>(double x) { return j1(x); }
-template <typename T> __device__ __forceinline__ T j0_dev(T x);
-template <> __device__ __forceinline__ float j0_dev<float>(float x) { return j0f(x); }
-template <> __device__ __forceinline__ double j0_dev<double>(double x) { return j0(x); }
+// ---- Bessel J1 as the reference evaluates it ---------------------------------------------
+// The reference's Airy beam calls torch.special.bessel_j1 (special.py:535).  torch 2.11's
+// kernel (ATen/native/Math.h, bessel_j1_forward) uses the Cephes j1 coefficient sets but
+// evaluates the monic denominators RQ and QQ by plain Horner recursion, without the implied
+// leading 1, so its float64 result differs from the true J1 by up to 4.7e-7 (5 < x < 8).  Parity
+// is with the reference, so this routine restates THAT evaluation (same coefficients, same
+// grouping) in float64 for both kernel precisions.  The optional analytic-derivative path
+// (full_grad) uses CUDA libm's accurate j0().
+__device__ __forceinline__ double horner(const double* c, int n, double z) {
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) r = r * z + c[i];
+    return r;
+}
+__device__ double j1_ref(double x) {
+    const double PP[7] = {7.62125616208173112003e-04, 7.31397056940917570436e-02,
+                          1.12719608129684925192e+00, 5.11207951146807644818e+00,
+                          8.42404590141772420927e+00, 5.21451598682361504063e+00,
+                          1.00000000000000000254e+00};
+    const double PQ[7] = {5.71323128072548699714e-04, 6.88455908754495404082e-02,
+                          1.10514232634061696926e+00, 5.07386386128601488557e+00,
+                          8.39985554327604159757e+00, 5.20982848682361821619e+00,
+                          9.99999999999999997461e-01};
+    const double QP[8] = {5.10862594750176621635e-02, 4.98213872951233449420e+00,
+                          7.58238284132545283818e+01, 3.66779609360150777800e+02,
+                          7.10856304998926107277e+02, 5.97489612400613639965e+02,
+                          2.11688757100572135698e+02, 2.52070205858023719784e+01};
+    const double QQ[7] = {7.42373277035675149943e+01, 1.05644886038262816351e+03,
+                          4.98641058337653607651e+03, 9.56231892404756170795e+03,
+                          7.99704160447350683650e+03, 2.82619278517639096600e+03,
+                          3.36093607810698293419e+02};
+    const double RP[4] = {-8.99971225705559398224e+08, 4.52228297998194034323e+11,
+                          -7.27494245221818276015e+13, 3.68295732863852883286e+15};
+    const double RQ[8] = {6.20836478118054335476e+02, 2.56987256757748830383e+05,
+                          8.35146791431949253037e+07, 2.21511595479792499675e+10,
+                          4.74914122079991414898e+12, 7.84369607876235854894e+14,
+                          8.95222336184627338078e+16, 5.32278620332680085395e+18};
+    const double sgn = x < 0.0 ? -1.0 : 1.0;
+    x = fabs(x);
+    if (x <= 5.0) {
+        const double z = x * x;
+        const double rp = horner(RP, 4, z), rq = horner(RQ, 8, z);
+        return sgn * (rp / rq * x * (z - 1.46819706421238932572e+01) *
+                      (z - 4.92184563216946036703e+01));
+    }
+    const double w = 5.0 / x;
+    const double z = w * w;
+    const double pp = horner(PP, 7, z), pq = horner(PQ, 7, z);
+    const double qp = horner(QP, 8, z), qq = horner(QQ, 7, z);
+    const double xn = x - 2.356194490192344928846982537459627163;
+    double sn, cs;
+    sincos(xn, &sn, &cs);
+    return sgn * ((pp / pq * cs - w * (qp / qq) * sn) * 0.797884560802865355879892119868763737 /
+                  sqrt(x));
+}
 
 // write a [KC][TS+1] smem tile to A[chunk][soff + s0 + srow][k], zero beyond nvalid rows handled
 // by the producer (tile already holds zeros there)
@@ -202,9 +251,9 @@ build_airy_kernel(AiryArgs<T> a, const T* __restrict__ sky, long long lds,
             double d1, d2;
             double x = airy_x<T>(a, s, a.freqs[f], d1, d2);
             x = fmax(x, 1e-10);
-            const T xt = (T)x;
-            T h = (T)2 * j1_dev<T>(xt) / xt;
-            if (a.square) h = h * h;
+            double hd = 2.0 * j1_ref(x) / x;
+            if (a.square) hd = hd * hd;
+            const T h = (T)hd;
             if (Bout) Bout[(size_t)f * ldo + s] = h;
             v = h * sky[(size_t)f * lds + pix];
         }
@@ -238,17 +287,17 @@ build_airy_bwd_kernel(const T* __restrict__ dA, AiryArgs<T> a, int full_grad,
             double d1, d2;
             const double xr = airy_x<T>(a, s, a.freqs[f], d1, d2);
             const bool clipped = xr < 1e-10;
-            const T xt = (T)fmax(xr, 1e-10);
-            const T J1 = j1_dev<T>(xt);
-            const T h = (T)2 * J1 / xt;
-            const T B = a.square ? h * h : h;
+            const double xt = fmax(xr, 1e-10);
+            const double J1 = j1_ref(xt);
+            const double h = 2.0 * J1 / xt;
+            const T B = (T)(a.square ? h * h : h);
             const T I = sky[(size_t)f * lds + pix];
             if (dsky) dsky[(size_t)f * lds + pix] += B * g;
             if (dD && !clipped) {
                 // dh/dx: analytic (full) or with J1 held constant (what reference autograd sees)
-                T hp = full_grad ? ((T)2 * j0_dev<T>(xt) / xt - (T)4 * J1 / (xt * xt)) : (-h / xt);
-                T dBdx = a.square ? (T)2 * h * hp : hp;
-                const double w = (double)(I * g * dBdx);
+                const double hp = full_grad ? (2.0 * j0(xt) / xt - 4.0 * J1 / (xt * xt)) : (-h / xt);
+                const double dBdx = a.square ? 2.0 * h * hp : hp;
+                const double w = (double)I * (double)g * dBdx;
                 gew += w * d1;
                 gns += w * d2;
             }
