@@ -77,8 +77,9 @@ def device_info(device=0):
 
 
 def microbench(kind, iters=4096):
-    """kind: 'fp32' | 'fp64' | 'mufu' -> (Gop/s, ms). FMA counted as 2 flop."""
-    k = {"fp32": 0, "fp64": 1, "mufu": 2}[kind]
+    """kind: 'fp32' | 'fp64' | 'mufu' | 'fp32x2' -> (Gop/s, ms). FMA counted as 2 flop
+    (a packed FFMA2 as 4)."""
+    k = {"fp32": 0, "fp64": 1, "mufu": 2, "fp32x2": 3, "rf3_fp32": 4, "rf3_fp32x2": 5}[kind]
     g, ms = _D(), _D()
     rc = lib.b200rime_microbench(k, iters, ctypes.byref(g), ctypes.byref(ms))
     if rc != 0:

@@ -51,6 +51,75 @@ __global__ void __launch_bounds__(256) peak_dfma_kernel(int iters, double* sink)
     double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (r == 123.456) sink[0] = r;
 }
+__global__ void __launch_bounds__(256) peak_ffma2_kernel(int iters, float* sink) {
+    // packed FP32x2 FMA (SASS FFMA2): 8 independent chains of 64-bit register pairs
+    unsigned long long a[8];
+    const float m = 0.999f, c = 1e-3f;
+    unsigned long long mm, cc;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(mm) : "f"(m));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float x = threadIdx.x * 1e-3f + j;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a[j]) : "f"(x), "f"(x + 0.5f));
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[j]) : "l"(mm), "l"(cc));
+        }
+    }
+    unsigned long long r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r ^= a[j];
+    if (r == 0x123456789ull) sink[0] = 1.f;
+}
+// register-file bandwidth probes: every FMA reads three distinct, non-repeating registers
+__global__ void __launch_bounds__(256) rf3_ffma_kernel(int iters, float* sink) {
+    float acc[16], x[16], y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        acc[j] = threadIdx.x * 1e-3f + j;
+        x[j] = 0.999f + 1e-6f * (threadIdx.x + j);
+        y[j] = 1e-3f * (j + 1);
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[j]) : "f"(x[j]), "f"(y[j]));
+        }
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r += acc[j];
+    if (r == 123.456f) sink[0] = r;
+}
+__global__ void __launch_bounds__(256) rf3_ffma2_kernel(int iters, float* sink) {
+    unsigned long long acc[16], x[16], y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float a = threadIdx.x * 1e-3f + j, b = 0.999f + 1e-6f * (threadIdx.x + j), c = 1e-3f * (j + 1);
+        asm("mov.b64 %0, {%1, %2};" : "=l"(acc[j]) : "f"(a), "f"(a + 0.5f));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x[j]) : "f"(b), "f"(b - 1e-4f));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(y[j]) : "f"(c), "f"(c * 0.5f));
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[j]) : "l"(x[j]), "l"(y[j]));
+        }
+    }
+    unsigned long long r = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r ^= acc[j];
+    if (r == 0x123456789ull) sink[0] = 1.f;
+}
 __global__ void __launch_bounds__(256) peak_mufu_kernel(int iters, float* sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 0.1f, a2 = a0 + 0.2f, a3 = a0 + 0.3f;
     for (int i = 0; i < iters; ++i) {
@@ -102,6 +171,9 @@ int b200rime_microbench(int kind, int iters, double* gops, double* ms) {
         cudaEventRecord(e0);
         if (kind == 0) peak_ffma_kernel<<<blocks, threads>>>(iters, (float*)sink);
         else if (kind == 1) peak_dfma_kernel<<<blocks, threads>>>(iters, (double*)sink);
+        else if (kind == 3) peak_ffma2_kernel<<<blocks, threads>>>(iters, (float*)sink);
+        else if (kind == 4) rf3_ffma_kernel<<<blocks, threads>>>(iters, (float*)sink);
+        else if (kind == 5) rf3_ffma2_kernel<<<blocks, threads>>>(iters, (float*)sink);
         else peak_mufu_kernel<<<blocks, threads>>>(iters, (float*)sink);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
@@ -114,7 +186,8 @@ int b200rime_microbench(int kind, int iters, double* gops, double* ms) {
     cudaEventDestroy(e1);
     cudaFree(sink);
     if (rc) return rc;
-    const double per_thread = (kind == 2) ? 32.0 * iters : 64.0 * iters * 2.0;
+    const double per_thread = (kind == 2) ? 32.0 * iters
+                              : ((kind == 3 || kind == 5) ? 64.0 * iters * 4.0 : 64.0 * iters * 2.0);
     const double total = per_thread * (double)blocks * threads;
     if (ms) *ms = best;
     if (gops) *gops = total / (best * 1e-3) / 1e9;

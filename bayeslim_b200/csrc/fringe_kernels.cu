@@ -10,6 +10,7 @@
 // centre, so the steady state is 4 FP32 ops (rotation) + 2 (multiply-accumulate) per
 // source.baseline.channel with no transcendental.  Every output has exactly one owner thread
 // and a fixed summation order: results are bitwise reproducible.
+#include <type_traits>
 #include "rime_math.cuh"
 #include "internal.h"
 
@@ -91,12 +92,8 @@ fringe_sum_fwd_kernel(const T* __restrict__ A, const double* __restrict__ shat,
     };
     if (tid == 0 && ntiles > 0) issue(0, 0);
 
-    T accr[KC], acci[KC];
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        accr[k] = 0;
-        acci[k] = 0;
-    }
+    FwdTile<T, KC> acc;
+    acc.zero();
 
     for (int it = 0; it < ntiles; ++it) {
         const int stage = it & 1;
@@ -105,22 +102,38 @@ fringe_sum_fwd_kernel(const T* __restrict__ A, const double* __restrict__ shat,
         const T* As = reinterpret_cast<const T*>(smem + stage * SM::STAGE_BYTES);
         const double4* Ss =
             reinterpret_cast<const double4*>(smem + stage * SM::STAGE_BYTES + SM::A_BYTES);
+        if (UNIFORM) {
+            // software pipeline: the seeds of source s+1 (float64 phase reduction + trigonometry,
+            // a long dependent chain that uses no FP32-pipe throughput) are issued inside the
+            // FFMA2 stream of source s, so a warp never leaves the FP32 pipe idle between sources
+            T zr, zi, wr, wi;
+            {
+                const double4 sh = Ss[0];
+                chunk_seed(fma(bx, sh.x, fma(by, sh.y, bz * sh.z)), cf.k_mid, cf.k_step, zr, zi, wr,
+                           wi);
+            }
 #pragma unroll 1
-        for (int s = 0; s < SRC_TILE; ++s) {
-            const double4 sh = Ss[s];
-            const double u = fma(bx, sh.x, fma(by, sh.y, bz * sh.z));
-            if (UNIFORM) {
-                T zr, zi, wr, wi;
-                chunk_seed(u, cf.k_mid, cf.k_step, zr, zi, wr, wi);
-                fwd_accumulate<T, KC>(As + s * KC, zr, zi, wr, wi, accr, acci);
-            } else {
+            for (int s = 0; s < SRC_TILE; ++s) {
+                T nzr, nzi, nwr, nwi;
+                const double4 sh = Ss[(s + 1) & (SRC_TILE - 1)];
+                chunk_seed(fma(bx, sh.x, fma(by, sh.y, bz * sh.z)), cf.k_mid, cf.k_step, nzr, nzi,
+                           nwr, nwi);
+                acc.accumulate(As + s * KC, zr, zi, wr, wi);
+                zr = nzr;
+                zi = nzi;
+                wr = nwr;
+                wi = nwi;
+            }
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < SRC_TILE; ++s) {
+                const double4 sh = Ss[s];
+                const double u = fma(bx, sh.x, fma(by, sh.y, bz * sh.z));
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
                     T zr, zi;
                     channel_cis(u, kf[k], zr, zi);
-                    const T a = As[s * KC + k];
-                    accr[k] += a * zr;
-                    acci[k] += a * zi;
+                    acc.mac(k, As[s * KC + k], zr, zi);
                 }
             }
         }
@@ -133,13 +146,14 @@ fringe_sum_fwd_kernel(const T* __restrict__ A, const double* __restrict__ shat,
         constexpr int NC = N / 2;
 #pragma unroll
         for (int k = 0; k < KC; k += NC) {
+            T r0, i0, r1, i1;
+            acc.get(k, r0, i0);
+            acc.get(k + NC - 1, r1, i1);
             if (NC == 2) {
-                float4 v = make_float4((float)accr[k], (float)acci[k], (float)accr[k + NC - 1],
-                                       (float)acci[k + NC - 1]);
-                *reinterpret_cast<float4*>(out + 2 * k) = v;
+                *reinterpret_cast<float4*>(out + 2 * k) =
+                    make_float4((float)r0, (float)i0, (float)r1, (float)i1);
             } else {
-                double2 v = make_double2((double)accr[k], (double)acci[k]);
-                *reinterpret_cast<double2*>(out + 2 * k) = v;
+                *reinterpret_cast<double2*>(out + 2 * k) = make_double2((double)r0, (double)i0);
             }
         }
     }
@@ -181,7 +195,7 @@ reduce_units_kernel(const T* __restrict__ vpart, const int* __restrict__ ubeg, i
 // K2: backward to the perceived sky.  grid = (S/128, nchunk), block = 128 (thread <-> source)
 // -------------------------------------------------------------------------------------
 template <typename T, bool UNIFORM>
-__global__ void __launch_bounds__(SKY_THREADS, sizeof(T) == 4 ? 4 : 3)
+__global__ void __launch_bounds__(SKY_THREADS, sizeof(T) == 4 ? 3 : 3)
 fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ shat,
                           const double* __restrict__ blv, const double* __restrict__ freqs,
                           const int* __restrict__ tile_time, int nbl, int nt, int nfreq,
@@ -228,9 +242,8 @@ fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ s
     };
     if (tid < 32) issue(0, 0);
 
-    T acc[KC];
-#pragma unroll
-    for (int k = 0; k < KC; ++k) acc[k] = 0;
+    SkyTile<T, KC> acc;
+    acc.zero();
     T* out = dA + ((size_t)chunk * (size_t)S + s) * KC;
     bool first_flush = true;
     constexpr int SEG_TILES = BL_SEGMENT / BL_TILE;
@@ -243,20 +256,36 @@ fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ s
         const double4* Bs =
             reinterpret_cast<const double4*>(smem + stage * SM::STAGE_BYTES + SM::G_BYTES);
         const int rows = min(BL_TILE, nbl - it * BL_TILE);
+        if (UNIFORM) {
+            // seeds of baseline j+1 are issued inside the FFMA2 stream of baseline j (see K1)
+            T zr, zi, wr, wi;
+            {
+                const double4 bv = Bs[0];
+                chunk_seed(fma(bv.x, sx, fma(bv.y, sy, bv.z * sz)), cf.k_mid, cf.k_step, zr, zi, wr,
+                           wi);
+            }
 #pragma unroll 1
-        for (int j = 0; j < rows; ++j) {
-            const double4 bv = Bs[j];
-            const double u = fma(bv.x, sx, fma(bv.y, sy, bv.z * sz));
-            if (UNIFORM) {
-                T zr, zi, wr, wi;
-                chunk_seed(u, cf.k_mid, cf.k_step, zr, zi, wr, wi);
-                sky_accumulate<T, KC>(Gs + j * 2 * KC, zr, zi, wr, wi, acc);
-            } else {
+            for (int j = 0; j < rows; ++j) {
+                T nzr, nzi, nwr, nwi;
+                const double4 bv = Bs[min(j + 1, rows - 1)];
+                chunk_seed(fma(bv.x, sx, fma(bv.y, sy, bv.z * sz)), cf.k_mid, cf.k_step, nzr, nzi,
+                           nwr, nwi);
+                acc.accumulate(Gs + j * 2 * KC, zr, zi, wr, wi);
+                zr = nzr;
+                zi = nzi;
+                wr = nwr;
+                wi = nwi;
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < rows; ++j) {
+                const double4 bv = Bs[j];
+                const double u = fma(bv.x, sx, fma(bv.y, sy, bv.z * sz));
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
                     T zr, zi;
                     channel_cis(u, kf[k], zr, zi);
-                    acc[k] += zr * Gs[j * 2 * KC + 2 * k] + zi * Gs[j * 2 * KC + 2 * k + 1];
+                    acc.mac(k, zr, zi, Gs[j * 2 * KC + 2 * k], Gs[j * 2 * KC + 2 * k + 1]);
                 }
             }
         }
@@ -270,21 +299,20 @@ fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ s
                 if (N == 4) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (!first_flush) v = *reinterpret_cast<float4*>(o);
-                    v.x += (float)acc[k];
-                    v.y += (float)acc[k + 1];
-                    v.z += (float)acc[k + N - 2];
-                    v.w += (float)acc[k + N - 1];
+                    v.x += (float)acc.value(k);
+                    v.y += (float)acc.value(k + 1);
+                    v.z += (float)acc.value(k + N - 2);
+                    v.w += (float)acc.value(k + N - 1);
                     *reinterpret_cast<float4*>(o) = v;
                 } else {
                     double2 v = make_double2(0.0, 0.0);
                     if (!first_flush) v = *reinterpret_cast<double2*>(o);
-                    v.x += (double)acc[k];
-                    v.y += (double)acc[k + 1];
+                    v.x += (double)acc.value(k);
+                    v.y += (double)acc.value(k + 1);
                     *reinterpret_cast<double2*>(o) = v;
                 }
             }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) acc[k] = 0;
+            acc.zero();
             first_flush = false;
         }
     }
@@ -371,28 +399,51 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
         const T* As = reinterpret_cast<const T*>(smem + stage * SM::STAGE_BYTES);
         const double4* Ss =
             reinterpret_cast<const double4*>(smem + stage * SM::STAGE_BYTES + SM::A_BYTES);
+        if (UNIFORM) {
+            T zr, zi, wr, wi;
+            {
+                const double4 sh = Ss[0];
+                chunk_seed(fma(bx, sh.x, fma(by, sh.y, bz * sh.z)), cf.k_mid, cf.k_step, zr, zi, wr,
+                           wi);
+            }
 #pragma unroll 1
-        for (int s = 0; s < SRC_TILE; ++s) {
-            const double4 sh = Ss[s];
-            const double u = fma(bx, sh.x, fma(by, sh.y, bz * sh.z));
-            T du;
-            if (UNIFORM) {
-                T zr, zi, wr, wi;
-                chunk_seed(u, cf.k_mid, cf.k_step, zr, zi, wr, wi);
-                du = bl_accumulate<T, KC>(As + s * KC, zr, zi, wr, wi, gr, gi);
-            } else {
-                du = 0;
+            for (int s = 0; s < SRC_TILE; ++s) {
+                T nzr, nzi, nwr, nwi;
+                const double4 shn = Ss[(s + 1) & (SRC_TILE - 1)];
+                chunk_seed(fma(bx, shn.x, fma(by, shn.y, bz * shn.z)), cf.k_mid, cf.k_step, nzr,
+                           nzi, nwr, nwi);
+                T du;
+                if constexpr (std::is_same<T, float>::value)
+                    du = bl_accumulate_f32<KC>(As + s * KC, zr, zi, wr, wi, gr, gi);
+                else
+                    du = bl_accumulate<T, KC>(As + s * KC, zr, zi, wr, wi, gr, gi);
+                const double4 sh = Ss[s];
+                const double dud = (double)du;
+                dbx = fma(dud, sh.x, dbx);
+                dby = fma(dud, sh.y, dby);
+                dbz = fma(dud, sh.z, dbz);
+                zr = nzr;
+                zi = nzi;
+                wr = nwr;
+                wi = nwi;
+            }
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < SRC_TILE; ++s) {
+                const double4 sh = Ss[s];
+                const double u = fma(bx, sh.x, fma(by, sh.y, bz * sh.z));
+                T du = 0;
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
                     T zr, zi;
                     channel_cis(u, kf[k], zr, zi);
                     du += As[s * KC + k] * (zr * gi[k] - zi * gr[k]);
                 }
+                const double dud = (double)du;
+                dbx = fma(dud, sh.x, dbx);
+                dby = fma(dud, sh.y, dby);
+                dbz = fma(dud, sh.z, dbz);
             }
-            const double dud = (double)du;
-            dbx = fma(dud, sh.x, dbx);
-            dby = fma(dud, sh.y, dby);
-            dbz = fma(dud, sh.z, dbz);
         }
         __syncthreads();
     }

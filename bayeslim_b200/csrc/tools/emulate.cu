@@ -34,19 +34,19 @@ double run(int nfreq, double blmax, int nsrc, int nbl, unsigned seed, double* su
                 std::vector<double> fpad(freqs);
                 ChunkFreq cf = chunk_freq(freqs.data(), nfreq, c, KC, 1.0 / C_LIGHT);
                 alignas(16) T a[KC];
-                T accr[KC], acci[KC];
-                for (int k = 0; k < KC; ++k) {
-                    a[k] = (c * KC + k < nfreq) ? (T)a_amp : (T)0;
-                    accr[k] = acci[k] = 0;
-                }
+                FwdTile<T, KC> acc;
+                acc.zero();
+                for (int k = 0; k < KC; ++k) a[k] = (c * KC + k < nfreq) ? (T)a_amp : (T)0;
                 T zr, zi, wr, wi;
                 chunk_seed(u, cf.k_mid, cf.k_step, zr, zi, wr, wi);
-                fwd_accumulate<T, KC>(a, zr, zi, wr, wi, accr, acci);
+                acc.accumulate(a, zr, zi, wr, wi);
                 for (int k = 0; k < KC && c * KC + k < nfreq; ++k) {
                     int f = c * KC + k;
                     double p = 2 * M_PI * std::fmod(u * freqs[f] / C_LIGHT, 1.0);
                     std::complex<double> e = (double)(T)a_amp * std::complex<double>(std::cos(p), std::sin(p));
-                    std::complex<double> g((double)accr[k], (double)acci[k]);
+                    T gr_, gi_;
+                    acc.get(k, gr_, gi_);
+                    std::complex<double> g((double)gr_, (double)gi_);
                     worst_single = std::max(worst_single, std::abs(g - e) / (double)a_amp);
                     ref[f] += e;
                     got[f] += g;

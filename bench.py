@@ -331,6 +331,7 @@ def main():
     peaks = load_peaks()
     info = _lib.device_info(local)
     fp32_meas, _ = _lib.microbench("fp32", 4096)
+    fp32x2_meas, _ = _lib.microbench("fp32x2", 4096)
     fp64_meas, _ = _lib.microbench("fp64", 1024)
     mufu_meas, _ = _lib.microbench("mufu", 2048)
     fp32_theory = 2 * 128 * info["sm_count"] * (peaks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
@@ -389,7 +390,8 @@ def main():
         gpu_launches=launches,
         roofline=roofline, roofline_other_kernels=others, roofline_hbm=hbm,
         fp32_tflops_algorithmic=evals_total * flops_per_eval(grads) / (ms_step * 1e-3) / 1e12 / world,
-        peaks=dict(fp32_tflops_measured=fp32_meas / 1e3, fp64_tflops_measured=fp64_meas / 1e3,
+        peaks=dict(fp32_tflops_measured=fp32_meas / 1e3, fp32x2_tflops_measured=fp32x2_meas / 1e3,
+                   fp64_tflops_measured=fp64_meas / 1e3,
                    mufu_gops_measured=mufu_meas, fp32_tflops_theoretical=fp32_theory,
                    sm_count=info["sm_count"]),
         kernel_ms_per_step={n: d["ms"] / args.steps for n, d in k.items()},

@@ -193,7 +193,8 @@ int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, double
                                 long long S, double* dsky, double* dD, b200rime_stream_t stream);
 
 /* ---- on-device peak measurements used as roofline denominators ---------------------
- * kind: 0 = FP32 FFMA chains, 1 = FP64 DFMA chains, 2 = MUFU sin+cos.  Runs `iters`
+ * kind: 0 = FP32 FFMA chains, 1 = FP64 DFMA chains, 2 = MUFU sin+cos, 3 = packed FP32x2
+ * FFMA2 chains.  Runs `iters`
  * dependent-chain iterations on every SM and returns achieved Gop/s (FMA counted as 2 flop;
  * MUFU as 1 op) in *gops and the kernel time in *ms.  Synchronises the device. */
 int b200rime_microbench(int kind, int iters, double* gops, double* ms);
