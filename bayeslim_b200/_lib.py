@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200rime.so")
+LIB_PATH = os.environ.get("B200RIME_LIB", os.path.join(_HERE, "csrc", "libb200rime.so"))
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -79,7 +79,9 @@ def device_info(device=0):
 def microbench(kind, iters=4096):
     """kind: 'fp32' | 'fp64' | 'mufu' | 'fp32x2' -> (Gop/s, ms). FMA counted as 2 flop
     (a packed FFMA2 as 4)."""
-    k = {"fp32": 0, "fp64": 1, "mufu": 2, "fp32x2": 3, "rf3_fp32": 4, "rf3_fp32x2": 5}[kind]
+    k = {"fp32": 0, "fp64": 1, "mufu": 2, "fp32x2": 3, "rf3_fp32": 4, "rf3_fp32x2": 5,
+         "mix_rot_mac": 6, "mix_mac": 7, "mix_rot": 8, "rot_4ch": 9, "rot_8ch": 10,
+         "rotmac_4ch": 11, "rotmac_8ch": 12, "rot_1ch": 13}[kind]
     g, ms = _D(), _D()
     rc = lib.b200rime_microbench(k, iters, ctypes.byref(g), ctypes.byref(ms))
     if rc != 0:

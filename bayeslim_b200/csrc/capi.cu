@@ -1,7 +1,7 @@
 // Library identification, error text, device query and the peak-rate microbenchmarks.
 #include <cstdio>
 #include <cstring>
-#include "common.cuh"
+#include "rime_math.cuh"
 #include "internal.h"
 #include "../../include/b200rime.h"
 
@@ -120,6 +120,80 @@ __global__ void __launch_bounds__(256) rf3_ffma2_kernel(int iters, float* sink) 
     for (int j = 0; j < 16; ++j) r ^= acc[j];
     if (r == 0x123456789ull) sink[0] = 1.f;
 }
+// steady-state instruction mix of the float32 fringe kernels, registers only (no seeds, no
+// shared memory): mode 0 = rotation + MAC (the real mix), 1 = MACs with a scalar-broadcast
+// operand only, 2 = rotations (swizzled FMUL2 + FFMA2) only.  64 evaluations per inner pass.
+template <int MODE>
+__global__ void __launch_bounds__(128, 3) mix_kernel(int iters, float* sink) {
+    P2 acc[32];
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = p2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1e-3f * (k + 1) + 1e-6f * threadIdx.x;
+    const float th = 1e-3f * (threadIdx.x + 1);
+    const float wr = cosf(th), wi = sinf(th);
+    const P2 W1 = p2(wr, wr), Wup = p2(-wi, wi), Wdn = p2(wi, -wi);
+    P2 z = p2(1.f, 0.f), y = p2(0.f, 1.f);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+            if (MODE != 2) p2_mac(acc[k], z, p2(a[k & 7], a[k & 7]));
+            if (MODE != 1) z = p2_rot(z, W1, Wup);
+            if (MODE != 2) p2_mac(acc[k + 1], y, p2(a[(k + 1) & 7], a[(k + 1) & 7]));
+            if (MODE != 1) y = p2_rot(y, W1, Wdn);
+        }
+    }
+    float r = 0.f, x0, x1;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        p2_get(acc[k], x0, x1);
+        r += x0 + x1;
+    }
+    p2_get(z, x0, x1);
+    r += x0 + x1;
+    p2_get(y, x0, x1);
+    r += x0 + x1;
+    if (r == 123.456f) sink[0] = r;
+}
+// the same mix with NCH independent rotation chains per thread (latency vs throughput probe)
+template <int NCH, bool MAC>
+__global__ void __launch_bounds__(128, 3) chain_kernel(int iters, float* sink) {
+    P2 acc[32];
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = p2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1e-3f * (k + 1) + 1e-6f * threadIdx.x;
+    const float th = 1e-3f * (threadIdx.x + 1);
+    const float wr = cosf(th), wi = sinf(th);
+    const P2 W1 = p2(wr, wr), Wup = p2(-wi, wi);
+    P2 z[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) z[c] = p2(1.f - 0.01f * c, 0.01f * c);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 32; k += NCH) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (MAC) p2_mac(acc[k + c], z[c], p2(a[(k + c) & 7], a[(k + c) & 7]));
+                z[c] = p2_rot(z[c], W1, Wup);
+            }
+        }
+    }
+    float r = 0.f, x0, x1;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        p2_get(acc[k], x0, x1);
+        r += x0 + x1;
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        p2_get(z[c], x0, x1);
+        r += x0 + x1;
+    }
+    if (r == 123.456f) sink[0] = r;
+}
 __global__ void __launch_bounds__(256) peak_mufu_kernel(int iters, float* sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 0.1f, a2 = a0 + 0.2f, a3 = a0 + 0.3f;
     for (int i = 0; i < iters; ++i) {
@@ -174,6 +248,14 @@ int b200rime_microbench(int kind, int iters, double* gops, double* ms) {
         else if (kind == 3) peak_ffma2_kernel<<<blocks, threads>>>(iters, (float*)sink);
         else if (kind == 4) rf3_ffma_kernel<<<blocks, threads>>>(iters, (float*)sink);
         else if (kind == 5) rf3_ffma2_kernel<<<blocks, threads>>>(iters, (float*)sink);
+        else if (kind == 6) mix_kernel<0><<<sms * 12, 128>>>(iters, (float*)sink);
+        else if (kind == 7) mix_kernel<1><<<sms * 12, 128>>>(iters, (float*)sink);
+        else if (kind == 8) mix_kernel<2><<<sms * 12, 128>>>(iters, (float*)sink);
+        else if (kind == 9) chain_kernel<4, false><<<sms * 12, 128>>>(iters, (float*)sink);
+        else if (kind == 10) chain_kernel<8, false><<<sms * 12, 128>>>(iters, (float*)sink);
+        else if (kind == 11) chain_kernel<4, true><<<sms * 12, 128>>>(iters, (float*)sink);
+        else if (kind == 12) chain_kernel<8, true><<<sms * 12, 128>>>(iters, (float*)sink);
+        else if (kind == 13) chain_kernel<1, false><<<sms * 12, 128>>>(iters, (float*)sink);
         else peak_mufu_kernel<<<blocks, threads>>>(iters, (float*)sink);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
@@ -188,7 +270,12 @@ int b200rime_microbench(int kind, int iters, double* gops, double* ms) {
     if (rc) return rc;
     const double per_thread = (kind == 2) ? 32.0 * iters
                               : ((kind == 3 || kind == 5) ? 64.0 * iters * 4.0 : 64.0 * iters * 2.0);
-    const double total = per_thread * (double)blocks * threads;
+    double total = per_thread * (double)blocks * threads;
+    // mix kernels: 32 evaluations per pass; flop counts 10 (rot+mac), 4 (mac), 6 (rot) per eval
+    if (kind >= 6 && kind <= 8)
+        total = 32.0 * iters * (kind == 6 ? 10.0 : (kind == 7 ? 4.0 : 6.0)) * (double)sms * 12 * 128;
+    if (kind >= 9 && kind <= 13)
+        total = 32.0 * iters * ((kind == 11 || kind == 12) ? 10.0 : 6.0) * (double)sms * 12 * 128;
     if (ms) *ms = best;
     if (gops) *gops = total / (best * 1e-3) / 1e9;
     return 0;

@@ -11,14 +11,20 @@ namespace b200rime {
 constexpr double C_LIGHT = 2.99792458e8;   // reference telescope_model.py:355
 constexpr int SRC_TILE = 64;               // sources per shared-memory stage (fwd, bwd_bl)
 constexpr int SRC_PAD = 128;               // per-time padding of the packed source axis
-constexpr int BL_TILE = 32;                // baselines per shared-memory stage (bwd_sky)
+constexpr int BL_TILE = 64;                // baselines per shared-memory stage (bwd_sky)
 constexpr int FWD_THREADS = 128;           // thread <-> baseline
 constexpr int SKY_THREADS = 128;           // thread <-> source
 constexpr int BL_SEGMENT = 4096;           // baselines per fp32 accumulation segment (bwd_sky)
 
 template <typename T> struct Cfg;
+#ifndef B200_KC_F32
+#define B200_KC_F32 64
+#endif
+#ifndef B200_MINB_F32
+#define B200_MINB_F32 2
+#endif
 template <> struct Cfg<float> {
-    static constexpr int KC = 64;
+    static constexpr int KC = B200_KC_F32;
     typedef float2 cplx;
 };
 template <> struct Cfg<double> {

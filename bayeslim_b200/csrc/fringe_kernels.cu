@@ -43,7 +43,7 @@ template <typename T> struct SkySmem {
 // K1: forward.  grid = (ceil(Nbl/128), nchunk, nunits), block = 128 (thread <-> baseline)
 // -------------------------------------------------------------------------------------
 template <typename T, bool UNIFORM>
-__global__ void __launch_bounds__(FWD_THREADS, sizeof(T) == 4 ? 3 : 2)
+__global__ void __launch_bounds__(FWD_THREADS, sizeof(T) == 4 ? B200_MINB_F32 : 2)
 fringe_sum_fwd_kernel(const T* __restrict__ A, const double* __restrict__ shat,
                       const double* __restrict__ blv, const double* __restrict__ freqs,
                       const int4* __restrict__ units, int nbl, int nfreq, long long S,
@@ -195,7 +195,7 @@ reduce_units_kernel(const T* __restrict__ vpart, const int* __restrict__ ubeg, i
 // K2: backward to the perceived sky.  grid = (S/128, nchunk), block = 128 (thread <-> source)
 // -------------------------------------------------------------------------------------
 template <typename T, bool UNIFORM>
-__global__ void __launch_bounds__(SKY_THREADS, sizeof(T) == 4 ? 3 : 3)
+__global__ void __launch_bounds__(SKY_THREADS, sizeof(T) == 4 ? B200_MINB_F32 : 3)
 fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ shat,
                           const double* __restrict__ blv, const double* __restrict__ freqs,
                           const int* __restrict__ tile_time, int nbl, int nt, int nfreq,
@@ -234,9 +234,9 @@ fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ s
         unsigned char* dst = smem + stage * SM::STAGE_BYTES;
         if (tid == 0) mbar_expect_tx(&bars[stage], rows * (SM::ROW_BYTES + 32));
         __syncwarp();
-        if (tid < rows) {
-            const T* src = Gp + (((size_t)(b0 + tid) * nt + t) * nfp + (size_t)chunk * KC) * 2;
-            bulk_g2s(dst + tid * SM::ROW_BYTES, src, SM::ROW_BYTES, &bars[stage]);
+        for (int r = tid; r < rows; r += 32) {
+            const T* src = Gp + (((size_t)(b0 + r) * nt + t) * nfp + (size_t)chunk * KC) * 2;
+            bulk_g2s(dst + r * SM::ROW_BYTES, src, SM::ROW_BYTES, &bars[stage]);
         }
         if (tid == 0) bulk_g2s(dst + SM::G_BYTES, blv + (size_t)b0 * 4, rows * 32, &bars[stage]);
     };
@@ -326,7 +326,7 @@ fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ s
 // K3: backward to the baseline vectors.  grid/block as K1.
 // -------------------------------------------------------------------------------------
 template <typename T, bool UNIFORM>
-__global__ void __launch_bounds__(FWD_THREADS, sizeof(T) == 4 ? 3 : 2)
+__global__ void __launch_bounds__(FWD_THREADS, sizeof(T) == 4 ? B200_MINB_F32 : 2)
 fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
                          const double* __restrict__ shat, const double* __restrict__ blv,
                          const double* __restrict__ freqs, const int4* __restrict__ units, int nbl,
@@ -347,11 +347,20 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
     const int b = blockIdx.x * FWD_THREADS + tid;
     const bool valid = b < nbl;
     double bx = 0.0, by = 0.0, bz = 0.0;
-    T gr[KC], gi[KC];
+    constexpr bool PACKED = std::is_same<T, float>::value && UNIFORM;
+    // pre-scaled cotangent G'_k = nu_k G_k of this thread's baseline: scalar arrays, or (re, im)
+    // register pairs for the packed Horner form
+    T gr[PACKED ? 1 : KC], gi[PACKED ? 1 : KC];
+    P2 g2[PACKED ? KC : 1];
+    if (PACKED) {
 #pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        gr[k] = 0;
-        gi[k] = 0;
+        for (int k = 0; k < (PACKED ? KC : 1); ++k) g2[k] = p2(0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int k = 0; k < (PACKED ? 1 : KC); ++k) {
+            gr[k] = 0;
+            gi[k] = 0;
+        }
     }
     if (valid) {
         const double* p = blv + 4 * (size_t)b;
@@ -363,8 +372,12 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
         for (int k = 0; k < KC; ++k) {
             const int f = min(chunk * KC + k, nfreq - 1);
             const T nu = (T)freqs[f];
-            gr[k] = g[2 * k] * nu;
-            gi[k] = g[2 * k + 1] * nu;
+            if (PACKED) {
+                g2[PACKED ? k : 0] = p2((float)(g[2 * k] * nu), (float)(g[2 * k + 1] * nu));
+            } else {
+                gr[PACKED ? 0 : k] = g[2 * k] * nu;
+                gi[PACKED ? 0 : k] = g[2 * k + 1] * nu;
+            }
         }
     }
     const ChunkFreq cf = chunk_freq(freqs, nfreq, chunk, KC, sgn_over_c);
@@ -413,8 +426,8 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
                 chunk_seed(fma(bx, shn.x, fma(by, shn.y, bz * shn.z)), cf.k_mid, cf.k_step, nzr,
                            nzi, nwr, nwi);
                 T du;
-                if constexpr (std::is_same<T, float>::value)
-                    du = bl_accumulate_f32<KC>(As + s * KC, zr, zi, wr, wi, gr, gi);
+                if constexpr (PACKED)
+                    du = bl_accumulate_f32<KC>(As + s * KC, zr, zi, wr, wi, g2);
                 else
                     du = bl_accumulate<T, KC>(As + s * KC, zr, zi, wr, wi, gr, gi);
                 const double4 sh = Ss[s];
@@ -472,6 +485,14 @@ int launch_fwd(const T* A, const double* shat, const double* blv, const double* 
     dim3 grid((nbl + FWD_THREADS - 1) / FWD_THREADS, nchunk, nunits);
     const double sgn_over_c = (conj ? -1.0 : 1.0) / C_LIGHT;
     const int smem = FwdSmem<T>::TOTAL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fringe_sum_fwd_kernel<T, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fringe_sum_fwd_kernel<T, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
     if (uniform)
         fringe_sum_fwd_kernel<T, true><<<grid, FWD_THREADS, smem, st>>>(
             A, shat, blv, freqs, reinterpret_cast<const int4*>(units), nbl, nfreq, S, sgn_over_c,
@@ -509,6 +530,14 @@ int launch_bwd_sky(const T* Gp, const double* shat, const double* blv, const dou
     dim3 grid((unsigned)(S / SKY_THREADS), nchunk);
     const double sgn_over_c = (conj ? -1.0 : 1.0) / C_LIGHT;
     const int smem = SkySmem<T>::TOTAL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fringe_sum_bwd_sky_kernel<T, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fringe_sum_bwd_sky_kernel<T, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
     if (uniform)
         fringe_sum_bwd_sky_kernel<T, true><<<grid, SKY_THREADS, smem, st>>>(
             Gp, shat, blv, freqs, tile_time, nbl, nt, nfreq, S, sgn_over_c, dA);
@@ -530,6 +559,14 @@ int launch_bwd_bl(const T* Gp, const T* A, const double* shat, const double* blv
     dim3 grid((nbl + FWD_THREADS - 1) / FWD_THREADS, nchunk, nunits);
     const double sgn_over_c = (conj ? -1.0 : 1.0) / C_LIGHT;
     const int smem = FwdSmem<T>::TOTAL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fringe_sum_bwd_bl_kernel<T, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fringe_sum_bwd_bl_kernel<T, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
     if (uniform)
         fringe_sum_bwd_bl_kernel<T, true><<<grid, FWD_THREADS, smem, st>>>(
             Gp, A, shat, blv, freqs, reinterpret_cast<const int4*>(units), nbl, nt, nfreq, S,

@@ -286,33 +286,49 @@ __host__ __device__ __forceinline__ T bl_accumulate(const T* __restrict__ a, T z
     }
     return du_up + du_dn;
 }
-// float32: packed rotation, scalar (3-op) projection
+// float32: Horner form.  For one (baseline, source) the K3 output is a single scalar,
+//   du = Im( conj(z_mid) * sum_k c_k v^(k-MID) ),  c_k = a_k G'_k,  v = conj(w),
+// i.e. a polynomial in the unit complex v.  Horner evaluation folds the accumulation into the
+// complex multiply, H <- H*v + c_k = FFMA2(swap(H), (-vi, vi), c_k) then FFMA2(H, (vr, vr), .),
+// so an evaluation costs 3 packed ops (c_k: FMUL2 with a scalar-broadcast operand) instead of
+// rotation (2) + projection (3 scalar).  Two chains (channels >= MID in powers of v, channels
+// < MID in powers of conj(v)) keep the amplification of v's angle error at KC/2 steps.
+// g2[k] = (Gr'_k, Gi'_k) register pairs.
 template <int KC>
 __host__ __device__ __forceinline__ float bl_accumulate_f32(const float* __restrict__ a, float zr,
                                                             float zi, float wr, float wi,
-                                                            const float* __restrict__ gr,
-                                                            const float* __restrict__ gi) {
+                                                            const P2* __restrict__ g2) {
     constexpr int MID = KC / 2;
-    const P2 W1 = p2(wr, wr), Wup = p2(-wi, wi), Wdn = p2(wi, -wi);
-    P2 z = p2(zr, zi);
-    P2 y = p2_rot(z, W1, Wdn);
-    float du_up = 0.f, du_dn = 0.f;
+    const P2 V1 = p2(wr, wr);
+    const P2 Vup = p2(wi, -wi);      // multiply by v = conj(w) = (wr, -wi)
+    const P2 Vdn = p2(-wi, wi);      // multiply by conj(v) = w
     const Vec16<float>* av = reinterpret_cast<const Vec16<float>*>(a);
+    P2 Hu = p2(0.f, 0.f), Hd = p2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < MID; j += 4) {
-        Vec16<float> up = av[(MID + j) / 4];
-        Vec16<float> dn = av[(MID - 4 - j) / 4];
+        // up chain walks k = KC-1 ... MID ; down chain walks k = 0 ... MID-1
+        Vec16<float> up = av[(KC - 4 - j) / 4];
+        Vec16<float> dn = av[j / 4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float ar, ai, br, bi;
-            p2_get(z, ar, ai);
-            p2_get(y, br, bi);
-            du_up += up.get(q) * (ar * gi[MID + j + q] - ai * gr[MID + j + q]);
-            z = p2_rot(z, W1, Wup);
-            du_dn += dn.get(3 - q) * (br * gi[MID - 1 - j - q] - bi * gr[MID - 1 - j - q]);
-            y = p2_rot(y, W1, Wdn);
+            const int ku = KC - 1 - j - q;
+            const int kd = j + q;
+            const float au = up.get(3 - q);
+            const float ad = dn.get(q);
+            const P2 cu = p2_mul(g2[ku], p2(au, au));
+            const P2 cd = p2_mul(g2[kd], p2(ad, ad));
+            Hu = p2_fma(Hu, V1, p2_fma(p2_swap(Hu), Vup, cu));   // Hu = Hu*v + c_ku
+            Hd = p2_fma(Hd, V1, p2_fma(p2_swap(Hd), Vdn, cd));   // Hd = Hd*w + c_kd
         }
     }
-    return du_up + du_dn;
+    // Hu = sum_{k>=MID} c_k v^(k-MID);  Hd = sum_{k<MID} c_k w^(MID-1-k)  ->  times w once more
+    Hd = p2_fma(Hd, V1, p2_mul(p2_swap(Hd), Vdn));
+    float sr, si, dr, di;
+    p2_get(Hu, sr, si);
+    p2_get(Hd, dr, di);
+    sr += dr;
+    si += di;
+    return zr * si - zi * sr;        // Im(conj(z_mid) * S)
 }
+
 }  // namespace b200rime

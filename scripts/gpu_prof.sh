@@ -6,7 +6,7 @@ timeout 120 python - > gpurun_out/microbench.json 2> gpurun_out/microbench.err <
 import json
 from bayeslim_b200 import _lib
 out = dict(device=_lib.device_info(0))
-for kind, it in (("fp32", 4096), ("fp32x2", 4096), ("rf3_fp32", 4096), ("rf3_fp32x2", 4096), ("fp64", 1024), ("mufu", 2048)):
+for kind, it in (("fp32", 4096), ("fp32x2", 4096), ("rf3_fp32", 4096), ("rf3_fp32x2", 4096), ("mix_rot_mac", 4096), ("mix_mac", 4096), ("mix_rot", 4096), ("fp64", 1024), ("mufu", 2048)):
     g, ms = _lib.microbench(kind, it)
     out[kind] = dict(gops=g, ms=ms)
 print(json.dumps(out))
