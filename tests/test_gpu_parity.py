@@ -347,3 +347,29 @@ def test_airy_full_gradient_option_matches_finite_difference():
     # the forward uses the reference's (torch) J1, which is itself only good to ~5e-7, so its
     # numerical derivative and the analytic Bessel derivative agree to that level, not better
     assert abs(analytic - fd) / abs(fd) < 2e-5
+
+
+def test_integration_md_stub_runs():
+    """The ctypes stub printed in INTEGRATION.md (what a BayesLIM maintainer would paste into
+    rime_model.py) must run as written against the built library."""
+    if DOUBLE:
+        pytest.skip("calls the real library")
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S)
+             if "def b200_prod_and_sum" in b][0]
+    block = block.replace('"libb200rime.so"', repr(_lib.LIB_PATH))
+    ns = {}
+    exec(block, ns)
+    g = torch.Generator().manual_seed(4)
+    Nf, Ns, Nbl = 70, 300, 9
+    X = torch.rand(Nf, Ns, generator=g)
+    zen = torch.rand(Ns, generator=g, dtype=torch.float64) * 89
+    az = torch.rand(Ns, generator=g, dtype=torch.float64) * 360
+    blv = (torch.rand(Nbl, 3, generator=g, dtype=torch.float64) - 0.5) * 300
+    freqs = torch.linspace(100e6, 200e6, Nf, dtype=torch.float64)
+    V = ns["b200_prod_and_sum"](X.cuda(), zen.cuda(), az.cuda(), blv.cuda(), freqs.cuda())
+    F = orc.gen_fringe(blv, zen, az, freqs)
+    Vo = torch.einsum('bfs,fs->bf', F, X.to(F.dtype))
+    assert relmax(V, Vo, "integration_stub/V") < 1e-5
