@@ -364,7 +364,7 @@ def test_integration_md_stub_runs():
     exec(block, ns)
     g = torch.Generator().manual_seed(4)
     Nf, Ns, Nbl = 70, 300, 9
-    X = torch.rand(Nf, Ns, generator=g)
+    X = torch.rand(Nf, Ns, generator=g, dtype=torch.float32)   # session default may be float64
     zen = torch.rand(Ns, generator=g, dtype=torch.float64) * 89
     az = torch.rand(Ns, generator=g, dtype=torch.float64) * 360
     blv = (torch.rand(Nbl, 3, generator=g, dtype=torch.float64) - 0.5) * 300
