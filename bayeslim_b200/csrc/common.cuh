@@ -23,6 +23,9 @@ template <typename T> struct Cfg;
 #ifndef B200_MINB_F32
 #define B200_MINB_F32 2
 #endif
+#ifndef B200_MINB_SKY_F32
+#define B200_MINB_SKY_F32 3
+#endif
 template <> struct Cfg<float> {
     static constexpr int KC = B200_KC_F32;
     typedef float2 cplx;

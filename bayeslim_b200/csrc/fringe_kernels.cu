@@ -195,7 +195,7 @@ reduce_units_kernel(const T* __restrict__ vpart, const int* __restrict__ ubeg, i
 // K2: backward to the perceived sky.  grid = (S/128, nchunk), block = 128 (thread <-> source)
 // -------------------------------------------------------------------------------------
 template <typename T, bool UNIFORM>
-__global__ void __launch_bounds__(SKY_THREADS, sizeof(T) == 4 ? B200_MINB_F32 : 3)
+__global__ void __launch_bounds__(SKY_THREADS, sizeof(T) == 4 ? B200_MINB_SKY_F32 : 3)
 fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ shat,
                           const double* __restrict__ blv, const double* __restrict__ freqs,
                           const int* __restrict__ tile_time, int nbl, int nt, int nfreq,
@@ -227,20 +227,17 @@ fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ s
     __syncthreads();
 
     const int ntiles = (nbl + BL_TILE - 1) / BL_TILE;
-    // executed by all 32 lanes of warp 0: one bulk copy per cotangent row + one for the vectors
+    // the cotangent is laid out [t][chunk][baseline][KC]: a tile of rows is one contiguous block
     auto issue = [&](int tile, int stage) {
         const int b0 = tile * BL_TILE;
         const int rows = min(BL_TILE, nbl - b0);
         unsigned char* dst = smem + stage * SM::STAGE_BYTES;
-        if (tid == 0) mbar_expect_tx(&bars[stage], rows * (SM::ROW_BYTES + 32));
-        __syncwarp();
-        for (int r = tid; r < rows; r += 32) {
-            const T* src = Gp + (((size_t)(b0 + r) * nt + t) * nfp + (size_t)chunk * KC) * 2;
-            bulk_g2s(dst + r * SM::ROW_BYTES, src, SM::ROW_BYTES, &bars[stage]);
-        }
-        if (tid == 0) bulk_g2s(dst + SM::G_BYTES, blv + (size_t)b0 * 4, rows * 32, &bars[stage]);
+        mbar_expect_tx(&bars[stage], rows * (SM::ROW_BYTES + 32));
+        const T* src = Gp + ((((size_t)t * gridDim.y + chunk) * nbl + b0) * KC) * 2;
+        bulk_g2s(dst, src, rows * SM::ROW_BYTES, &bars[stage]);
+        bulk_g2s(dst + SM::G_BYTES, blv + (size_t)b0 * 4, rows * 32, &bars[stage]);
     };
-    if (tid < 32) issue(0, 0);
+    if (tid == 0) issue(0, 0);
 
     SkyTile<T, KC> acc;
     acc.zero();
@@ -250,7 +247,7 @@ fringe_sum_bwd_sky_kernel(const T* __restrict__ Gp, const double* __restrict__ s
 
     for (int it = 0; it < ntiles; ++it) {
         const int stage = it & 1;
-        if (tid < 32 && it + 1 < ntiles) issue(it + 1, stage ^ 1);
+        if (tid == 0 && it + 1 < ntiles) issue(it + 1, stage ^ 1);
         mbar_wait(&bars[stage], (it >> 1) & 1);
         const T* Gs = reinterpret_cast<const T*>(smem + stage * SM::STAGE_BYTES);
         const double4* Bs =
@@ -367,7 +364,7 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
         bx = p[0];
         by = p[1];
         bz = p[2];
-        const T* g = Gp + (((size_t)b * nt + un.x) * nfp + (size_t)chunk * KC) * 2;
+        const T* g = Gp + ((((size_t)un.x * nchunk + chunk) * nbl + b) * KC) * 2;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             const int f = min(chunk * KC + k, nfreq - 1);

@@ -218,19 +218,15 @@ template <typename T, int KC> struct SkyTile {
         }
     }
 };
-template <int KC> struct SkyTile<float, KC> {           // pair accumulators (sum zr*Gr, sum zi*Gi)
-    P2 v[KC];
+template <int KC> struct SkyTile<float, KC> {   // packed rotation, scalar real accumulators
+    float acc[KC];
     __host__ __device__ __forceinline__ void zero() {
 #pragma unroll
-        for (int k = 0; k < KC; ++k) v[k] = p2(0.f, 0.f);
+        for (int k = 0; k < KC; ++k) acc[k] = 0.f;
     }
-    __host__ __device__ __forceinline__ float value(int k) const {
-        float x, y;
-        p2_get(v[k], x, y);
-        return x + y;
-    }
+    __host__ __device__ __forceinline__ float value(int k) const { return acc[k]; }
     __host__ __device__ __forceinline__ void mac(int k, float zr, float zi, float gr, float gi) {
-        v[k] = p2_fma(p2(zr, zi), p2(gr, gi), v[k]);
+        acc[k] = fmaf(zi, gi, fmaf(zr, gr, acc[k]));
     }
     __host__ __device__ __forceinline__ void accumulate(const float* __restrict__ g, float zr,
                                                         float zi, float wr, float wi) {
@@ -245,11 +241,12 @@ template <int KC> struct SkyTile<float, KC> {           // pair accumulators (su
             Vec16<float> dn = gv[(MID - 2 - j) / 2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const P2 gu = p2(up.get(2 * q), up.get(2 * q + 1));
-                const P2 gd = p2(dn.get(2 * (1 - q)), dn.get(2 * (1 - q) + 1));
-                p2_mac(v[MID + j + q], z, gu);
+                float ar, ai, br, bi;
+                p2_get(z, ar, ai);
+                p2_get(y, br, bi);
+                mac(MID + j + q, ar, ai, up.get(2 * q), up.get(2 * q + 1));
                 z = p2_rot(z, W1, Wup);
-                p2_mac(v[MID - 1 - j - q], y, gd);
+                mac(MID - 1 - j - q, br, bi, dn.get(2 * (1 - q)), dn.get(2 * (1 - q) + 1));
                 y = p2_rot(y, W1, Wdn);
             }
         }

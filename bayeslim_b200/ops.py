@@ -31,6 +31,8 @@ VPART_BUDGET = 6 << 30
 # longest run of sources accumulated in float32 registers before a float64 reduction
 UNIT_MAX_SRC = 8192
 UNIT_MIN_SRC = 256
+# grid.z limit of a launch (units per launch)
+MAX_GRID_UNITS = 32768
 
 
 def _sfx(dtype):
@@ -383,7 +385,7 @@ class _FringeSum(torch.autograd.Function):
             units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
             esize = 8 if sfx == "f32" else 16
             per_unit = nbl * nfp * esize
-            max_units = max(1, VPART_BUDGET // per_unit)
+            max_units = min(max(1, VPART_BUDGET // per_unit), MAX_GRID_UNITS)
             # sub-batches of whole times whose unit partials fit the workspace budget
             t0 = 0
             batches = []
@@ -425,20 +427,28 @@ class _FringeSum(torch.autograd.Function):
         dbl = torch.zeros(nbl, 3, dtype=torch.float64, device=dev) if need_bl else None
         if nbl > 0 and nt > 0 and geom.S > 0:
             Gr = torch.view_as_real(G.contiguous())
-            Gp = torch.zeros(nbl, nt, nfp, 2, dtype=rdtype, device=dev)
+            # cotangent in kernel layout [t][chunk][baseline][KC] (zero padded in frequency): a
+            # tile of baselines is one contiguous block for the TMA engine
+            Gp = torch.zeros(nt, nchunk, nbl, kc, 2, dtype=rdtype, device=dev)
+            Gv = Gp.permute(2, 0, 1, 3, 4)                     # (nbl, nt, nchunk, kc, 2) view
+            pad = nfp - nfreq
             for p in range(nplane):
-                Gp[:, :, :nfreq] = Gr[p]
+                src = Gr[p] if pad == 0 else torch.nn.functional.pad(Gr[p], (0, 0, 0, pad))
+                Gv.copy_(src.reshape(nbl, nt, nchunk, kc, 2))
                 if need_A:
                     _call("fringe_sum_bwd_sky", sfx, Gp, geom.shat, blv, freqs64,
                           geom.tile_time, nbl, nt, nfreq, geom.S, conj, uniform, dA[p])
                 if need_bl:
                     units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
-                    nun = units.shape[0]
-                    part = torch.empty(nun, nchunk, nbl, 4, dtype=torch.float64, device=dev)
-                    _call("fringe_sum_bwd_bl", sfx, Gp, A[p], geom.shat, blv,
-                          freqs64, units, nun, nbl, nt, nfreq, geom.S, conj, uniform,
-                          part)
-                    dbl = dbl + part.sum(dim=(0, 1))[:, :3]
+                    per_unit = nchunk * nbl * 32
+                    step = min(max(1, (VPART_BUDGET // 4) // per_unit), MAX_GRID_UNITS)
+                    for u0 in range(0, units.shape[0], step):
+                        nun = min(step, units.shape[0] - u0)
+                        part = torch.empty(nun, nchunk, nbl, 4, dtype=torch.float64, device=dev)
+                        _call("fringe_sum_bwd_bl", sfx, Gp, A[p], geom.shat, blv,
+                              freqs64, units[u0:], nun, nbl, nt, nfreq, geom.S, conj, uniform,
+                              part)
+                        dbl = dbl + part.sum(dim=(0, 1))[:, :3]
         gbl = dbl.to(device=bdev, dtype=bdtype) if need_bl else None
         return dA, gbl, None, None, None, None, None
 

@@ -34,7 +34,7 @@
  *     units : int32 [nunits][4]       {time index, s_begin, s_end, 0}; s_* are packed
  *                                     indices, multiples of 64, inside one time's range
  *     Vpart : cplx  [nunits][Nbl][Nfp] per-unit partial visibilities
- *     Gp    : cplx  [Nbl][Nt][Nfp]    cotangent dL/dV, zero padded in frequency
+ *     Gp    : cplx  [Nt][nchunk][Nbl][KC]  cotangent dL/dV, zero padded in frequency
  */
 #ifndef B200RIME_H
 #define B200RIME_H
@@ -84,7 +84,7 @@ int b200rime_reduce_units_f64(const double* Vpart, const int* ubeg, int nt, int 
                               b200rime_stream_t stream);
 
 /* ---- fringe sum backward to the perceived sky ----------------------------------
- * dA[f][s] = sum_b Re( conj(F[b][f][s]) * Gp[b][t(s)][f] )   (autograd of rime_model.py:429
+ * dA[f][s] = sum_b Re( conj(F[b][f][s]) * Gp[t(s)][f][b] )   (autograd of rime_model.py:429
  * w.r.t. psky, for a real plane).  tile_time: int32 [S/128] time index of each 128-source
  * tile.  Baselines are summed in index order by the thread that owns (s, chunk): no atomics. */
 int b200rime_fringe_sum_bwd_sky_f32(const float* Gp, const double* shat, const double* blv,
@@ -98,7 +98,7 @@ int b200rime_fringe_sum_bwd_sky_f64(const double* Gp, const double* shat, const 
 
 /* ---- fringe sum backward to the baseline vectors --------------------------------
  * dblpart[u][chunk][b][0..2] = sum_{s in u} shat[s] * sgn*(2 pi / c) *
- *                              sum_{f in chunk} freqs[f] A[f][s] Im( conj(F) Gp[b][t][f] )
+ *                              sum_{f in chunk} freqs[f] A[f][s] Im( conj(F) Gp[t][f][b] )
  * (autograd of telescope_model.py:356 w.r.t. blvecs); float64 [nunits][nchunk][Nbl][4]. */
 int b200rime_fringe_sum_bwd_bl_f32(const float* Gp, const float* A, const double* shat,
                                    const double* blv, const double* freqs, const int* units,

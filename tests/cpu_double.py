@@ -36,6 +36,13 @@ def _A_rows(A, nfreq):
     return A.permute(0, 2, 1).reshape(nchunk * kc, S)[:nfreq]
 
 
+def _G_rows(Gp):
+    """kernel layout [nt][nchunk][nbl][kc][2] -> complex (nbl, nt, nfp)"""
+    nt, nchunk, nbl, kc, _ = Gp.shape
+    g = Gp.permute(2, 0, 1, 3, 4).reshape(nbl, nt, nchunk * kc, 2).double()
+    return torch.complex(g[..., 0], g[..., 1])
+
+
 def fringe_sum_fwd(sfx, A, shat, blv, freqs, units, nunits, nbl, nfreq, S, conj, uniform, vpart):
     Af = _A_rows(A, nfreq).double()
     for u in range(nunits):
@@ -64,7 +71,7 @@ def reduce_units(sfx, vpart, ubeg, nt, nbl, nfreq, V, sb, st, sf, are, aim, accu
 def fringe_sum_bwd_sky(sfx, Gp, shat, blv, freqs, tile_time, nbl, nt, nfreq, S, conj, uniform, dA):
     kc = _kc(sfx)
     pad = _lib.SRC_PAD
-    G = torch.complex(Gp[..., 0].double(), Gp[..., 1].double())   # (nbl, nt, nfp)
+    G = _G_rows(Gp)                                               # (nbl, nt, nfp)
     out = torch.zeros(dA.shape[0] * kc, S, dtype=torch.float64)
     for tile in range(S // pad):
         t = int(tile_time[tile])
@@ -78,7 +85,7 @@ def fringe_sum_bwd_bl(sfx, Gp, A, shat, blv, freqs, units, nunits, nbl, nt, nfre
                       part):
     kc = _kc(sfx)
     Af = _A_rows(A, nfreq).double()
-    G = torch.complex(Gp[..., 0].double(), Gp[..., 1].double())
+    G = _G_rows(Gp)
     sgn = -1.0 if conj else 1.0
     part.zero_()
     nchunk = part.shape[1]
