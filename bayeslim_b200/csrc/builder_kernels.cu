@@ -140,33 +140,66 @@ __device__ __forceinline__ T interp_at(const T* __restrict__ brow, const int* __
     return b;
 }
 
-template <typename T>
+// Neighbour tables of one source held in registers (NNN = 1 or 4: nearest / bilinear, the
+// common cases) or re-read through L1 (NNN = 0: any count, e.g. 9 / 16 for bi-quadratic / cubic).
+template <typename T, int NNN> struct Nbr {
+    int idx[NNN];
+    T w[NNN];
+    __device__ __forceinline__ void load(const int* __restrict__ inds, const T* __restrict__ wgts,
+                                         int nnn, int s) {
+#pragma unroll
+        for (int i = 0; i < NNN; ++i) {
+            idx[i] = inds[(size_t)s * NNN + i];
+            w[i] = wgts[(size_t)s * NNN + i];
+        }
+    }
+    __device__ __forceinline__ T at(const T* __restrict__ brow, const int*, const T*, int, int) const {
+        T b = 0;
+#pragma unroll
+        for (int i = 0; i < NNN; ++i) b += brow[idx[i]] * w[i];
+        return b;
+    }
+};
+template <typename T> struct Nbr<T, 0> {
+    __device__ __forceinline__ void load(const int*, const T*, int, int) {}
+    __device__ __forceinline__ T at(const T* __restrict__ brow, const int* __restrict__ inds,
+                                    const T* __restrict__ wgts, int nnn, int s) const {
+        return interp_at<T>(brow, inds, wgts, nnn, s);
+    }
+};
+
+template <typename T, int NNN>
 __global__ void __launch_bounds__(BUILD_THREADS)
 build_interp_kernel(const T* __restrict__ bmap, long long ldb, const int* __restrict__ inds,
                     const T* __restrict__ wgts, int nnn, const T* __restrict__ sky, long long lds,
                     const int* __restrict__ cut, int nfreq, int ns, long long soff, long long S,
                     T* __restrict__ A) {
     constexpr int KC = Cfg<T>::KC;
+    constexpr int ROWS = BUILD_THREADS / 32;
     __shared__ T tile[KC][TS + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int chunk = blockIdx.y;
     const int s = blockIdx.x * TS + tx;
     const bool live = s < ns;
     const int pix = live ? cut[s] : 0;
-    for (int k = ty; k < KC; k += BUILD_THREADS / 32) {
-        const int f = chunk * KC + k;
-        T v = 0;
-        if (live && f < nfreq) {
-            const T b = interp_at<T>(bmap + (size_t)f * ldb, inds, wgts, nnn, s);
-            v = b * sky[(size_t)f * lds + pix];
-        }
-        tile[k][tx] = v;
+    Nbr<T, NNN> nb;
+    if (live) nb.load(inds, wgts, nnn, s);
+    // all gathers of this thread's KC/ROWS channels are issued before they are consumed
+    T v[KC / ROWS];
+#pragma unroll
+    for (int i = 0; i < KC / ROWS; ++i) {
+        const int f = chunk * KC + ty + i * ROWS;
+        v[i] = 0;
+        if (live && f < nfreq)
+            v[i] = nb.at(bmap + (size_t)f * ldb, inds, wgts, nnn, s) * sky[(size_t)f * lds + pix];
     }
+#pragma unroll
+    for (int i = 0; i < KC / ROWS; ++i) tile[ty + i * ROWS][tx] = v[i];
     __syncthreads();
     store_tile<T, KC>(tile, A, S, soff + (long long)blockIdx.x * TS, chunk, TS);
 }
 
-template <typename T>
+template <typename T, int NNN>
 __global__ void __launch_bounds__(BUILD_THREADS)
 build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, long long ldb,
                         const int* __restrict__ inds, const T* __restrict__ wgts, int nnn,
@@ -174,6 +207,7 @@ build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, lo
                         int nfreq, int ns, long long soff, long long S, T* __restrict__ dsky,
                         T* __restrict__ dBI, long long ldd) {
     constexpr int KC = Cfg<T>::KC;
+    constexpr int ROWS = BUILD_THREADS / 32;
     __shared__ T tile[KC][TS + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int chunk = blockIdx.y;
@@ -182,14 +216,27 @@ build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, lo
     const int s = blockIdx.x * TS + tx;
     if (s >= ns) return;
     const int pix = cut[s];
-    for (int k = ty; k < KC; k += BUILD_THREADS / 32) {
+    Nbr<T, NNN> nb;
+    nb.load(inds, wgts, nnn, s);
+    T b[KC / ROWS], I[KC / ROWS];
+#pragma unroll
+    for (int i = 0; i < KC / ROWS; ++i) {
+        const int f = chunk * KC + ty + i * ROWS;
+        b[i] = 0;
+        I[i] = 0;
+        if (f < nfreq) {
+            b[i] = nb.at(bmap + (size_t)f * ldb, inds, wgts, nnn, s);
+            I[i] = sky[(size_t)f * lds + pix];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KC / ROWS; ++i) {
+        const int k = ty + i * ROWS;
         const int f = chunk * KC + k;
         if (f >= nfreq) break;
         const T g = tile[k][tx];
-        const T b = interp_at<T>(bmap + (size_t)f * ldb, inds, wgts, nnn, s);
-        const T I = sky[(size_t)f * lds + pix];
-        if (dsky) dsky[(size_t)f * lds + pix] += b * g;
-        if (dBI) dBI[(size_t)f * ldd + s] = I * g;
+        if (dsky) dsky[(size_t)f * lds + pix] += b[i] * g;
+        if (dBI) dBI[(size_t)f * ldd + s] = I[i] * g;
     }
 }
 
@@ -358,8 +405,15 @@ int launch_build_interp(const T* bmap, long long ldb, const int* inds, const T* 
     if (ns_pad % TS || soff % TS || soff + ns_pad > S)
         return set_error("build_interp: bad padding/offset");
     dim3 grid(ns_pad / TS, nchunks<T>(nfreq));
-    build_interp_kernel<T><<<grid, BUILD_THREADS, 0, st>>>(bmap, ldb, inds, wgts, nnn, sky, lds, cut,
-                                                           nfreq, ns, soff, S, A);
+    if (nnn == 4)
+        build_interp_kernel<T, 4><<<grid, BUILD_THREADS, 0, st>>>(bmap, ldb, inds, wgts, nnn, sky,
+                                                                  lds, cut, nfreq, ns, soff, S, A);
+    else if (nnn == 1)
+        build_interp_kernel<T, 1><<<grid, BUILD_THREADS, 0, st>>>(bmap, ldb, inds, wgts, nnn, sky,
+                                                                  lds, cut, nfreq, ns, soff, S, A);
+    else
+        build_interp_kernel<T, 0><<<grid, BUILD_THREADS, 0, st>>>(bmap, ldb, inds, wgts, nnn, sky,
+                                                                  lds, cut, nfreq, ns, soff, S, A);
     return check_launch("build_interp");
 }
 template <typename T>
@@ -370,8 +424,15 @@ int launch_build_interp_bwd(const T* dA, const T* bmap, long long ldb, const int
     if (ns <= 0 || nfreq <= 0) return 0;
     if (soff % TS) return set_error("build_interp_bwd: bad offset");
     dim3 grid((ns + TS - 1) / TS, nchunks<T>(nfreq));
-    build_interp_bwd_kernel<T><<<grid, BUILD_THREADS, 0, st>>>(
-        dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd);
+    if (nnn == 4)
+        build_interp_bwd_kernel<T, 4><<<grid, BUILD_THREADS, 0, st>>>(
+            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd);
+    else if (nnn == 1)
+        build_interp_bwd_kernel<T, 1><<<grid, BUILD_THREADS, 0, st>>>(
+            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd);
+    else
+        build_interp_bwd_kernel<T, 0><<<grid, BUILD_THREADS, 0, st>>>(
+            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd);
     return check_launch("build_interp_bwd");
 }
 template <typename T>

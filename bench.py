@@ -342,6 +342,15 @@ def main():
             return None
         return evals_rank * args.steps * flop_per_eval / (k[name]["ms"] * 1e-3) / 1e12
 
+    # DRAM traffic per launch from the committed ncu --set full capture of this workload
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("workload") == args.workload:
+            traffic = {kn.split("_kernel")[0]: v["dram_bytes_per_launch"]
+                       for kn, v in tj["kernels"].items()}
     fwd_tf = rate("fringe_sum_fwd", FLOP_FWD)
     roofline = dict(bound="fp32", kernel="fringe_sum_fwd_f32", achieved=fwd_tf,
                     peak=fp32_meas / 1e3, unit="TFLOP/s",
@@ -350,7 +359,8 @@ def main():
                                 "(MEASURED_PEAKS.json has no FP32 figure)",
                     peak_theoretical=fp32_theory,
                     frac_of_theoretical=(fwd_tf / fp32_theory) if fwd_tf else None,
-                    flop_per_eval=FLOP_FWD, traffic=None,
+                    flop_per_eval=FLOP_FWD, traffic=traffic.get("fringe_sum_fwd"),
+                    traffic_unit="DRAM bytes per launch (ncu dram__bytes_read+write, 1 time of C3)",
                     ms_per_launch=k.get("fringe_sum_fwd", {}).get("ms", 0) /
                     max(k.get("fringe_sum_fwd", {}).get("launches", 1), 1))
     others = {}
@@ -371,7 +381,7 @@ def main():
         gbs = bytes_step * args.steps / (k[bname]["ms"] * 1e-3) / 1e9
         hbm = dict(bound="hbm", kernel=bname + "_f32", achieved=gbs, peak=peaks["hbm_gbs"],
                    unit="GB/s", frac=gbs / peaks["hbm_gbs"], peak_source=peaks["source"],
-                   traffic=None)
+                   traffic=traffic.get(bname))
 
     line = dict(
         metric="rime_evals_per_sec_fwd_bwd", value=evals_total / (ms_step * 1e-3), unit=unit,
