@@ -34,10 +34,12 @@ _SIGS = {
     "pack": [_P, _L, _I, _I, _I, _L, _L, _P, _P],
     "unpack": [_P, _L, _I, _I, _L, _L, _P, _P],
     "build_interp": [_P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P],
-    "build_interp_bwd": [_P, _P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _L, _L, _P, _P, _L, _P],
+    "build_interp_bwd": [_P, _P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _L, _L, _P, _P, _L, _P, _P],
+    "gather_times": [_P, _L, _P, _I, _I, _I, _P, _L, _P],
     "interp_transpose": [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P],
     "build_airy": [_D, _D, _D, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P, _L, _P],
-    "build_airy_bwd": [_P, _D, _D, _D, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _L, _L, _P, _P, _P],
+    "build_airy_bwd": [_P, _D, _D, _D, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _L, _L, _P, _P, _P,
+                       _L, _P],
 }
 for _name, _sig in _SIGS.items():
     for _suffix in ("f32", "f64"):

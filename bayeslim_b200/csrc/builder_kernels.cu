@@ -180,8 +180,8 @@ build_interp_kernel(const T* __restrict__ bmap, long long ldb, const int* __rest
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int chunk = blockIdx.y;
     const int s = blockIdx.x * TS + tx;
-    const bool live = s < ns;
-    const int pix = live ? cut[s] : 0;
+    const int pix = (s < ns) ? cut[s] : -1;       // cut < 0 marks a padding entry
+    const bool live = pix >= 0;
     Nbr<T, NNN> nb;
     if (live) nb.load(inds, wgts, nnn, s);
     // all gathers of this thread's KC/ROWS channels are issued before they are consumed
@@ -205,7 +205,7 @@ build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, lo
                         const int* __restrict__ inds, const T* __restrict__ wgts, int nnn,
                         const T* __restrict__ sky, long long lds, const int* __restrict__ cut,
                         int nfreq, int ns, long long soff, long long S, T* __restrict__ dsky,
-                        T* __restrict__ dBI, long long ldd) {
+                        T* __restrict__ dBI, long long ldd, T* __restrict__ dIs) {
     constexpr int KC = Cfg<T>::KC;
     constexpr int ROWS = BUILD_THREADS / 32;
     __shared__ T tile[KC][TS + 1];
@@ -216,6 +216,15 @@ build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, lo
     const int s = blockIdx.x * TS + tx;
     if (s >= ns) return;
     const int pix = cut[s];
+    if (pix < 0) {                                // padding entry: contributes nothing
+        for (int k = ty; k < KC; k += ROWS) {
+            const int f = chunk * KC + k;
+            if (f >= nfreq) break;
+            if (dBI) dBI[(size_t)f * ldd + s] = 0;
+            if (dIs) dIs[(size_t)f * ldd + s] = 0;
+        }
+        return;
+    }
     Nbr<T, NNN> nb;
     nb.load(inds, wgts, nnn, s);
     T b[KC / ROWS], I[KC / ROWS];
@@ -236,6 +245,7 @@ build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, lo
         if (f >= nfreq) break;
         const T g = tile[k][tx];
         if (dsky) dsky[(size_t)f * lds + pix] += b[i] * g;
+        if (dIs) dIs[(size_t)f * ldd + s] = b[i] * g;
         if (dBI) dBI[(size_t)f * ldd + s] = I[i] * g;
     }
 }
@@ -289,8 +299,8 @@ build_airy_kernel(AiryArgs<T> a, const T* __restrict__ sky, long long lds,
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int chunk = blockIdx.y;
     const int s = blockIdx.x * TS + tx;
-    const bool live = s < ns;
-    const int pix = live ? cut[s] : 0;
+    const int pix = (s < ns) ? cut[s] : -1;
+    const bool live = pix >= 0;
     for (int k = ty; k < KC; k += BUILD_THREADS / 32) {
         const int f = chunk * KC + k;
         T v = 0;
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(BUILD_THREADS)
 build_airy_bwd_kernel(const T* __restrict__ dA, AiryArgs<T> a, int full_grad,
                       const T* __restrict__ sky, long long lds, const int* __restrict__ cut,
                       int nfreq, int ns, long long soff, long long S, T* __restrict__ dsky,
-                      double* __restrict__ dD) {
+                      double* __restrict__ dD, T* __restrict__ dIs, long long ldd) {
     constexpr int KC = Cfg<T>::KC;
     __shared__ T tile[KC][TS + 1];
     __shared__ double red[2][BUILD_THREADS / 32];
@@ -325,8 +335,14 @@ build_airy_bwd_kernel(const T* __restrict__ dA, AiryArgs<T> a, int full_grad,
     __syncthreads();
     const int s = blockIdx.x * TS + tx;
     double gew = 0.0, gns = 0.0;
-    if (s < ns) {
-        const int pix = cut[s];
+    const int pix = (s < ns) ? cut[s] : -1;
+    if (s < ns && pix < 0 && dIs) {
+        for (int k = ty; k < KC; k += BUILD_THREADS / 32) {
+            const int f = chunk * KC + k;
+            if (f < nfreq) dIs[(size_t)f * ldd + s] = 0;
+        }
+    }
+    if (pix >= 0) {
         for (int k = ty; k < KC; k += BUILD_THREADS / 32) {
             const int f = chunk * KC + k;
             if (f >= nfreq) break;
@@ -340,6 +356,7 @@ build_airy_bwd_kernel(const T* __restrict__ dA, AiryArgs<T> a, int full_grad,
             const T B = (T)(a.square ? h * h : h);
             const T I = sky[(size_t)f * lds + pix];
             if (dsky) dsky[(size_t)f * lds + pix] += B * g;
+            if (dIs) dIs[(size_t)f * ldd + s] = B * g;
             if (dD && !clipped) {
                 // dh/dx: analytic (full) or with J1 held constant (what reference autograd sees)
                 const double hp = full_grad ? (2.0 * j0(xt) / xt - 4.0 * J1 / (xt * xt)) : (-h / xt);
@@ -371,6 +388,26 @@ build_airy_bwd_kernel(const T* __restrict__ dA, AiryArgs<T> a, int full_grad,
             dD[2 * blk + 0] = a0;
             dD[2 * blk + 1] = a1;
         }
+    }
+}
+
+// dsky[f][p] += sum_t dIs[f][pos[t][p]]  (pos < 0: pixel p is outside the FOV at time t).
+// One owner per (f, p), times added in index order: the deterministic replacement of the
+// per-time index_add of cut_sky_fov's backward when all times are built in one launch.
+template <typename T>
+__global__ void __launch_bounds__(BUILD_THREADS)
+gather_times_kernel(const T* __restrict__ dIs, long long ldd, const int* __restrict__ pos, int nt,
+                    int npix, int nfreq, T* __restrict__ dsky, long long lds) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    for (int f = blockIdx.y; f < nfreq; f += gridDim.y) {
+        const T* row = dIs + (size_t)f * ldd;
+        T acc = 0;
+        for (int t = 0; t < nt; ++t) {
+            const int j = pos[(size_t)t * npix + p];
+            if (j >= 0) acc += row[j];
+        }
+        dsky[(size_t)f * lds + p] += acc;
     }
 }
 
@@ -420,19 +457,19 @@ template <typename T>
 int launch_build_interp_bwd(const T* dA, const T* bmap, long long ldb, const int* inds,
                             const T* wgts, int nnn, const T* sky, long long lds, const int* cut,
                             int nfreq, int ns, long long soff, long long S, T* dsky, T* dBI,
-                            long long ldd, cudaStream_t st) {
+                            long long ldd, T* dIs, cudaStream_t st) {
     if (ns <= 0 || nfreq <= 0) return 0;
     if (soff % TS) return set_error("build_interp_bwd: bad offset");
     dim3 grid((ns + TS - 1) / TS, nchunks<T>(nfreq));
     if (nnn == 4)
         build_interp_bwd_kernel<T, 4><<<grid, BUILD_THREADS, 0, st>>>(
-            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd);
+            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd, dIs);
     else if (nnn == 1)
         build_interp_bwd_kernel<T, 1><<<grid, BUILD_THREADS, 0, st>>>(
-            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd);
+            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd, dIs);
     else
         build_interp_bwd_kernel<T, 0><<<grid, BUILD_THREADS, 0, st>>>(
-            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd);
+            dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky, dBI, ldd, dIs);
     return check_launch("build_interp_bwd");
 }
 template <typename T>
@@ -477,14 +514,23 @@ template <typename T>
 int launch_build_airy_bwd(const T* dA, double Dew, double Dns, double freq_ratio, int square,
                           int full_grad, const T* sinzen, const T* sin2az, const double* freqs,
                           const T* sky, long long lds, const int* cut, int nfreq, int ns,
-                          long long soff, long long S, T* dsky, double* dD, cudaStream_t st) {
+                          long long soff, long long S, T* dsky, double* dD, T* dIs, long long ldd,
+                          cudaStream_t st) {
     if (ns <= 0 || nfreq <= 0) return 0;
     if (soff % TS) return set_error("build_airy_bwd: bad offset");
     dim3 grid((ns + TS - 1) / TS, nchunks<T>(nfreq));
     build_airy_bwd_kernel<T><<<grid, BUILD_THREADS, 0, st>>>(
         dA, make_airy<T>(Dew, Dns, freq_ratio, square, sinzen, sin2az, freqs), full_grad, sky, lds,
-        cut, nfreq, ns, soff, S, dsky, dD);
+        cut, nfreq, ns, soff, S, dsky, dD, dIs, ldd);
     return check_launch("build_airy_bwd");
+}
+template <typename T>
+int launch_gather_times(const T* dIs, long long ldd, const int* pos, int nt, int npix, int nfreq,
+                        T* dsky, long long lds, cudaStream_t st) {
+    if (npix <= 0 || nfreq <= 0 || nt <= 0) return 0;
+    dim3 grid((npix + BUILD_THREADS - 1) / BUILD_THREADS, nfreq < 65535 ? nfreq : 65535);
+    gather_times_kernel<T><<<grid, BUILD_THREADS, 0, st>>>(dIs, ldd, pos, nt, npix, nfreq, dsky, lds);
+    return check_launch("gather_times");
 }
 
 }  // namespace b200rime
@@ -527,18 +573,18 @@ int b200rime_build_interp_f64(const double* bmap, long long ldb, const int* inds
 int b200rime_build_interp_bwd_f32(const float* dA, const float* bmap, long long ldb,
                                   const int* inds, const float* wgts, int nnn, const float* sky,
                                   long long lds, const int* cut, int nfreq, int ns, long long soff,
-                                  long long S, float* dsky, float* dBI, long long ldd,
+                                  long long S, float* dsky, float* dBI, long long ldd, float* dIs,
                                   void* stream) {
     return launch_build_interp_bwd<float>(dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns,
-                                          soff, S, dsky, dBI, ldd, ST(stream));
+                                          soff, S, dsky, dBI, ldd, dIs, ST(stream));
 }
 int b200rime_build_interp_bwd_f64(const double* dA, const double* bmap, long long ldb,
                                   const int* inds, const double* wgts, int nnn, const double* sky,
                                   long long lds, const int* cut, int nfreq, int ns, long long soff,
-                                  long long S, double* dsky, double* dBI, long long ldd,
+                                  long long S, double* dsky, double* dBI, long long ldd, double* dIs,
                                   void* stream) {
     return launch_build_interp_bwd<double>(dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns,
-                                           soff, S, dsky, dBI, ldd, ST(stream));
+                                           soff, S, dsky, dBI, ldd, dIs, ST(stream));
 }
 int b200rime_interp_transpose_f32(const float* dBI, long long ldd, const int* rowptr,
                                   const int* col, const float* val, int npix, int nfreq,
@@ -577,19 +623,29 @@ int b200rime_build_airy_bwd_f32(const float* dA, double Dew, double Dns, double 
                                 int square, int full_grad, const float* sinzen,
                                 const float* sin2az, const double* freqs, const float* sky,
                                 long long lds, const int* cut, int nfreq, int ns, long long soff,
-                                long long S, float* dsky, double* dD, void* stream) {
+                                long long S, float* dsky, double* dD, float* dIs, long long ldd,
+                                void* stream) {
     return launch_build_airy_bwd<float>(dA, Dew, Dns, freq_ratio, square, full_grad, sinzen, sin2az,
-                                        freqs, sky, lds, cut, nfreq, ns, soff, S, dsky, dD,
+                                        freqs, sky, lds, cut, nfreq, ns, soff, S, dsky, dD, dIs, ldd,
                                         ST(stream));
 }
 int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, double freq_ratio,
                                 int square, int full_grad, const double* sinzen,
                                 const double* sin2az, const double* freqs, const double* sky,
                                 long long lds, const int* cut, int nfreq, int ns, long long soff,
-                                long long S, double* dsky, double* dD, void* stream) {
+                                long long S, double* dsky, double* dD, double* dIs, long long ldd,
+                                void* stream) {
     return launch_build_airy_bwd<double>(dA, Dew, Dns, freq_ratio, square, full_grad, sinzen,
                                          sin2az, freqs, sky, lds, cut, nfreq, ns, soff, S, dsky, dD,
-                                         ST(stream));
+                                         dIs, ldd, ST(stream));
+}
+int b200rime_gather_times_f32(const float* dIs, long long ldd, const int* pos, int nt, int npix,
+                              int nfreq, float* dsky, long long lds, void* stream) {
+    return launch_gather_times<float>(dIs, ldd, pos, nt, npix, nfreq, dsky, lds, ST(stream));
+}
+int b200rime_gather_times_f64(const double* dIs, long long ldd, const int* pos, int nt, int npix,
+                              int nfreq, double* dsky, long long lds, void* stream) {
+    return launch_gather_times<double>(dIs, ldd, pos, nt, npix, nfreq, dsky, lds, ST(stream));
 }
 
 }  // extern "C"

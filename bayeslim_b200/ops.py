@@ -217,36 +217,61 @@ def pack_planes(geom, planes):
 
 
 # ----------------------------------------------------------------------------- fused builders
-class InterpRecord:
-    """Per-time tables of the interpolated-beam builder (device): FOV cut indices into the sky,
-    neighbour indices/weights into the beam map, and their CSR transpose for the adjoint."""
+def _packed_cut(geom, cuts, npix):
+    """(cut, pos): cut int32 [S] = sky pixel of every packed source (-1 for padding entries);
+    pos int32 [Nt][Npix] = packed index of pixel p at time t (-1 outside the FOV)."""
+    dev = geom.device
+    cut = torch.full((max(geom.S, 1),), -1, dtype=torch.int32, device=dev)
+    pos = torch.full((geom.nt, npix), -1, dtype=torch.int32, device=dev)
+    for t, c in enumerate(cuts):
+        n = geom.ns[t]
+        if n == 0:
+            continue
+        c = c.to(dev)
+        cut[geom.toff[t]:geom.toff[t] + n] = c.to(torch.int32)
+        pos[t, c.long()] = torch.arange(geom.toff[t], geom.toff[t] + n, dtype=torch.int32,
+                                        device=dev)
+    return cut.contiguous(), pos.contiguous()
 
-    def __init__(self, cut, inds, wgts, npix_beam, dtype, device):
-        self.cut = cut.to(device=device, dtype=torch.int32).contiguous()
-        self.inds = inds.to(device=device, dtype=torch.int32).contiguous()
-        self.wgts = wgts.to(device=device, dtype=dtype).contiguous()
-        self.nnn = int(inds.shape[1]) if inds.ndim == 2 else 1
-        self.ns = int(len(cut))
-        self.npix_beam = npix_beam
+
+class InterpTable:
+    """Device tables of the interpolated-beam builder for one time group, over the packed
+    source axis: FOV cut into the sky, neighbour indices / weights into the beam map, and their
+    CSR transpose for the adjoint (built on first backward)."""
+
+    def __init__(self, geom, cuts, inds_list, wgts_list, npix_sky, npix_beam, dtype):
+        dev = geom.device
+        S = max(geom.S, 1)
+        self.nnn = int(inds_list[0].shape[1]) if len(inds_list) and inds_list[0].ndim == 2 else 1
+        self.npix_sky, self.npix_beam = npix_sky, npix_beam
+        self.cut, self.pos = _packed_cut(geom, cuts, npix_sky)
+        self.inds = torch.zeros(S, self.nnn, dtype=torch.int32, device=dev)
+        self.wgts = torch.zeros(S, self.nnn, dtype=dtype, device=dev)
+        for t, (i, w) in enumerate(zip(inds_list, wgts_list)):
+            n = geom.ns[t]
+            if n:
+                sl = slice(geom.toff[t], geom.toff[t] + n)
+                self.inds[sl] = i.to(dev).reshape(n, self.nnn).to(torch.int32)
+                self.wgts[sl] = w.to(dev).reshape(n, self.nnn).to(dtype)
         self._csr = None
 
     def csr(self):
-        """CSR transpose (beam pixel -> [(source, weight)]), built on first backward."""
         if self._csr is None:
-            flat = self.inds.reshape(-1).long()
+            live = (self.cut >= 0).repeat_interleave(self.nnn)
+            flat = self.inds.reshape(-1).long()[live]
+            src = torch.arange(self.inds.shape[0], device=flat.device).repeat_interleave(self.nnn)[live]
+            w = self.wgts.reshape(-1)[live]
             order = torch.argsort(flat, stable=True)
             counts = torch.bincount(flat, minlength=self.npix_beam)
             rowptr = torch.zeros(self.npix_beam + 1, dtype=torch.int32, device=flat.device)
             rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
-            col = (order // self.nnn).to(torch.int32).contiguous()
-            val = self.wgts.reshape(-1)[order].contiguous()
-            self._csr = (rowptr, col, val)
+            self._csr = (rowptr, src[order].to(torch.int32).contiguous(), w[order].contiguous())
         return self._csr
 
 
 class _BuildInterp(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, sky, bmap, geom, recs):
+    def forward(ctx, sky, bmap, geom, tab):
         _need_cuda(sky, bmap)
         dtype, sfx = sky.dtype, _sfx(sky.dtype)
         sky = sky.contiguous()
@@ -254,60 +279,70 @@ class _BuildInterp(torch.autograd.Function):
         nfreq = sky.shape[0]
         assert bmap.shape[0] == nfreq
         kc = _lib.KC[sfx]
-        A = torch.empty(1, nchunks(nfreq, dtype), max(geom.S, 1), kc, dtype=dtype, device=sky.device)
-        for t, r in enumerate(recs):
-            _call("build_interp", sfx, bmap, bmap.shape[1], r.inds, r.wgts, r.nnn,
-                  sky, sky.shape[1], r.cut, nfreq, r.ns, geom.ns_pad[t], geom.toff[t],
-                  geom.S, A[0])
+        S = max(geom.S, 1)
+        A = torch.empty(1, nchunks(nfreq, dtype), S, kc, dtype=dtype, device=sky.device)
+        if geom.S > 0:
+            _call("build_interp", sfx, bmap, bmap.shape[1], tab.inds, tab.wgts, tab.nnn, sky,
+                  sky.shape[1], tab.cut, nfreq, geom.S, geom.S, 0, geom.S, A[0])
         ctx.save_for_backward(sky, bmap)
-        ctx.geom, ctx.recs = geom, recs
+        ctx.geom, ctx.tab = geom, tab
         return A
 
     @staticmethod
     def backward(ctx, dA):
         sky, bmap = ctx.saved_tensors
-        geom, recs = ctx.geom, ctx.recs
+        geom, tab = ctx.geom, ctx.tab
         dA = dA.contiguous()
         sfx = _sfx(sky.dtype)
         nfreq = sky.shape[0]
         need_sky, need_beam = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dsky = torch.zeros_like(sky) if need_sky else None
         dbmap = torch.zeros_like(bmap) if need_beam else None
-        nsmax = max([r.ns for r in recs] + [1])
-        dBI = torch.empty(nfreq, nsmax, dtype=sky.dtype, device=sky.device) if need_beam else None
-        for t, r in enumerate(recs):
-            if r.ns == 0:
-                continue
-            _call("build_interp_bwd", sfx, dA[0], bmap, bmap.shape[1], r.inds, r.wgts,
-                  r.nnn, sky, sky.shape[1], r.cut, nfreq, r.ns, geom.toff[t], geom.S,
-                  dsky, dBI, nsmax)
+        if geom.S > 0 and (need_sky or need_beam):
+            S = geom.S
+            dIs = torch.empty(nfreq, S, dtype=sky.dtype, device=sky.device) if need_sky else None
+            dBI = torch.empty(nfreq, S, dtype=sky.dtype, device=sky.device) if need_beam else None
+            _call("build_interp_bwd", sfx, dA[0], bmap, bmap.shape[1], tab.inds, tab.wgts, tab.nnn,
+                  sky, sky.shape[1], tab.cut, nfreq, S, 0, S, None, dBI, S, dIs)
+            if need_sky:
+                _call("gather_times", sfx, dIs, S, tab.pos, geom.nt, tab.npix_sky, nfreq, dsky,
+                      sky.shape[1])
             if need_beam:
-                rowptr, col, val = r.csr()
-                _call("interp_transpose", sfx, dBI, nsmax, rowptr, col, val,
-                      r.npix_beam, nfreq, dbmap, bmap.shape[1])
+                rowptr, col, val = tab.csr()
+                _call("interp_transpose", sfx, dBI, S, rowptr, col, val, tab.npix_beam, nfreq,
+                      dbmap, bmap.shape[1])
         return dsky, dbmap, None, None
 
 
-def build_interp(sky, bmap, geom, recs):
-    """sky (Nf, Npix), bmap (Nf, Npb) -> A (1, nchunk, S, KC)."""
-    return _BuildInterp.apply(sky, bmap, geom, recs)
+def build_interp(sky, bmap, geom, tab):
+    """sky (Nf, Npix), bmap (Nf, Npb) -> A (1, nchunk, S, KC); one launch for all times."""
+    return _BuildInterp.apply(sky, bmap, geom, tab)
 
 
-class AiryRecord:
-    """Per-time tables of the Airy builder: cut, sin(min(zen, 90deg)) and sin(az)^2."""
+class AiryTable:
+    """Device tables of the Airy builder over the packed source axis: cut,
+    sin(min(zen, 90deg)) and sin(az)^2."""
 
-    def __init__(self, cut, zen_deg, az_deg, dtype, device):
-        self.cut = cut.to(device=device, dtype=torch.int32).contiguous()
-        zen = torch.clamp(zen_deg.to(device, torch.float64) * D2R, max=math.pi / 2)
-        az = az_deg.to(device, torch.float64) * D2R
-        self.sinzen = torch.sin(zen).to(dtype).contiguous()
-        self.sin2az = (torch.abs(torch.sin(az)) ** 2).to(dtype).contiguous()
-        self.ns = int(len(cut))
+    def __init__(self, geom, cuts, zen_list, az_list, npix_sky, dtype):
+        dev = geom.device
+        S = max(geom.S, 1)
+        self.npix_sky = npix_sky
+        self.cut, self.pos = _packed_cut(geom, cuts, npix_sky)
+        self.sinzen = torch.zeros(S, dtype=dtype, device=dev)
+        self.sin2az = torch.zeros(S, dtype=dtype, device=dev)
+        for t, (z, a) in enumerate(zip(zen_list, az_list)):
+            n = geom.ns[t]
+            if n:
+                sl = slice(geom.toff[t], geom.toff[t] + n)
+                zen = torch.clamp(z.to(dev, torch.float64) * D2R, max=math.pi / 2)
+                az = a.to(dev, torch.float64) * D2R
+                self.sinzen[sl] = torch.sin(zen).to(dtype)
+                self.sin2az[sl] = (torch.abs(torch.sin(az)) ** 2).to(dtype)
 
 
 class _BuildAiry(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, sky, diam, geom, recs, freqs64, freq_ratio, square, full_grad):
+    def forward(ctx, sky, diam, geom, tab, freqs64, freq_ratio, square, full_grad):
         _need_cuda(sky)
         dtype, sfx = sky.dtype, _sfx(sky.dtype)
         sky = sky.contiguous()
@@ -317,48 +352,53 @@ class _BuildAiry(torch.autograd.Function):
         asym = d.numel() > 1
         Dns = float(d[1]) if asym else Dew
         kc = _lib.KC[sfx]
-        A = torch.empty(1, nchunks(nfreq, dtype), max(geom.S, 1), kc, dtype=dtype, device=sky.device)
-        for t, r in enumerate(recs):
-            _call("build_airy", sfx, Dew, Dns, float(freq_ratio), int(square), r.sinzen,
-                  r.sin2az if asym else None, freqs64, sky, sky.shape[1], r.cut,
-                  nfreq, r.ns, geom.ns_pad[t], geom.toff[t], geom.S, A[0], None, 0)
+        S = max(geom.S, 1)
+        A = torch.empty(1, nchunks(nfreq, dtype), S, kc, dtype=dtype, device=sky.device)
+        if geom.S > 0:
+            _call("build_airy", sfx, Dew, Dns, float(freq_ratio), int(square), tab.sinzen,
+                  tab.sin2az if asym else None, freqs64, sky, sky.shape[1], tab.cut, nfreq, geom.S,
+                  geom.S, 0, geom.S, A[0], None, 0)
         ctx.save_for_backward(sky, freqs64)
-        ctx.meta = (geom, recs, Dew, Dns, asym, float(freq_ratio), int(square), int(full_grad),
+        ctx.meta = (geom, tab, Dew, Dns, asym, float(freq_ratio), int(square), int(full_grad),
                     diam.shape, diam.dtype, diam.device)
         return A
 
     @staticmethod
     def backward(ctx, dA):
         sky, freqs64 = ctx.saved_tensors
-        geom, recs, Dew, Dns, asym, ratio, square, full_grad, dshape, ddtype, ddev = ctx.meta
+        geom, tab, Dew, Dns, asym, ratio, square, full_grad, dshape, ddtype, ddev = ctx.meta
         dA = dA.contiguous()
         sfx = _sfx(sky.dtype)
         nfreq = sky.shape[0]
         need_sky, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dsky = torch.zeros_like(sky) if need_sky else None
-        gD = torch.zeros(2, dtype=torch.float64, device=sky.device)
-        for t, r in enumerate(recs):
-            if r.ns == 0:
-                continue
+        gdiam = None
+        if geom.S > 0 and (need_sky or need_d):
+            S = geom.S
+            dIs = torch.empty(nfreq, S, dtype=sky.dtype, device=sky.device) if need_sky else None
             dD = None
             if need_d:
-                nb = _lib.lib.b200rime_airy_bwd_blocks(nfreq, r.ns)
+                nb = _lib.lib.b200rime_airy_bwd_blocks(nfreq, S)
                 dD = torch.zeros(nb, 2, dtype=torch.float64, device=sky.device)
-            _call("build_airy_bwd", sfx, dA[0], Dew, Dns, ratio, square, full_grad, r.sinzen,
-                  r.sin2az if asym else None, freqs64, sky, sky.shape[1], r.cut,
-                  nfreq, r.ns, geom.toff[t], geom.S, dsky, dD)
+            _call("build_airy_bwd", sfx, dA[0], Dew, Dns, ratio, square, full_grad, tab.sinzen,
+                  tab.sin2az if asym else None, freqs64, sky, sky.shape[1], tab.cut, nfreq, S, 0, S,
+                  None, dD, dIs, S)
+            if need_sky:
+                _call("gather_times", sfx, dIs, S, tab.pos, geom.nt, tab.npix_sky, nfreq, dsky,
+                      sky.shape[1])
             if need_d:
-                gD = gD + dD.sum(0)
-        gdiam = None
-        if need_d:
-            g = gD if asym else gD[:1]
-            gdiam = g.to(device=ddev, dtype=ddtype).reshape(dshape)
+                gD = dD.sum(0)
+                g = gD if asym else gD[:1]
+                gdiam = g.to(device=ddev, dtype=ddtype).reshape(dshape)
+        elif need_d:
+            gdiam = torch.zeros(dshape, dtype=ddtype, device=ddev)
         return dsky, gdiam, None, None, None, None, None, None
 
 
-def build_airy(sky, diam, geom, recs, freqs64, freq_ratio=1.0, square=True, full_grad=False):
-    """sky (Nf, Npix), diam tensor with 1 (D) or 2 (Dew, Dns) elements -> A (1, nchunk, S, KC)."""
-    return _BuildAiry.apply(sky, diam, geom, recs, freqs64, freq_ratio, square, full_grad)
+def build_airy(sky, diam, geom, tab, freqs64, freq_ratio=1.0, square=True, full_grad=False):
+    """sky (Nf, Npix), diam tensor with 1 (D) or 2 (Dew, Dns) elements -> A (1, nchunk, S, KC);
+    one launch for all times."""
+    return _BuildAiry.apply(sky, diam, geom, tab, freqs64, freq_ratio, square, full_grad)
 
 
 # ----------------------------------------------------------------------------- fringe sum

@@ -38,8 +38,8 @@ class _GeometryRecord:
         self.cuts = None      # per-time int64 index tensors (or None when the FOV keeps all)
         self.zen = None       # per-time cut zen/az [deg], float64, device
         self.az = None
-        self.airy = {}        # dtype -> [AiryRecord]
-        self.interp = {}      # (id(R), dtype) -> [InterpRecord]
+        self.airy = {}        # dtype -> ops.AiryTable
+        self.interp = {}      # (id(R), interp_mode, dtype) -> ops.InterpTable
 
 
 class RIME(utils.Module):
@@ -274,8 +274,7 @@ class RIME(utils.Module):
         b, R = self.beam, self.beam.R
         dtype = sky.dtype
         if dtype not in rec.airy:
-            rec.airy[dtype] = [ops.AiryRecord(c, z, a, dtype, dev)
-                               for c, z, a in zip(rec.cuts, rec.zen, rec.az)]
+            rec.airy[dtype] = ops.AiryTable(rec.geom, rec.cuts, rec.zen, rec.az, sky.shape[-1], dtype)
         p = b.total_params().to(dev)
         f64 = self._freqs64(b, dev)
         planes = [ops.build_airy(sky[0, 0], p[ipol, 0, 0, 0], rec.geom, rec.airy[dtype], f64,
@@ -292,11 +291,10 @@ class RIME(utils.Module):
         bmap = R.beam_cache.to(dev)
         key = (id(R), R.interp_mode, dtype)
         if key not in rec.interp:
-            recs = []
-            for c, z, a in zip(rec.cuts, rec.zen, rec.az):
-                inds, wgts = R.get_interp(z, a)
-                recs.append(ops.InterpRecord(c, inds, wgts, bmap.shape[-1], dtype, dev))
-            rec.interp[key] = recs
+            tabs = [R.get_interp(z, a) for z, a in zip(rec.zen, rec.az)]
+            rec.interp[key] = ops.InterpTable(rec.geom, rec.cuts, [t[0] for t in tabs],
+                                              [t[1] for t in tabs], sky.shape[-1], bmap.shape[-1],
+                                              dtype)
         planes = [ops.build_interp(sky[0, 0], bmap[ipol, 0, 0], rec.geom, rec.interp[key])
                   for ipol in range(b.Npol)]
         return planes[0] if len(planes) == 1 else torch.cat(planes, dim=0)

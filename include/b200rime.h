@@ -127,7 +127,8 @@ int b200rime_unpack_f64(const double* A, long long ldx, int nfreq, int ns, long 
  * Interpolated pixel beam (PixInterp.interp utils.py:833-841 + cut_sky_fov beam_model.py:1696
  * + beam*sky beam_model.py:341):
  *   A[f][soff+s] = ( sum_{i<nnn} bmap[f*ldb + inds[s][i]] * wgts[s][i] ) * sky[f*lds + cut[s]]
- * inds int32 [ns][nnn], wgts real [ns][nnn], cut int32 [ns]. */
+ * inds int32 [ns][nnn], wgts real [ns][nnn], cut int32 [ns]; cut[s] < 0 marks a padding entry
+ * (A = 0), so one call with ns = ns_pad = S, soff = 0 builds every time of a group at once. */
 int b200rime_build_interp_f32(const float* bmap, long long ldb, const int* inds,
                               const float* wgts, int nnn, const float* sky, long long lds,
                               const int* cut, int nfreq, int ns, int ns_pad, long long soff,
@@ -136,22 +137,33 @@ int b200rime_build_interp_f64(const double* bmap, long long ldb, const int* inds
                               const double* wgts, int nnn, const double* sky, long long lds,
                               const int* cut, int nfreq, int ns, int ns_pad, long long soff,
                               long long S, double* A, b200rime_stream_t stream);
-/* backward of the above given dA: writes
- *   dsky[f*lds + cut[s]] += B[f][s] * dA[f][s]            (cut indices are unique per time)
- *   dBI[f*ldd + s]        = sky[f][cut[s]] * dA[f][s]      (row-major (Nf, ns) workspace)
- * followed by b200rime_interp_transpose_* which gathers dBI into the beam map through the
- * CSR transpose of (inds, wgts):  dbmap[f*ldb + p] += sum_{j in [rowptr[p], rowptr[p+1])}
- * val[j] * dBI[f*ldd + col[j]]   -- one owner per (f, p), no atomics. */
+/* backward of the above given dA: writes (each output optional, NULL to skip)
+ *   dsky[f*lds + cut[s]] += B[f][s] * dA[f][s]   read-modify-write; legal only when the call
+ *                                                covers ONE time (cut indices unique)
+ *   dIs[f*ldd + s]        = B[f][s] * dA[f][s]   row-major (Nf, ns) -- the multi-time form:
+ *                                                follow with b200rime_gather_times_*
+ *   dBI[f*ldd + s]        = sky[f][cut[s]] * dA[f][s]
+ * b200rime_interp_transpose_* then gathers dBI into the beam map through the CSR transpose of
+ * (inds, wgts):  dbmap[f*ldb + p] += sum_{j in [rowptr[p], rowptr[p+1])} val[j] *
+ * dBI[f*ldd + col[j]]   -- one owner per (f, p), no atomics. */
 int b200rime_build_interp_bwd_f32(const float* dA, const float* bmap, long long ldb,
                                   const int* inds, const float* wgts, int nnn, const float* sky,
                                   long long lds, const int* cut, int nfreq, int ns, long long soff,
-                                  long long S, float* dsky, float* dBI, long long ldd,
+                                  long long S, float* dsky, float* dBI, long long ldd, float* dIs,
                                   b200rime_stream_t stream);
 int b200rime_build_interp_bwd_f64(const double* dA, const double* bmap, long long ldb,
                                   const int* inds, const double* wgts, int nnn, const double* sky,
                                   long long lds, const int* cut, int nfreq, int ns, long long soff,
-                                  long long S, double* dsky, double* dBI, long long ldd,
+                                  long long S, double* dsky, double* dBI, long long ldd, double* dIs,
                                   b200rime_stream_t stream);
+/* dsky[f*lds + p] += sum_t dIs[f*ldd + pos[t*npix + p]]  over the times with pos >= 0
+ * (pos: int32 [nt][npix], packed source index of sky pixel p at time t, or -1 when p is outside
+ * the FOV).  One owner per (f, p), times added in index order: deterministic adjoint of
+ * cut_sky_fov (beam_model.py:1696) for a whole time group. */
+int b200rime_gather_times_f32(const float* dIs, long long ldd, const int* pos, int nt, int npix,
+                              int nfreq, float* dsky, long long lds, b200rime_stream_t stream);
+int b200rime_gather_times_f64(const double* dIs, long long ldd, const int* pos, int nt, int npix,
+                              int nfreq, double* dsky, long long lds, b200rime_stream_t stream);
 int b200rime_interp_transpose_f32(const float* dBI, long long ldd, const int* rowptr,
                                   const int* col, const float* val, int npix, int nfreq,
                                   float* dbmap, long long ldb, b200rime_stream_t stream);
@@ -175,9 +187,10 @@ int b200rime_build_airy_f64(double Dew, double Dns, double freq_ratio, int squar
                             const double* sky, long long lds, const int* cut, int nfreq, int ns,
                             int ns_pad, long long soff, long long S, double* A, double* Bout,
                             long long ldo, b200rime_stream_t stream);
-/* backward: dsky[f*lds + cut[s]] += B * dA ; dD[block][0..1] partial sums of
- * dL/dDew, dL/dDns (float64 [nblocks][2], nblocks = b200rime_airy_bwd_blocks(nfreq, ns)),
- * summed by the caller in index order.  full_grad != 0 uses the analytic derivative
+/* backward: dsky[f*lds + cut[s]] += B * dA (single-time calls) or dIs[f*ldd + s] = B * dA
+ * (multi-time calls, then b200rime_gather_times_*); dD[block][0..1] partial sums of
+ * dL/dDew, dL/dDns (float64 [nblocks][2], zero-initialised by the caller,
+ * nblocks = b200rime_airy_bwd_blocks(nfreq, ns)), summed by the caller in index order.  full_grad != 0 uses the analytic derivative
  * d(2J1/x)/dx = 2 J0/x - 4 J1/x^2; full_grad == 0 reproduces the reference's autograd,
  * which treats J1(x) as a constant (torch.special.bessel_j1 has no derivative formula). */
 int b200rime_airy_bwd_blocks(int nfreq, int ns);
@@ -185,12 +198,14 @@ int b200rime_build_airy_bwd_f32(const float* dA, double Dew, double Dns, double 
                                 int square, int full_grad, const float* sinzen,
                                 const float* sin2az, const double* freqs, const float* sky,
                                 long long lds, const int* cut, int nfreq, int ns, long long soff,
-                                long long S, float* dsky, double* dD, b200rime_stream_t stream);
+                                long long S, float* dsky, double* dD, float* dIs, long long ldd,
+                                b200rime_stream_t stream);
 int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, double freq_ratio,
                                 int square, int full_grad, const double* sinzen,
                                 const double* sin2az, const double* freqs, const double* sky,
                                 long long lds, const int* cut, int nfreq, int ns, long long soff,
-                                long long S, double* dsky, double* dD, b200rime_stream_t stream);
+                                long long S, double* dsky, double* dD, double* dIs, long long ldd,
+                                b200rime_stream_t stream);
 
 /* ---- on-device peak measurements used as roofline denominators ---------------------
  * kind: 0 = FP32 FFMA chains, 1 = FP64 DFMA chains, 2 = MUFU sin+cos, 3 = packed FP32x2

@@ -114,20 +114,36 @@ def _interp(bmap, inds, wgts):
     return (bmap[:, inds.long()] * wgts[None]).sum(-1)            # (nf, ns)
 
 
+def _live(cut, ns):
+    c = cut[:ns].long()
+    return c >= 0, c.clamp(min=0)
+
+
 def build_interp(sfx, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, ns_pad, soff, S, A):
-    B = _interp(bmap, inds.reshape(ns, nnn), wgts.reshape(ns, nnn))
-    X = B * sky[:, cut.long()]
+    live, c = _live(cut, ns)
+    B = _interp(bmap, inds[:ns].reshape(ns, nnn), wgts[:ns].reshape(ns, nnn))
+    X = B * sky[:, c] * live[None]
     pack(sfx, X.contiguous(), ns, nfreq, ns, ns_pad, soff, S, A)
 
 
 def build_interp_bwd(sfx, dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky,
-                     dBI, ldd):
-    g = _A_rows(dA, nfreq)[:, soff:soff + ns]
-    B = _interp(bmap, inds.reshape(ns, nnn), wgts.reshape(ns, nnn))
+                     dBI, ldd, dIs):
+    live, c = _live(cut, ns)
+    g = _A_rows(dA, nfreq)[:, soff:soff + ns] * live[None]
+    B = _interp(bmap, inds[:ns].reshape(ns, nnn), wgts[:ns].reshape(ns, nnn))
     if dsky is not None:
-        dsky[:, cut.long()] += B * g
+        dsky.index_add_(1, c, (B * g).to(dsky.dtype))
+    if dIs is not None:
+        dIs[:, :ns] = B * g
     if dBI is not None:
-        dBI[:, :ns] = sky[:, cut.long()] * g
+        dBI[:, :ns] = sky[:, c] * g
+
+
+def gather_times(sfx, dIs, ldd, pos, nt, npix, nfreq, dsky, lds):
+    for t in range(nt):
+        p = pos[t].long()
+        ok = p >= 0
+        dsky[:, ok] += dIs[:, p[ok]]
 
 
 def interp_transpose(sfx, dBI, ldd, rowptr, col, val, npix, nfreq, dbmap, ldb):
@@ -152,19 +168,27 @@ def _airy(Dew, Dns, ratio, square, sinzen, sin2az, freqs, nfreq, T):
 
 def build_airy(sfx, Dew, Dns, ratio, square, sinzen, sin2az, freqs, sky, lds, cut, nfreq, ns,
                ns_pad, soff, S, A, Bout, ldo):
-    _, x, J1, h, _, _ = _airy(Dew, Dns, ratio, square, sinzen, sin2az, freqs, nfreq, sky.dtype)
+    live, c = _live(cut, ns)
+    sz = sinzen[:ns]
+    s2 = sin2az[:ns] if sin2az is not None else None
+    _, x, J1, h, _, _ = _airy(Dew, Dns, ratio, square, sz, s2, freqs, nfreq, sky.dtype)
     B = h * h if square else h
-    pack(sfx, (B * sky[:, cut.long()]).contiguous(), ns, nfreq, ns, ns_pad, soff, S, A)
+    pack(sfx, (B * sky[:, c] * live[None]).contiguous(), ns, nfreq, ns, ns_pad, soff, S, A)
 
 
 def build_airy_bwd(sfx, dA, Dew, Dns, ratio, square, full_grad, sinzen, sin2az, freqs, sky, lds, cut,
-                   nfreq, ns, soff, S, dsky, dD):
-    g = _A_rows(dA, nfreq)[:, soff:soff + ns]
-    xr, x, J1, h, d1, d2 = _airy(Dew, Dns, ratio, square, sinzen, sin2az, freqs, nfreq, sky.dtype)
+                   nfreq, ns, soff, S, dsky, dD, dIs, ldd):
+    live, c = _live(cut, ns)
+    g = _A_rows(dA, nfreq)[:, soff:soff + ns] * live[None]
+    sz = sinzen[:ns]
+    s2 = sin2az[:ns] if sin2az is not None else None
+    xr, x, J1, h, d1, d2 = _airy(Dew, Dns, ratio, square, sz, s2, freqs, nfreq, sky.dtype)
     B = h * h if square else h
-    I = sky[:, cut.long()]
+    I = sky[:, c]
     if dsky is not None:
-        dsky[:, cut.long()] += B * g
+        dsky.index_add_(1, c, (B * g).to(dsky.dtype))
+    if dIs is not None:
+        dIs[:, :ns] = B * g
     if dD is not None:
         hp = (2 * torch.special.bessel_j0(x) / x - 4 * J1 / (x * x)) if full_grad else (-h / x)
         dBdx = 2 * h * hp if square else hp
@@ -178,6 +202,7 @@ _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
               fringe_sum_bwd_sky=fringe_sum_bwd_sky, fringe_sum_bwd_bl=fringe_sum_bwd_bl,
               pack=pack, unpack=unpack, build_interp=build_interp,
               build_interp_bwd=build_interp_bwd, interp_transpose=interp_transpose,
+              gather_times=gather_times,
               build_airy=build_airy, build_airy_bwd=build_airy_bwd)
 
 

@@ -373,3 +373,126 @@ def test_integration_md_stub_runs():
     F = orc.gen_fringe(blv, zen, az, freqs)
     Vo = torch.einsum('bfs,fs->bf', F, X.to(F.dtype))
     assert relmax(V, Vo, "integration_stub/V") < 1e-5
+
+
+# ------------------------------------------------------------------ remaining SURVEY 8(a) rows
+def _small_array(device, freqs):
+    ants, vecs = ba.utils._make_hex(2, D=14.6)
+    return ants, ba.telescope_model.ArrayModel(
+        ba.utils.AntposDict(ants, torch.as_tensor(vecs, dtype=torch.float64, device=device)),
+        freqs=freqs, device=device)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_c1_full_size_vs_oracle(dtype):
+    """BASELINE config 1 at full size: HERA-37, 63 unique baselines, 1000 point sources
+    (power law), Airy beam, 64 freqs, 10 times."""
+    rime = workloads.point_airy(1000, 64, 10, DEV, dtype, bls='uniq')
+    with torch.no_grad():
+        V = rime().data
+    assert V.shape == (1, 1, 63, 10, 64)
+    Vo = _oracle_of_workload(rime, 'airy', list(range(63)), slice(None))
+    assert relmax(V, Vo, "c1_full/%s/V" % str(dtype)[6:]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_gauss_response_generic_path(dtype):
+    """A response without a fused builder (GaussResponse, beam_model.py:848-899) goes through
+    torch + pack_planes + the CUDA fringe sum; gradients reach the Gaussian widths."""
+    g = torch.Generator().manual_seed(21)
+    freqs = torch.linspace(120e6, 180e6, 20, dtype=torch.float64, device=DEV)
+    ants, array = _small_array(DEV, freqs)
+    bls = workloads.all_cross_bls(ants)
+    Ns = 90
+    ra = torch.rand(Ns, generator=g, dtype=torch.float64) * 360
+    dec = torch.rand(Ns, generator=g, dtype=torch.float64) * 80 - 70
+    sp = torch.rand(1, 1, 20, Ns, generator=g, dtype=torch.float64).to(dtype)
+    sky = ba.sky_model.PointSky(sp.to(DEV), torch.stack([ra, dec]).to(DEV),
+                                R=ba.sky_model.PointSkyResponse(freqs.to(dtype), freq_mode='channel',
+                                                                device=DEV), parameter=True)
+    bp = torch.tensor([0.3, 0.4], dtype=dtype).reshape(1, 1, 1, 1, 2).repeat(1, 1, 1, 20, 1)
+    beam = ba.beam_model.PixelBeam(bp.to(DEV), freqs, R=ba.beam_model.GaussResponse(powerbeam=True),
+                                   pol='e', powerbeam=True, fov=180, parameter=True)
+    rime = ba.RIME(sky, ba.telescope_model.TelescopeModel(workloads.LOCATION, device=DEV), beam,
+                   array, bls, np.linspace(2458148.15, 2458148.2, 2), freqs, device=DEV)
+    V = rime().data
+    (V.real ** 2 + V.imag ** 2).sum().backward()
+    # oracle
+    zenaz = [(za[0].cpu().double(), za[1].cpu().double()) for za in workloads.zenaz_of(rime)]
+    spo = sp.double().clone().requires_grad_(True)
+    bpo = bp.double().clone().requires_grad_(True)
+    blvecs = orc.get_blvecs(array.antvecs.cpu().double(), ants, bls)
+    Vo = orc.rime_forward(spo, zenaz, lambda z, a: orc.gauss_response(bpo, z, a),
+                          bls, blvecs, freqs.cpu(), fov=180.0)
+    (Vo.real ** 2 + Vo.imag ** 2).sum().backward()
+    tag = "gauss_generic/%s" % str(dtype)[6:]
+    assert relmax(V, Vo, tag + "/V") < TOL[dtype]
+    assert relmax(sky.params.grad, spo.grad, tag + "/dsky") < 5 * TOL[dtype]
+    assert relmax(beam.params.grad, bpo.grad, tag + "/dbeam") < 5 * TOL[dtype]
+
+
+def test_healpix_pixel_beam_and_composite_sky():
+    """PixelResponse with pixtype='healpix' (RING bilinear weights; parity unpinned, checked
+    against the oracle's independent restatement) and a two-component CompositeModel whose
+    visibilities RIME sums (the reference's own sum raises, rime_model.py:377)."""
+    dtype = torch.float64
+    g = torch.Generator().manual_seed(22)
+    freqs = torch.linspace(120e6, 180e6, 6, dtype=torch.float64, device=DEV)
+    ants, array = _small_array(DEV, freqs)
+    bls = workloads.all_cross_bls(ants)[:9]
+    nside = 8
+    theta, phi = ba.healpix.pix2ang(nside)
+    bmap = torch.as_tensor(np.exp(-0.5 * (theta / 0.5) ** 2))[None, None, None, None, :].repeat(
+        1, 1, 1, 6, 1).to(dtype)
+    R = ba.beam_model.PixelResponse(freqs, 'healpix', nside=nside, freq_mode='channel',
+                                    powerbeam=True, device=DEV)
+    beam = ba.beam_model.PixelBeam(bmap.to(DEV), freqs, R=R, pol='e', powerbeam=True, fov=180,
+                                   parameter=True)
+    comps, refs = {}, []
+    for name, Ns in (("a", 40), ("b", 25)):
+        ra = torch.rand(Ns, generator=g, dtype=torch.float64) * 360
+        dec = torch.rand(Ns, generator=g, dtype=torch.float64) * 80 - 70
+        sp = torch.rand(1, 1, 6, Ns, generator=g, dtype=torch.float64)
+        comps[name] = ba.sky_model.PointSky(
+            sp.to(DEV), torch.stack([ra, dec]).to(DEV), name=name,
+            R=ba.sky_model.PointSkyResponse(freqs, freq_mode='channel', device=DEV), parameter=True)
+        refs.append((name, Ns, ra, dec, sp))
+    sky = ba.sky_model.CompositeModel(comps)
+    tel = ba.telescope_model.TelescopeModel(workloads.LOCATION, device=DEV)
+    times = np.linspace(2458148.15, 2458148.2, 2)
+    rime = ba.RIME(sky, tel, beam, array, bls, times, freqs, device=DEV)
+    V = rime().data
+    (V.real ** 2 + V.imag ** 2).sum().backward()
+    # oracle: sum of the two components, healpix weights from the oracle's own restatement
+    blvecs = orc.get_blvecs(array.antvecs.cpu().double(), ants, bls)
+    bo = bmap.double().clone().requires_grad_(True)
+    Vo = 0
+    for name, Ns, ra, dec, sp in refs:
+        zenaz = [tuple(x.cpu().double() for x in tel.conv_cache[(name, Ns, t)]) for t in times]
+
+        def beam_fn(z, a):
+            inds, wgts = orc.healpix_interp_weights(nside, (z * orc.D2R).numpy(), (a * orc.D2R).numpy())
+            return orc.interp_map(bo.abs(), inds, wgts)
+        Vo = Vo + orc.rime_forward(sp.double(), zenaz, beam_fn, bls, blvecs, freqs.cpu(), fov=180.0)
+    (Vo.real ** 2 + Vo.imag ** 2).sum().backward()
+    assert relmax(V, Vo, "healpix_composite/float64/V") < 1e-10
+    assert relmax(beam.params.grad, bo.grad, "healpix_composite/float64/dbeam") < 1e-9
+
+
+def test_float32_frequency_grid_takes_exact_path():
+    """A frequency grid rounded to float32 (+-8 Hz jitter) is not uniform enough for the rotation
+    recurrence on long baselines: RIME must detect it and evaluate every channel directly, with
+    the same accuracy."""
+    rime = workloads.point_airy(400, 96, 2, DEV, torch.float32, layout='hera350', bls='all')
+    rime.setup_sim_bls(rime.sim_bls[::400])
+    f32grid = torch.linspace(100e6, 200e6, 96, dtype=torch.float32).double().to(DEV)
+    rime.array.set_freqs(f32grid)
+    rime.beam.freqs = f32grid
+    rime.sky.R.freqs = f32grid.float()
+    rime.clear_geometry_cache()
+    rime._bl_meta = {}
+    with torch.no_grad():
+        V = rime().data
+    assert list(rime._bl_meta.values()) == [False]
+    Vo = _oracle_of_workload(rime, 'airy', list(range(len(rime.sim_bls))), slice(None))
+    assert relmax(V, Vo, "f32grid_exact_path/V") < 1e-5
