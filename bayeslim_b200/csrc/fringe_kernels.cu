@@ -61,7 +61,6 @@ fringe_sum_fwd_kernel(const T* __restrict__ A, const double* __restrict__ shat,
     const int ntiles = (un.z - un.y) / SRC_TILE;
     const int b = blockIdx.x * FWD_THREADS + tid;
     const bool valid = b < nbl;
-    const bool warp_live = blockIdx.x * FWD_THREADS + (tid & ~31) < nbl;
     double bx = 0.0, by = 0.0, bz = 0.0;
     if (valid) {
         const double* p = blv + 4 * (size_t)b;
@@ -99,13 +98,11 @@ fringe_sum_fwd_kernel(const T* __restrict__ A, const double* __restrict__ shat,
     for (int it = 0; it < ntiles; ++it) {
         const int stage = it & 1;
         if (tid == 0 && it + 1 < ntiles) issue(it + 1, stage ^ 1);
+        mbar_wait(&bars[stage], (it >> 1) & 1);
         const T* As = reinterpret_cast<const T*>(smem + stage * SM::STAGE_BYTES);
         const double4* Ss =
             reinterpret_cast<const double4*>(smem + stage * SM::STAGE_BYTES + SM::A_BYTES);
-        // a warp whose 32 baselines all lie beyond Nbl only keeps the barrier protocol
-        if (warp_live) mbar_wait(&bars[stage], (it >> 1) & 1);
-        if (!warp_live) {
-        } else if (UNIFORM) {
+        if (UNIFORM) {
             // software pipeline: the seeds of source s+1 (float64 phase reduction + trigonometry,
             // a long dependent chain that uses no FP32-pipe throughput) are issued inside the
             // FFMA2 stream of source s, so a warp never leaves the FP32 pipe idle between sources
@@ -346,7 +343,6 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
     const int ntiles = (un.z - un.y) / SRC_TILE;
     const int b = blockIdx.x * FWD_THREADS + tid;
     const bool valid = b < nbl;
-    const bool warp_live = blockIdx.x * FWD_THREADS + (tid & ~31) < nbl;
     double bx = 0.0, by = 0.0, bz = 0.0;
     constexpr bool PACKED = std::is_same<T, float>::value && UNIFORM;
     // pre-scaled cotangent G'_k = nu_k G_k of this thread's baseline: scalar arrays, or (re, im)
@@ -409,12 +405,11 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
     for (int it = 0; it < ntiles; ++it) {
         const int stage = it & 1;
         if (tid == 0 && it + 1 < ntiles) issue(it + 1, stage ^ 1);
-        if (warp_live) mbar_wait(&bars[stage], (it >> 1) & 1);
+        mbar_wait(&bars[stage], (it >> 1) & 1);
         const T* As = reinterpret_cast<const T*>(smem + stage * SM::STAGE_BYTES);
         const double4* Ss =
             reinterpret_cast<const double4*>(smem + stage * SM::STAGE_BYTES + SM::A_BYTES);
-        if (!warp_live) {
-        } else if (UNIFORM) {
+        if (UNIFORM) {
             T zr, zi, wr, wi;
             {
                 const double4 sh = Ss[0];
