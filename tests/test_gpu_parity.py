@@ -496,3 +496,40 @@ def test_float32_frequency_grid_takes_exact_path():
     assert list(rime._bl_meta.values()) == [False]
     Vo = _oracle_of_workload(rime, 'airy', list(range(len(rime.sim_bls))), slice(None))
     assert relmax(V, Vo, "f32grid_exact_path/V") < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_edge_cases_empty_single_and_degenerate(dtype):
+    """Empty and degenerate shapes the reference handles implicitly: no source above the horizon
+    (every time empty), a single frequency channel, a single baseline, an autocorrelation only."""
+    g = torch.Generator().manual_seed(31)
+    # (a) one channel, one (zero-length) baseline, ragged tiny source counts
+    zen = [torch.tensor([10.0, 50.0, 80.0], dtype=torch.float64), torch.zeros(0, dtype=torch.float64)]
+    az = [torch.tensor([0.0, 120.0, 300.0], dtype=torch.float64), torch.zeros(0, dtype=torch.float64)]
+    geom = ops.Geometry([z.to(DEV) for z in zen], [a.to(DEV) for a in az], DEV)
+    freqs = torch.tensor([150e6], dtype=torch.float64)
+    X = [torch.rand(1, 1, 3, generator=g, dtype=torch.float64), torch.zeros(1, 1, 0, dtype=torch.float64)]
+    for blv in (torch.zeros(1, 3, dtype=torch.float64), torch.tensor([[14.6, 0.0, 0.0]], dtype=torch.float64)):
+        A = ops.pack_planes(geom, [x.to(device=DEV, dtype=dtype) for x in X])
+        V = ops.fringe_sum(A, blv.to(DEV), geom, freqs.to(DEV), 1)
+        Vo = _oracle_fringe_sum([X[0]], zen[:1], az[:1], blv, freqs)
+        assert V.shape == (1, 1, 2, 1)
+        assert relmax(V[:, :, :1], Vo) < TOL[dtype]
+        assert float(V[:, :, 1].abs().max()) == 0.0          # the empty time contributes exactly 0
+    # (b) every time empty: S == 0
+    geom0 = ops.Geometry([torch.zeros(0, dtype=torch.float64, device=DEV)] * 2,
+                         [torch.zeros(0, dtype=torch.float64, device=DEV)] * 2, DEV)
+    A0 = ops.pack_planes(geom0, [torch.zeros(1, 4, 0, dtype=dtype, device=DEV, requires_grad=True)] * 2)
+    b0 = torch.rand(5, 3, generator=g, dtype=torch.float64).to(DEV).requires_grad_(True)
+    f4 = torch.linspace(1e8, 2e8, 4, dtype=torch.float64, device=DEV)
+    V0 = ops.fringe_sum(A0, b0, geom0, f4, 4)
+    assert V0.shape == (1, 5, 2, 4) and float(V0.abs().max()) == 0.0
+    V0.real.sum().backward()
+    assert float(b0.grad.abs().max()) == 0.0
+    # (c) RIME with a field of view so narrow that nothing is ever inside it
+    rime = workloads.point_airy(50, 8, 2, DEV, dtype)
+    rime.beam.fov = 1e-6
+    rime.clear_geometry_cache()
+    with torch.no_grad():
+        Vn = rime().data
+    assert Vn.shape == (1, 1, 666, 2, 8) and float(Vn.abs().max()) == 0.0
