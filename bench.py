@@ -211,7 +211,21 @@ def cpu_reference(workload, steps, warmup, threads=None):
 
 
 # --------------------------------------------------------------------------- main
+def emit(line):
+    """Print the one JSON line on the process's ORIGINAL stdout (fd saved in main)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # libraries (NCCL's version banner, torch warnings) may write to fd 1; keep stdout clean for
+    # the single JSON line the driver parses by routing everything else to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -242,7 +256,7 @@ def main():
                     e2e=dict(value=r["value"], unit=unit, h2d_bytes_per_step=0,
                              d2h_bytes_per_step=0),
                     gpu_launches=0)
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch.distributed as dist
@@ -273,7 +287,7 @@ def main():
         if e2e_buffers is not None:
             for p, h in zip(params, e2e_buffers["h_out"]):
                 h.copy_(p.grad, non_blocking=True)
-            e2e_buffers["loss"] = float(loss)           # D2H + sync
+            e2e_buffers["loss"] = float(loss.detach())  # D2H + sync
         return loss
 
     def barrier():
@@ -411,7 +425,7 @@ def main():
         r = cpu_reference(args.workload, 1, 1)
         line["cpu_baseline"] = dict(value=r["value"], unit=unit, cores=r["cores"], kind="port",
                                     sample=r["sample"])
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
