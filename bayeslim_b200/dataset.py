@@ -73,7 +73,7 @@ class VisData(TensorData):
 
     def setup_meta(self, telescope=None, antpos=None):
         self.telescope = telescope
-        if antpos is not None and not isinstance(antpos, utils.AntposDict):
+        if antpos is not None and not (hasattr(antpos, 'ants') and hasattr(antpos, 'antvecs')):
             antpos = utils.AntposDict(list(antpos.keys()), list(antpos.values()))
         self.antpos = antpos
         self.ants = antpos.ants if antpos is not None else None

@@ -29,6 +29,33 @@ from . import utils, dataset, beam_model, ops
 from .dataset import VisData
 
 
+# ---- beam accessors written against the REFERENCE PixelBeam attribute set (params, p0, fov,
+# ant2beam, skycut_cache/query_cache/set_skycut_cache), so that reference beam objects can be
+# handed to this RIME unchanged
+def _beam_params(beam):
+    return beam.params if getattr(beam, 'p0', None) is None else beam.params + beam.p0
+
+
+def _beam_sky_cut(beam, zen):
+    """FOV cut of beam_model.py:221-224 (strict zen < fov/2; everything for fov >= 360)."""
+    cached = beam.query_cache(zen) if getattr(beam, 'skycut_cache', False) else None
+    if cached is not None:
+        return cached
+    cut = torch.where(zen < beam.fov / 2)[0] if beam.fov < 360 else slice(None)
+    if getattr(beam, 'skycut_cache', False):
+        beam.set_skycut_cache(zen, cut, device=getattr(beam, 'skycut_device', None))
+    return cut
+
+
+def _beam_model_pairs(beam, bls):
+    """Sorted unique (model_i, model_j) pairs and the pair index of every baseline
+    (beam_model.py:303-305, 366-367)."""
+    pairs = [(beam.ant2beam[b[0]], beam.ant2beam[b[1]]) for b in bls]
+    uniq = sorted(set(pairs))
+    lookup = {mp: i for i, mp in enumerate(uniq)}
+    return uniq, [lookup[p] for p in pairs]
+
+
 class _GeometryRecord:
     """Per (sky component, time group) device tables, built once and reused by every forward."""
 
@@ -241,7 +268,7 @@ class RIME(utils.Module):
             az = torch.as_tensor(za[1]).to(dev, torch.float64)
             tkey = (sky_comp.name, len(ra), time)
             zen._arr_hash = tkey
-            cut = self.beam.sky_cut(zen)
+            cut = _beam_sky_cut(self.beam, zen)
             if isinstance(cut, slice):
                 cut = torch.arange(len(zen), device=dev)
             cut = cut.to(dev)
@@ -275,7 +302,7 @@ class RIME(utils.Module):
         dtype = sky.dtype
         if dtype not in rec.airy:
             rec.airy[dtype] = ops.AiryTable(rec.geom, rec.cuts, rec.zen, rec.az, sky.shape[-1], dtype)
-        p = b.total_params().to(dev)
+        p = _beam_params(b).to(dev)
         f64 = self._freqs64(b, dev)
         planes = [ops.build_airy(sky[0, 0], p[ipol, 0, 0, 0], rec.geom, rec.airy[dtype], f64,
                                  freq_ratio=R.freq_ratio, square=True,
@@ -287,7 +314,7 @@ class RIME(utils.Module):
         b, R = self.beam, self.beam.R
         dtype = sky.dtype
         if R.beam_cache is None:
-            R.set_beam_cache(b.total_params())
+            R.set_beam_cache(_beam_params(b))
         bmap = R.beam_cache.to(dev)
         key = (id(R), R.interp_mode, dtype)
         if key not in rec.interp:
@@ -303,8 +330,8 @@ class RIME(utils.Module):
         """Any response function: beam and beam*sky*beam^H in torch on the device (cheap: not
         multiplied by Nbl), then one real plane per (pol product, model pair, re|im)."""
         b = self.beam
-        p = b.total_params()
-        modelpairs, mp_idx = b.model_pairs(self.sim_bls)
+        p = _beam_params(b)
+        modelpairs, mp_idx = _beam_model_pairs(b, self.sim_bls)
         per_time = []
         for cut, zen, az in zip(rec.cuts, rec.zen, rec.az):
             beam = b.R(p, zen, az, b.freqs)

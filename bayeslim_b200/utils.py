@@ -198,11 +198,14 @@ class AntposDict:
     def __init__(self, ants, antvecs):
         self.ants = [int(a) for a in ants]
         self._ant_idx = {a: i for i, a in enumerate(self.ants)}
-        try:
-            self.antvecs = torch.as_tensor(np.asarray(antvecs) if not isinstance(
-                antvecs, torch.Tensor) else antvecs)
-        except (ValueError, TypeError):
-            self.antvecs = torch.vstack(list(antvecs))
+        if isinstance(antvecs, torch.Tensor):
+            self.antvecs = antvecs
+        else:
+            antvecs = list(antvecs)
+            if len(antvecs) and isinstance(antvecs[0], torch.Tensor):
+                self.antvecs = torch.vstack([a.reshape(1, -1) for a in antvecs])
+            else:
+                self.antvecs = torch.as_tensor(np.asarray(antvecs))
 
     def keys(self):
         return iter(self.ants)
