@@ -59,7 +59,7 @@ fringe_sum_fwd_kernel(const T* __restrict__ A, const double* __restrict__ shat,
     const int nfp = gridDim.y * KC;
     const int4 un = units[blockIdx.z];
     const int ntiles = (un.z - un.y) / SRC_TILE;
-    const int b = blockIdx.x * FWD_THREADS + tid;
+    const int b = blockIdx.x * blockDim.x + tid;      // block = 128, 64 or 32 baselines
     const bool valid = b < nbl;
     double bx = 0.0, by = 0.0, bz = 0.0;
     if (valid) {
@@ -70,7 +70,7 @@ fringe_sum_fwd_kernel(const T* __restrict__ A, const double* __restrict__ shat,
     }
     const ChunkFreq cf = chunk_freq(freqs, nfreq, chunk, KC, sgn_over_c);
     if (!UNIFORM) {
-        for (int k = tid; k < KC; k += FWD_THREADS) {
+        for (int k = tid; k < KC; k += blockDim.x) {
             int f = min(chunk * KC + k, nfreq - 1);
             kf[k] = sgn_over_c * freqs[f];
         }
@@ -341,7 +341,7 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
     const int nfp = nchunk * KC;
     const int4 un = units[blockIdx.z];
     const int ntiles = (un.z - un.y) / SRC_TILE;
-    const int b = blockIdx.x * FWD_THREADS + tid;
+    const int b = blockIdx.x * blockDim.x + tid;      // block = 128, 64 or 32 baselines
     const bool valid = b < nbl;
     double bx = 0.0, by = 0.0, bz = 0.0;
     constexpr bool PACKED = std::is_same<T, float>::value && UNIFORM;
@@ -379,7 +379,7 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
     }
     const ChunkFreq cf = chunk_freq(freqs, nfreq, chunk, KC, sgn_over_c);
     if (!UNIFORM) {
-        for (int k = tid; k < KC; k += FWD_THREADS) {
+        for (int k = tid; k < KC; k += blockDim.x) {
             int f = min(chunk * KC + k, nfreq - 1);
             kf[k] = sgn_over_c * freqs[f];
         }
@@ -470,6 +470,16 @@ fringe_sum_bwd_bl_kernel(const T* __restrict__ Gp, const T* __restrict__ A,
 // -------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------
+// baselines per CTA: 128 unless a ragged baseline count would idle more than ~4% of the lanes
+// (e.g. the 63 unique baselines of HERA-37), then 64 or 32
+static inline int pick_bl_block(int nbl) {
+    auto padded = [&](int n) { return ((nbl + n - 1) / n) * n; };
+    const double best = (double)padded(32);
+    if (padded(128) <= 1.04 * best) return 128;
+    if (padded(64) <= 1.04 * best) return 64;
+    return 32;
+}
+
 template <typename T>
 int launch_fwd(const T* A, const double* shat, const double* blv, const double* freqs,
                const int* units, int nunits, int nbl, int nfreq, long long S, int conj, int uniform,
@@ -479,7 +489,8 @@ int launch_fwd(const T* A, const double* shat, const double* blv, const double* 
     constexpr int KC = Cfg<T>::KC;
     const int nchunk = (nfreq + KC - 1) / KC;
     if (nchunk > 65535 || nunits > 65535) return set_error("fringe_sum_fwd: grid too large");
-    dim3 grid((nbl + FWD_THREADS - 1) / FWD_THREADS, nchunk, nunits);
+    const int nthr = pick_bl_block(nbl);
+    dim3 grid((nbl + nthr - 1) / nthr, nchunk, nunits);
     const double sgn_over_c = (conj ? -1.0 : 1.0) / C_LIGHT;
     const int smem = FwdSmem<T>::TOTAL;
     static bool attr_set = false;
@@ -491,11 +502,11 @@ int launch_fwd(const T* A, const double* shat, const double* blv, const double* 
         attr_set = true;
     }
     if (uniform)
-        fringe_sum_fwd_kernel<T, true><<<grid, FWD_THREADS, smem, st>>>(
+        fringe_sum_fwd_kernel<T, true><<<grid, nthr, smem, st>>>(
             A, shat, blv, freqs, reinterpret_cast<const int4*>(units), nbl, nfreq, S, sgn_over_c,
             vpart);
     else
-        fringe_sum_fwd_kernel<T, false><<<grid, FWD_THREADS, smem, st>>>(
+        fringe_sum_fwd_kernel<T, false><<<grid, nthr, smem, st>>>(
             A, shat, blv, freqs, reinterpret_cast<const int4*>(units), nbl, nfreq, S, sgn_over_c,
             vpart);
     return check_launch("fringe_sum_fwd");
@@ -553,7 +564,8 @@ int launch_bwd_bl(const T* Gp, const T* A, const double* shat, const double* blv
     constexpr int KC = Cfg<T>::KC;
     const int nchunk = (nfreq + KC - 1) / KC;
     if (nchunk > 65535 || nunits > 65535) return set_error("fringe_sum_bwd_bl: grid too large");
-    dim3 grid((nbl + FWD_THREADS - 1) / FWD_THREADS, nchunk, nunits);
+    const int nthr = pick_bl_block(nbl);
+    dim3 grid((nbl + nthr - 1) / nthr, nchunk, nunits);
     const double sgn_over_c = (conj ? -1.0 : 1.0) / C_LIGHT;
     const int smem = FwdSmem<T>::TOTAL;
     static bool attr_set = false;
@@ -565,11 +577,11 @@ int launch_bwd_bl(const T* Gp, const T* A, const double* shat, const double* blv
         attr_set = true;
     }
     if (uniform)
-        fringe_sum_bwd_bl_kernel<T, true><<<grid, FWD_THREADS, smem, st>>>(
+        fringe_sum_bwd_bl_kernel<T, true><<<grid, nthr, smem, st>>>(
             Gp, A, shat, blv, freqs, reinterpret_cast<const int4*>(units), nbl, nt, nfreq, S,
             sgn_over_c, dblpart);
     else
-        fringe_sum_bwd_bl_kernel<T, false><<<grid, FWD_THREADS, smem, st>>>(
+        fringe_sum_bwd_bl_kernel<T, false><<<grid, nthr, smem, st>>>(
             Gp, A, shat, blv, freqs, reinterpret_cast<const int4*>(units), nbl, nt, nfreq, S,
             sgn_over_c, dblpart);
     return check_launch("fringe_sum_bwd_bl");

@@ -147,7 +147,7 @@ class Geometry:
         if key in self._unit_cache:
             return self._unit_cache[key]
         tile = _lib.SRC_TILE
-        base = ((nbl + 127) // 128) * nchunk
+        base = ((nbl + 63) // 64) * nchunk // 2 + 1
         target = 24 * sm_count
         want = max(self.nt, -(-target // max(base, 1)))
         per = max(self.S, 1) / want
@@ -155,10 +155,13 @@ class Geometry:
         rows, ubeg = [], [0]
         for t in range(self.nt):
             s0, s1 = self.toff[t], self.toff[t + 1]
-            while s0 < s1:
-                e = min(s0 + unit, s1)
-                rows.append((t, s0, e, 0))
-                s0 = e
+            n = -(-(s1 - s0) // unit)                       # units of this time ...
+            if n:
+                step = -(-(s1 - s0) // (n * tile)) * tile   # ... of (nearly) equal length
+                while s0 < s1:
+                    e = min(s0 + step, s1)
+                    rows.append((t, s0, e, 0))
+                    s0 = e
             ubeg.append(len(rows))
         units = torch.as_tensor(np.asarray(rows, dtype=np.int32).reshape(-1, 4), device=self.device)
         out = (units, ubeg)

@@ -136,6 +136,11 @@ def build_workload(name, nt, device, rank, world):
         desc = ("C2: HERA-37 (666 cross baselines) x 10k point sources x Airy beam x 256 freqs, "
                 "fwd+bwd to sky")
         grads = "sky"
+    elif name == "c1":
+        rime = workloads.point_airy(1000, 64, nt * world, device, torch.float32, bls='uniq')
+        desc = ("C1: HERA-37 (63 unique baselines) x 1k point sources x Airy beam x 64 freqs, "
+                "fwd+bwd to sky")
+        grads = "sky"
     else:
         raise ValueError(name)
     if world > 1:                      # weak scaling: rank r owns times [r*nt, (r+1)*nt)
@@ -165,13 +170,19 @@ def cpu_reference(workload, steps, warmup, threads=None):
         nbl, nf = 32, 128
         rime = workloads.pixel_interp(128, nf, 1, 'cpu', dt, n_bl=nbl, antpos_param=True)
         sample = "C3 slice: %d baselines x %d freqs x 1 time x all sources above horizon" % (nbl, nf)
+    elif workload == "c1":
+        nbl, nf = 63, 64
+        rime = workloads.point_airy(1000, nf, 10, 'cpu', dt, bls='uniq')
+        sample = "C1 at full size: 63 unique baselines x 64 freqs x 10 times x 1k sources"
     else:
         nbl, nf = 63, 256
         rime = workloads.point_airy(10000, nf, 1, 'cpu', dt, bls='uniq')
         sample = "C2 slice: 63 unique baselines x %d freqs x 1 of 60 times x 10k sources" % nf
     ra, dec = rime.sky.angs[0], rime.sky.angs[1]
-    za = rime.telescope.eq2top(rime.sim_times[0], ra, dec)
-    zenaz = [(za[0].to(dt), za[1].to(dt))]
+    zenaz = []
+    for tm in rime.sim_times:
+        za = rime.telescope.eq2top(tm, ra, dec)
+        zenaz.append((za[0].to(dt), za[1].to(dt)))
     freqs = rime.array.freqs.to(dt)
     sp = rime.sky.params.detach().clone().requires_grad_(True)
     bp = rime.beam.params.detach().clone().requires_grad_(workload == "c3")
@@ -198,7 +209,7 @@ def cpu_reference(workload, steps, warmup, threads=None):
         loss.backward()
         return float(loss)
 
-    ns = int((zenaz[0][0] < 90).sum())
+    ns = sum(int((z < 90).sum()) for z, _ in zenaz)
     evals = ns * len(bls) * nf
     for _ in range(warmup):
         step()
@@ -231,14 +242,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c1"])
     ap.add_argument("--nt", type=int, default=None, help="times per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    nt = args.nt or (2 if args.workload == "c3" else 60)
+    nt = args.nt or {"c3": 2, "c2": 60, "c1": 10}[args.workload]
     unit = "source*baseline*freq*time evals/s (fwd+bwd)"
 
     if args.impl == "reference":
