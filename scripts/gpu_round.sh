@@ -22,6 +22,8 @@ echo "smoke exit $?"; tail -n 5 gpurun_out/smoke.log
 if [ "$1" != "quick" ]; then
 timeout 900 python bench.py --workload c2 --steps 3 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
 echo "bench c2 exit $?"; cat gpurun_out/bench_c2.json; tail -n 5 gpurun_out/bench_c2.err
+timeout 300 python bench.py --workload c1 --steps 5 --warmup 3 > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err
+echo "bench c1 exit $?"; cut -c1-300 gpurun_out/bench_c1.json; tail -n 3 gpurun_out/bench_c1.err
 timeout 1500 python bench.py --workload c3 --nt 1 --steps 2 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err
 echo "bench c3 exit $?"; cat gpurun_out/bench_c3.json; tail -n 5 gpurun_out/bench_c3.err
 fi
