@@ -191,11 +191,13 @@ class PixelBeam(utils.Module):
 
 def perceived_sky(beam, sky, modelpairs, Npol, Nvec, powerbeam):
     """beam (Npol, Nvec, Nmodel, Nf, Ns), sky (Nvec, Nvec, Nf, Ns) -> (Npol|2, Npol|1, Nmp, Nf, Ns).
+    The trailing (Nf, Ns) axes may be any broadcastable trailing shape (RIME passes tensors in
+    the tiled layout (nchunk, S, KC)).
     The four polarisation modes of beam_model.py:334-363; mixed real/complex operands of the
     Jones product are promoted to a common dtype (the reference's einsum raises otherwise)."""
     i1 = torch.as_tensor([mp[0] for mp in modelpairs], device=beam.device)
     beam1 = beam.index_select(2, i1)
-    if sky.ndim == 4:
+    if sky.ndim == beam.ndim - 1:          # give the sky a model-pair axis
         sky = sky[:, :, None]
     if powerbeam:
         if Npol == 1:

@@ -183,15 +183,19 @@ build_interp_kernel(const T* __restrict__ bmap, long long ldb, const int* __rest
     const int pix = (s < ns) ? cut[s] : -1;       // cut < 0 marks a padding entry
     const bool live = pix >= 0;
     Nbr<T, NNN> nb;
-    if (live) nb.load(inds, wgts, nnn, s);
+    if (live && bmap) nb.load(inds, wgts, nnn, s);
     // all gathers of this thread's KC/ROWS channels are issued before they are consumed
     T v[KC / ROWS];
 #pragma unroll
     for (int i = 0; i < KC / ROWS; ++i) {
         const int f = chunk * KC + ty + i * ROWS;
         v[i] = 0;
-        if (live && f < nfreq)
-            v[i] = nb.at(bmap + (size_t)f * ldb, inds, wgts, nnn, s) * sky[(size_t)f * lds + pix];
+        if (live && f < nfreq) {
+            // bmap == NULL: pure FOV gather of the sky; sky == NULL: pure beam interpolation
+            const T b = bmap ? nb.at(bmap + (size_t)f * ldb, inds, wgts, nnn, s) : (T)1;
+            const T I = sky ? sky[(size_t)f * lds + pix] : (T)1;
+            v[i] = b * I;
+        }
     }
 #pragma unroll
     for (int i = 0; i < KC / ROWS; ++i) tile[ty + i * ROWS][tx] = v[i];
@@ -226,7 +230,7 @@ build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, lo
         return;
     }
     Nbr<T, NNN> nb;
-    nb.load(inds, wgts, nnn, s);
+    if (bmap) nb.load(inds, wgts, nnn, s);
     T b[KC / ROWS], I[KC / ROWS];
 #pragma unroll
     for (int i = 0; i < KC / ROWS; ++i) {
@@ -234,8 +238,8 @@ build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, lo
         b[i] = 0;
         I[i] = 0;
         if (f < nfreq) {
-            b[i] = nb.at(bmap + (size_t)f * ldb, inds, wgts, nnn, s);
-            I[i] = sky[(size_t)f * lds + pix];
+            b[i] = bmap ? nb.at(bmap + (size_t)f * ldb, inds, wgts, nnn, s) : (T)1;
+            I[i] = sky ? sky[(size_t)f * lds + pix] : (T)1;
         }
     }
 #pragma unroll

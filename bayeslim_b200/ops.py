@@ -273,40 +273,46 @@ class InterpTable:
 
 
 class _BuildInterp(torch.autograd.Function):
+    """A = interp(bmap) * gather(sky); either operand may be None (factor 1)."""
+
     @staticmethod
     def forward(ctx, sky, bmap, geom, tab):
+        ref = sky if sky is not None else bmap
         _need_cuda(sky, bmap)
-        dtype, sfx = sky.dtype, _sfx(sky.dtype)
-        sky = sky.contiguous()
-        bmap = bmap.to(dtype).contiguous()
-        nfreq = sky.shape[0]
-        assert bmap.shape[0] == nfreq
+        dtype, sfx = ref.dtype, _sfx(ref.dtype)
+        sky = sky.contiguous() if sky is not None else None
+        bmap = bmap.to(dtype).contiguous() if bmap is not None else None
+        nfreq = ref.shape[0]
         kc = _lib.KC[sfx]
         S = max(geom.S, 1)
-        A = torch.empty(1, nchunks(nfreq, dtype), S, kc, dtype=dtype, device=sky.device)
+        A = torch.empty(1, nchunks(nfreq, dtype), S, kc, dtype=dtype, device=ref.device)
         if geom.S > 0:
-            _call("build_interp", sfx, bmap, bmap.shape[1], tab.inds, tab.wgts, tab.nnn, sky,
-                  sky.shape[1], tab.cut, nfreq, geom.S, geom.S, 0, geom.S, A[0])
+            _call("build_interp", sfx, bmap, bmap.shape[1] if bmap is not None else 0, tab.inds,
+                  tab.wgts, tab.nnn, sky, sky.shape[1] if sky is not None else 0, tab.cut, nfreq,
+                  geom.S, geom.S, 0, geom.S, A[0])
+        else:
+            A.zero_()
         ctx.save_for_backward(sky, bmap)
-        ctx.geom, ctx.tab = geom, tab
+        ctx.geom, ctx.tab, ctx.nfreq = geom, tab, nfreq
         return A
 
     @staticmethod
     def backward(ctx, dA):
         sky, bmap = ctx.saved_tensors
-        geom, tab = ctx.geom, ctx.tab
+        geom, tab, nfreq = ctx.geom, ctx.tab, ctx.nfreq
         dA = dA.contiguous()
-        sfx = _sfx(sky.dtype)
-        nfreq = sky.shape[0]
-        need_sky, need_beam = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        sfx = _sfx(dA.dtype)
+        need_sky = sky is not None and ctx.needs_input_grad[0]
+        need_beam = bmap is not None and ctx.needs_input_grad[1]
         dsky = torch.zeros_like(sky) if need_sky else None
         dbmap = torch.zeros_like(bmap) if need_beam else None
         if geom.S > 0 and (need_sky or need_beam):
             S = geom.S
-            dIs = torch.empty(nfreq, S, dtype=sky.dtype, device=sky.device) if need_sky else None
-            dBI = torch.empty(nfreq, S, dtype=sky.dtype, device=sky.device) if need_beam else None
-            _call("build_interp_bwd", sfx, dA[0], bmap, bmap.shape[1], tab.inds, tab.wgts, tab.nnn,
-                  sky, sky.shape[1], tab.cut, nfreq, S, 0, S, None, dBI, S, dIs)
+            dIs = torch.empty(nfreq, S, dtype=dA.dtype, device=dA.device) if need_sky else None
+            dBI = torch.empty(nfreq, S, dtype=dA.dtype, device=dA.device) if need_beam else None
+            _call("build_interp_bwd", sfx, dA[0], bmap, bmap.shape[1] if bmap is not None else 0,
+                  tab.inds, tab.wgts, tab.nnn, sky, sky.shape[1] if sky is not None else 0, tab.cut,
+                  nfreq, S, 0, S, None, dBI, S, dIs)
             if need_sky:
                 _call("gather_times", sfx, dIs, S, tab.pos, geom.nt, tab.npix_sky, nfreq, dsky,
                       sky.shape[1])
@@ -318,7 +324,8 @@ class _BuildInterp(torch.autograd.Function):
 
 
 def build_interp(sky, bmap, geom, tab):
-    """sky (Nf, Npix), bmap (Nf, Npb) -> A (1, nchunk, S, KC); one launch for all times."""
+    """sky (Nf, Npix), bmap (Nf, Npb) -> A (1, nchunk, S, KC); one launch for all times.
+    sky=None: interpolated beam only; bmap=None: FOV-gathered sky only."""
     return _BuildInterp.apply(sky, bmap, geom, tab)
 
 

@@ -297,6 +297,14 @@ class RIME(utils.Module):
             return 'interp'
         return None
 
+    def _interp_pol_mode(self, sky):
+        """True when the beam is an interpolated pixel beam in a polarised / voltage / multi-model
+        mode: Jones and coherency planes are then built by the CUDA interpolation / gather
+        kernels directly in the tiled layout and combined element-wise."""
+        b, R = self.beam, self.beam.R
+        return (R.__class__.__name__ == 'PixelResponse' and getattr(R, 'Rchi', None) is None
+                and not (getattr(b, 'theta_x', 0) > 0 or getattr(b, 'theta_y', 0) > 0))
+
     def _build_airy(self, sky, rec, dev):
         b, R = self.beam, self.beam.R
         dtype = sky.dtype
@@ -316,13 +324,8 @@ class RIME(utils.Module):
         if R.beam_cache is None:
             R.set_beam_cache(_beam_params(b))
         bmap = R.beam_cache.to(dev)
-        key = (id(R), R.interp_mode, dtype)
-        if key not in rec.interp:
-            tabs = [R.get_interp(z, a) for z, a in zip(rec.zen, rec.az)]
-            rec.interp[key] = ops.InterpTable(rec.geom, rec.cuts, [t[0] for t in tabs],
-                                              [t[1] for t in tabs], sky.shape[-1], bmap.shape[-1],
-                                              dtype)
-        planes = [ops.build_interp(sky[0, 0], bmap[ipol, 0, 0], rec.geom, rec.interp[key])
+        tab = self._interp_table(sky, rec, bmap, dtype)
+        planes = [ops.build_interp(sky[0, 0], bmap[ipol, 0, 0], rec.geom, tab)
                   for ipol in range(b.Npol)]
         return planes[0] if len(planes) == 1 else torch.cat(planes, dim=0)
 
@@ -340,6 +343,48 @@ class RIME(utils.Module):
             per_time.append(beam_model.perceived_sky(beam, cut_sky, modelpairs, b.Npol, b.Nvec,
                                                      b.powerbeam))
         return per_time, modelpairs, mp_idx
+
+    def _interp_table(self, sky, rec, bmap, dtype):
+        R = self.beam.R
+        key = (id(R), R.interp_mode, dtype)
+        if key not in rec.interp:
+            tabs = [R.get_interp(z, a) for z, a in zip(rec.zen, rec.az)]
+            rec.interp[key] = ops.InterpTable(rec.geom, rec.cuts, [t[0] for t in tabs],
+                                              [t[1] for t in tabs], sky.shape[-1], bmap.shape[-1],
+                                              dtype)
+        return rec.interp[key]
+
+    def _tiled_pol_planes(self, sky, rec, dev):
+        """Perceived sky of the polarised modes (beam_model.py:343-363) in the tiled layout:
+        every Jones element J[a, b, model] is interpolated and every coherency element C[b, c]
+        gathered through the FOV cut by the CUDA builder (one launch each, all times), then
+        P = J C J^H is an element-wise torch expression on (nchunk, S, KC) tensors.  Nothing of
+        shape (.., Nf, Ns, Nneighbours) is ever formed (the reference's gather temp is 25 GB per
+        time at nside 256)."""
+        b, R = self.beam, self.beam.R
+        rdtype = ops._real(sky.dtype)
+        if R.beam_cache is None:
+            R.set_beam_cache(_beam_params(b))
+        bmap = R.beam_cache.to(dev)
+        tab = self._interp_table(sky, rec, bmap, rdtype)
+
+        def tiled(x2d, is_beam):
+            if x2d.is_complex():
+                return torch.complex(tiled(x2d.real, is_beam), tiled(x2d.imag, is_beam))
+            x2d = x2d.to(rdtype)
+            A = ops.build_interp(None, x2d, rec.geom, tab) if is_beam \
+                else ops.build_interp(x2d, None, rec.geom, tab)
+            return A[0]
+
+        J = torch.stack([torch.stack([torch.stack([tiled(bmap[a, v, m], True)
+                                                   for m in range(bmap.shape[2])])
+                                      for v in range(bmap.shape[1])])
+                         for a in range(bmap.shape[0])])            # (Npol, Nvec, Nmodel, *tile)
+        C = torch.stack([torch.stack([tiled(sky[v, w], False) for w in range(sky.shape[1])])
+                         for v in range(sky.shape[0])])             # (Nvec, Nvec, *tile)
+        modelpairs, mp_idx = _beam_model_pairs(b, self.sim_bls)
+        psky = beam_model.perceived_sky(J, C, modelpairs, b.Npol, b.Nvec, b.powerbeam)
+        return psky, modelpairs, mp_idx
 
     # ------------------------------------------------------------------ forward
     def forward(self, *args, prior_cache=None, **kwargs):
@@ -372,8 +417,14 @@ class RIME(utils.Module):
                     else self._build_interp(sky, rec, dev)
                 V = ops.fringe_sum(A, blvecs, rec.geom, f64, nfreq, conj=False, uniform=uniform)
                 skyvis = V[:, None]                     # (Npol, 1, Nbl, Nt, Nf)
+            elif self._interp_pol_mode(sky):
+                psky, modelpairs, mp_idx = self._tiled_pol_planes(sky, rec, dev)
+                skyvis = self._sum_model_pairs(psky, None, modelpairs, mp_idx, sky, rec, dev,
+                                               blvecs, f64, nfreq, uniform)
             else:
-                skyvis = self._forward_generic(sky, rec, dev, blvecs, f64, nfreq, uniform)
+                per_time, modelpairs, mp_idx = self._generic_planes(sky, rec, dev)
+                skyvis = self._sum_model_pairs(None, per_time, modelpairs, mp_idx, sky, rec, dev,
+                                               blvecs, f64, nfreq, uniform)
             if self.verbose:
                 log("sky model {}/{} | {} elapsed".format(i + 1, len(sky_components),
                                                           elapsed_time(start)), verbose=True)
@@ -393,22 +444,31 @@ class RIME(utils.Module):
                       cov=None, history=self._history())
         return vd
 
-    def _forward_generic(self, sky, rec, dev, blvecs, f64, nfreq, uniform):
-        per_time, modelpairs, mp_idx = self._generic_planes(sky, rec, dev)
-        P, Q = per_time[0].shape[0], per_time[0].shape[1]
-        cplx = per_time[0].is_complex()
+    def _sum_model_pairs(self, tiled, per_time, modelpairs, mp_idx, sky, rec, dev, blvecs, f64,
+                         nfreq, uniform):
+        """Fringe-sum the perceived sky of every model pair over its own baselines.  The
+        perceived sky comes either already tiled, (P, Q, Nmp, nchunk, S, KC), or as per-time
+        row-major tensors (P, Q, Nmp, Nf, Ns_t) that are packed first.  Complex perceived skies
+        are split into real planes (V = V_re + i V_im)."""
+        ref = tiled if tiled is not None else per_time[0]
+        P, Q = ref.shape[0], ref.shape[1]
+        cplx = ref.is_complex()
+        # kernel precision follows the sky tensor (float64 frequency/angle inputs of a response
+        # function must not silently promote a float32 session, SURVEY 9.6)
+        rdtype = ops._real(sky.dtype)
         mp_idx_t = torch.as_tensor(mp_idx, device=dev)
         out = None
         for m in range(len(modelpairs)):
             sel = torch.where(mp_idx_t == m)[0]
-            planes = []
-            for X in per_time:
-                Xm = X[:, :, m].reshape(P * Q, X.shape[-2], X.shape[-1])
-                planes.append(torch.cat([Xm.real, Xm.imag], dim=0) if cplx else Xm)
-            # kernel precision follows the sky tensor (float64 frequency/angle inputs of a
-            # response function must not silently promote a float32 session)
-            rdtype = ops._real(sky.dtype)
-            A = ops.pack_planes(rec.geom, [pl.to(rdtype).contiguous() for pl in planes])
+            if tiled is not None:
+                Xm = tiled[:, :, m].reshape((P * Q,) + tuple(tiled.shape[3:]))
+                A = (torch.cat([Xm.real, Xm.imag], dim=0) if cplx else Xm).to(rdtype).contiguous()
+            else:
+                planes = []
+                for X in per_time:
+                    Xm = X[:, :, m].reshape(P * Q, X.shape[-2], X.shape[-1])
+                    planes.append(torch.cat([Xm.real, Xm.imag], dim=0) if cplx else Xm)
+                A = ops.pack_planes(rec.geom, [pl.to(rdtype).contiguous() for pl in planes])
             V = ops.fringe_sum(A, blvecs.index_select(0, sel), rec.geom, f64, nfreq, conj=False,
                                uniform=uniform)
             if cplx:

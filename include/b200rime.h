@@ -127,7 +127,10 @@ int b200rime_unpack_f64(const double* A, long long ldx, int nfreq, int ns, long 
  * Interpolated pixel beam (PixInterp.interp utils.py:833-841 + cut_sky_fov beam_model.py:1696
  * + beam*sky beam_model.py:341):
  *   A[f][soff+s] = ( sum_{i<nnn} bmap[f*ldb + inds[s][i]] * wgts[s][i] ) * sky[f*lds + cut[s]]
- * inds int32 [ns][nnn], wgts real [ns][nnn], cut int32 [ns]; cut[s] < 0 marks a padding entry
+ * bmap == NULL gives the pure FOV gather A = sky[f][cut[s]], sky == NULL the pure interpolation
+ * (factor 1 in place of the missing operand; used to build the Jones / coherency planes of the
+ * polarised modes, beam_model.py:343-363, which torch then combines element-wise in the tiled
+ * layout).  inds int32 [ns][nnn], wgts real [ns][nnn], cut int32 [ns]; cut[s] < 0 marks a padding entry
  * (A = 0), so one call with ns = ns_pad = S, soff = 0 builds every time of a group at once. */
 int b200rime_build_interp_f32(const float* bmap, long long ldb, const int* inds,
                               const float* wgts, int nnn, const float* sky, long long lds,

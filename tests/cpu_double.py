@@ -121,8 +121,9 @@ def _live(cut, ns):
 
 def build_interp(sfx, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, ns_pad, soff, S, A):
     live, c = _live(cut, ns)
-    B = _interp(bmap, inds[:ns].reshape(ns, nnn), wgts[:ns].reshape(ns, nnn))
-    X = B * sky[:, c] * live[None]
+    B = _interp(bmap, inds[:ns].reshape(ns, nnn), wgts[:ns].reshape(ns, nnn)) if bmap is not None else 1.0
+    I = sky[:, c] if sky is not None else 1.0
+    X = (B * I * live[None]).to(A.dtype).expand(nfreq, ns)
     pack(sfx, X.contiguous(), ns, nfreq, ns, ns_pad, soff, S, A)
 
 
@@ -130,13 +131,14 @@ def build_interp_bwd(sfx, dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, 
                      dBI, ldd, dIs):
     live, c = _live(cut, ns)
     g = _A_rows(dA, nfreq)[:, soff:soff + ns] * live[None]
-    B = _interp(bmap, inds[:ns].reshape(ns, nnn), wgts[:ns].reshape(ns, nnn))
+    B = _interp(bmap, inds[:ns].reshape(ns, nnn), wgts[:ns].reshape(ns, nnn)) if bmap is not None else 1.0
+    I = sky[:, c] if sky is not None else 1.0
     if dsky is not None:
         dsky.index_add_(1, c, (B * g).to(dsky.dtype))
     if dIs is not None:
         dIs[:, :ns] = B * g
     if dBI is not None:
-        dBI[:, :ns] = sky[:, c] * g
+        dBI[:, :ns] = I * g
 
 
 def gather_times(sfx, dIs, ldd, pos, nt, npix, nfreq, dsky, lds):
