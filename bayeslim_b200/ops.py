@@ -503,6 +503,190 @@ class _FringeSum(torch.autograd.Function):
         return dA, gbl, None, None, None, None, None
 
 
+# ----------------------------------------------------------- antenna-factorised fringe sum
+ANT_FWD_MIN_FILL = 0.55     # wanted pairs / computed pairs below which the baseline-owned K1 wins
+ANT_BWD_MIN_FILL = 0.40     # Nbl / na_pad^2 below which K2 + K3 win
+ANT_H_BUDGET = 4 << 30      # bytes of Hermitian cotangent matrix per backward sub-batch of times
+
+
+def _xpos(a):
+    """Position of antenna slot a (0..63) inside a 64-wide operand row (include/b200rime.h)."""
+    return (((a >> 1) & 1) << 5) | ((a >> 2) << 1) | (a & 1)
+
+
+class AntTiling:
+    """Tiling of a baseline list over 64 x 64 blocks of antenna pairs for the antenna-factorised
+    kernels.  i_idx / j_idx: antenna row (into antvecs) of the first / second antenna of every
+    baseline, whose vector is antvecs[j] - antvecs[i] (telescope_model.py:221-239)."""
+
+    def __init__(self, i_idx, j_idx, na, device):
+        T = _lib.ANT_TILE
+        i = np.asarray(i_idx, dtype=np.int64)
+        j = np.asarray(j_idx, dtype=np.int64)
+        nbl = len(i)
+        self.nbl, self.na = nbl, int(na)
+        self.nblk = max(1, -(-self.na // T))
+        self.na_pad = self.nblk * T
+        bi, bj = i // T, j // T
+        swap = (bi > bj) | ((bi == bj) & (i > j))        # fold onto the upper triangle
+        x = np.where(swap, j, i)
+        y = np.where(swap, i, j)
+        key = (x // T) * self.nblk + (y // T)
+        uniq, tid = np.unique(key, return_inverse=True)
+        self.ntile = len(uniq)
+        ar = np.arange(T)
+        tile_ant = -np.ones((self.ntile, 2 * T), dtype=np.int32)
+        for n, kq in enumerate(uniq):
+            xb, yb = divmod(int(kq), self.nblk)
+            ax, ay = xb * T + ar, yb * T + ar
+            tile_ant[n, :T] = np.where(ax < self.na, ax, -1)
+            tile_ant[n, T:] = np.where(ay < self.na, ay, -1)
+        flat = tid * T * T + (x % T) * T + (y % T)
+        self.unique = len(np.unique(flat)) == nbl         # a pair listed twice cannot be tiled
+        tile_bl = -np.ones(self.ntile * T * T, dtype=np.int32)
+        tile_bl[flat] = (np.arange(nbl) << 1) | swap
+        self.fill_fwd = nbl / max(self.ntile * T * T, 1)
+        self.fill_bwd = nbl / float(self.na_pad ** 2)
+        self.usable = (self.unique and nbl > 0 and self.fill_fwd >= ANT_FWD_MIN_FILL
+                       and self.fill_bwd >= ANT_BWD_MIN_FILL)
+        dev = torch.device(device)
+        self.tile_ant = torch.as_tensor(tile_ant, device=dev)
+        self.tile_bl = torch.as_tensor(tile_bl.reshape(self.ntile, T, T), device=dev)
+        self.i = torch.as_tensor(i, device=dev)
+        self.j = torch.as_tensor(j, device=dev)
+        # scatter coordinates of the Hermitian cotangent matrix (see include/b200rime.h):
+        # row a -> (block, position in block), column m -> (stage, index in stage)
+        st = _lib.ANT_STAGE
+        pos = np.asarray([_xpos(a) for a in range(T)], dtype=np.int64)
+        t = lambda v: torch.as_tensor(v, device=dev)
+        self.h_ji = (t(j // T), t(i // st), t(i % st), t(pos[j % T]))     # H[a = j][m = i] = G
+        cross = i != j
+        self.h_cross = t(np.nonzero(cross)[0])
+        self.h_auto = t(np.nonzero(~cross)[0])
+        ic, jc = i[cross], j[cross]
+        self.h_ij = (t(ic // T), t(jc // st), t(jc % st), t(pos[ic % T]))  # H[a = i][m = j] = conj G
+
+    def antv4(self, antvecs):
+        out = torch.zeros(self.na_pad, 4, dtype=torch.float64, device=self.tile_ant.device)
+        out[:self.na, :3] = antvecs.detach().to(out.device, torch.float64)
+        return out
+
+    def hermitian_cotangent(self, G, nfp):
+        """G (nbl, nt, nf) complex64 -> Hp in the kernel layout (float32 view)."""
+        kg, st, T = _lib.ANT_KG, _lib.ANT_STAGE, _lib.ANT_TILE
+        nbl, nt, nf = G.shape
+        nkg = nfp // kg
+        if nfp != nf:
+            G = torch.nn.functional.pad(torch.view_as_real(G), (0, 0, 0, nfp - nf))
+            G = torch.view_as_complex(G)
+        Gq = G.reshape(nbl, nt, nkg, kg)
+        H = torch.zeros(nt, nkg, self.nblk, self.na_pad // st, kg, st, T, dtype=G.dtype,
+                        device=G.device)
+        b, ms, r, pa = self.h_ji
+        H[:, :, b, ms, :, r, pa] = Gq
+        b, ms, r, pa = self.h_ij
+        H[:, :, b, ms, :, r, pa] = Gq.index_select(0, self.h_cross).conj()
+        if len(self.h_auto):
+            b, ms, r, pa = [v.index_select(0, self.h_auto) for v in self.h_ji]
+            H[:, :, b, ms, :, r, pa] = (2 * Gq.index_select(0, self.h_auto).real).to(G.dtype)
+        return torch.view_as_real(H)
+
+
+class _AntFringeSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, antvecs, geom, freqs64, nfreq, conj, tiling):
+        _need_cuda(A, freqs64)
+        if A.dtype != torch.float32:
+            raise TypeError("fringe_sum_ant is float32 only")
+        A = A.contiguous()
+        dev = A.device
+        nplane, nchunk = A.shape[0], A.shape[1]
+        kc = _lib.KC["f32"]
+        nfp = nchunk * kc
+        nbl, nt = tiling.nbl, geom.nt
+        antv = tiling.antv4(antvecs)
+        V = torch.zeros(nplane, nbl, nt, nfreq, dtype=torch.complex64, device=dev)
+        if nbl > 0 and nt > 0 and geom.S > 0:
+            units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
+            per_unit = nbl * nfp * 8
+            max_units = min(max(1, VPART_BUDGET // per_unit), MAX_GRID_UNITS)
+            t0 = 0
+            batches = []
+            while t0 < nt:
+                t1 = t0 + 1
+                while t1 < nt and ubeg[t1 + 1] - ubeg[t0] <= max_units:
+                    t1 += 1
+                batches.append((t0, t1))
+                t0 = t1
+            nu_max = max(ubeg[b] - ubeg[a] for a, b in batches)
+            # pairs outside the tiling keep their zero: every wanted pair has exactly one owner
+            vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=torch.float32, device=dev)
+            Vr = torch.view_as_real(V)
+            for (ta, tb) in batches:
+                u0, u1 = ubeg[ta], ubeg[tb]
+                ub = torch.as_tensor(np.asarray(ubeg[ta:tb + 1], dtype=np.int32) - u0, device=dev)
+                for p in range(nplane):
+                    _call("antfringe_fwd", "f32", A[p], geom.shat, antv, freqs64, units[u0:],
+                          u1 - u0, tiling.tile_ant, tiling.tile_bl, tiling.ntile, nbl, nfreq,
+                          geom.S, int(conj), vpart)
+                    _call("reduce_units", "f32", vpart, ub, tb - ta, nbl, nfreq,
+                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, 0)
+        ctx.save_for_backward(A, antv, freqs64)
+        ctx.meta = (geom, nfreq, int(conj), tiling, antvecs.dtype, antvecs.device, antvecs.shape)
+        return V
+
+    @staticmethod
+    def backward(ctx, G):
+        A, antv, freqs64 = ctx.saved_tensors
+        geom, nfreq, conj, tiling, adtype, adev, ashape_ant = ctx.meta
+        need_A, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dev = G.device
+        nplane, nchunk, _, kc = A.shape
+        nfp = nchunk * kc
+        nkg = nfp // _lib.ANT_KG
+        nt = geom.nt
+        dA = torch.zeros_like(A) if need_A else None
+        dr = torch.zeros(tiling.na_pad, 3, dtype=torch.float64, device=dev) if need_r else None
+        if tiling.nbl > 0 and nt > 0 and geom.S > 0 and (need_A or need_r):
+            units, ubeg = geom.units(tiling.nbl, nchunk, sm_count(dev))
+            per_time = nfp * tiling.na_pad ** 2 * 8
+            tstep = max(1, ANT_H_BUDGET // per_time)
+            G = G.contiguous()
+            for p in range(nplane):
+                dApart = (torch.zeros(tiling.nblk, nchunk, A.shape[2], kc, dtype=torch.float32,
+                                      device=dev) if need_A else None)
+                for ta in range(0, nt, tstep):
+                    tb = min(nt, ta + tstep)
+                    u0, u1 = ubeg[ta], ubeg[tb]
+                    if u1 == u0:
+                        continue
+                    Hp = tiling.hermitian_cotangent(G[p, :, ta:tb], nfp)
+                    un = units[u0:u1].clone()
+                    un[:, 0] -= ta
+                    drpart = (torch.empty(u1 - u0, nkg, tiling.na_pad, 4, dtype=torch.float64,
+                                          device=dev) if need_r else None)
+                    _call("antfringe_bwd", "f32", Hp, A[p], geom.shat, antv, freqs64, un,
+                          u1 - u0, tiling.na_pad, nfreq, geom.S, conj, dApart, drpart)
+                    if need_r:
+                        dr = dr + drpart.sum(dim=(0, 1))[:, :3]
+                    del Hp
+                if need_A:
+                    dA[p] = dApart.sum(0)
+        gant = None
+        if need_r:
+            gant = torch.zeros(ashape_ant, dtype=torch.float64, device=dev)
+            gant[:tiling.na] = dr[:tiling.na]
+            gant = gant.to(device=adev, dtype=adtype)
+        return dA, gant, None, None, None, None, None
+
+
+def fringe_sum_ant(A, antvecs, tiling, geom, freqs64, nfreq, conj=False):
+    """Same sum as fringe_sum for the baselines (tiling.i, tiling.j) of antenna positions
+    antvecs (Na, 3), through the antenna-factorised float32 kernels; gradients flow to A and
+    straight to antvecs."""
+    return _AntFringeSum.apply(A, antvecs, geom, freqs64, nfreq, conj, tiling)
+
+
 def fringe_sum(A, blvecs, geom, freqs64, nfreq, conj=False, uniform=True):
     """A (nplane, nchunk, S, KC) real, blvecs (Nbl, 3) -> V (nplane, Nbl, Nt, Nf) complex:
     V[p, b, t, f] = sum_s A[p, f, s] exp(+-2 pi i (b . shat_s) nu_f / c)."""

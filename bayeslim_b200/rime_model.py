@@ -21,6 +21,7 @@ whose backward passes are CUDA kernels as well.  There is no CPU path: tensors m
 CUDA device, otherwise forward() raises.
 """
 from datetime import datetime
+import os
 
 import numpy as np
 import torch
@@ -139,6 +140,7 @@ class RIME(utils.Module):
         self.Nbl_groups = len(sim_bl_groups)
         self.sim_blvec_groups = {k: self.array.get_blvecs(v) for k, v in sim_bl_groups.items()}
         self._bl_meta = {}
+        self._ant_tilings = {}
         if data_bls is None:
             self.data_bl_groups = self.sim_bl_groups
             self._sim2data = {k: None for k in sim_bl_groups}
@@ -245,6 +247,38 @@ class RIME(utils.Module):
             uniform = ops.freqs_uniform(self._freqs64(self.array, dev), blmax, dtype)
             self._bl_meta[key] = uniform
         return blvecs, self._bl_meta[key]
+
+    def _ant_tiling(self, dev):
+        """ops.AntTiling of the current baseline group when the antenna-factorised float32
+        kernels pay off (the group covers most pairs of its antennas), else None.
+        B200RIME_ANT=0 forces the baseline-owned kernels."""
+        if os.environ.get("B200RIME_ANT", "1") == "0":
+            return None
+        key = (self._bl_key, dev)
+        if key not in self._ant_tilings:
+            til = None
+            try:
+                rows = getattr(self.array, '_ant_idx', None)
+                if rows is None:
+                    rows = {int(a): k for k, a in enumerate(self.array.ants)}
+                bls = self.sim_bls
+                i = [rows[int(b[0])] for b in bls]
+                j = [rows[int(b[1])] for b in bls]
+                til = ops.AntTiling(i, j, len(self.array.antvecs), dev)
+                if not til.usable:
+                    til = None
+            except (KeyError, TypeError, AttributeError, IndexError):
+                til = None
+            self._ant_tilings[key] = til
+        return self._ant_tilings[key]
+
+    def _fringe(self, A, blvecs, rec, f64, nfreq, uniform, dev):
+        """Fringe sum of tiled planes A over all baselines of the current group."""
+        til = self._ant_tiling(dev) if A.dtype == torch.float32 else None
+        if til is not None:
+            return ops.fringe_sum_ant(A, self.array.antvecs.to(dev), til, rec.geom, f64, nfreq,
+                                      conj=False)
+        return ops.fringe_sum(A, blvecs, rec.geom, f64, nfreq, conj=False, uniform=uniform)
 
     def _geometry(self, sky_comp, dev):
         """Per-time zen/az -> FOV cut -> packed source axis; cached per (component, time group)."""
@@ -415,7 +449,7 @@ class RIME(utils.Module):
             if mode is not None:
                 A = self._build_airy(sky, rec, dev) if mode == 'airy' \
                     else self._build_interp(sky, rec, dev)
-                V = ops.fringe_sum(A, blvecs, rec.geom, f64, nfreq, conj=False, uniform=uniform)
+                V = self._fringe(A, blvecs, rec, f64, nfreq, uniform, dev)
                 skyvis = V[:, None]                     # (Npol, 1, Nbl, Nt, Nf)
             elif self._interp_pol_mode(sky):
                 psky, modelpairs, mp_idx = self._tiled_pol_planes(sky, rec, dev)
@@ -469,8 +503,11 @@ class RIME(utils.Module):
                     Xm = X[:, :, m].reshape(P * Q, X.shape[-2], X.shape[-1])
                     planes.append(torch.cat([Xm.real, Xm.imag], dim=0) if cplx else Xm)
                 A = ops.pack_planes(rec.geom, [pl.to(rdtype).contiguous() for pl in planes])
-            V = ops.fringe_sum(A, blvecs.index_select(0, sel), rec.geom, f64, nfreq, conj=False,
-                               uniform=uniform)
+            if len(modelpairs) == 1:
+                V = self._fringe(A, blvecs, rec, f64, nfreq, uniform, dev)
+            else:
+                V = ops.fringe_sum(A, blvecs.index_select(0, sel), rec.geom, f64, nfreq,
+                                   conj=False, uniform=uniform)
             if cplx:
                 V = V[:P * Q] + 1j * V[P * Q:]
             V = V.reshape(P, Q, len(sel), V.shape[-2], V.shape[-1])

@@ -200,12 +200,74 @@ def build_airy_bwd(sfx, dA, Dew, Dns, ratio, square, full_grad, sinzen, sin2az, 
         dD[0, 1] = (w * d2).sum()
 
 
+def _ant_E(antv, shat, freqs, conj):
+    u = antv[:, :3].double() @ shat[:, :3].double().T            # (na, ns)
+    sgn = -1.0 if conj else 1.0
+    ph = 2 * math.pi * sgn * u[:, None, :] * freqs.double()[None, :, None] / C
+    return torch.complex(torch.cos(ph), torch.sin(ph))           # (na, nf, ns)
+
+
+def antfringe_fwd(sfx, A, shat, antv, freqs, units, nunits, tile_ant, tile_bl, ntile, nbl, nfreq,
+                  S, conj, vpart):
+    T = _lib.ANT_TILE
+    Af = _A_rows(A, nfreq).double()
+    for u in range(nunits):
+        _, s0, s1, _ = [int(v) for v in units[u]]
+        E = _ant_E(antv, shat[s0:s1], freqs[:nfreq], conj)
+        vpart[u, :, nfreq:] = 0
+        for n in range(ntile):
+            xs, ys = torch.where(tile_bl[n] >= 0)
+            e = tile_bl[n][xs, ys].long()
+            ax, ay = tile_ant[n, xs].long(), tile_ant[n, T + ys].long()
+            assert (ax >= 0).all() and (ay >= 0).all()
+            for c0 in range(0, len(e), 256):                      # bounded temporaries
+                sl = slice(c0, c0 + 256)
+                V = (E[ax[sl]].conj() * E[ay[sl]] * Af[None, :, s0:s1]).sum(-1)
+                V = torch.where((e[sl] & 1).bool()[:, None], V.conj(), V)
+                vpart[u, e[sl] >> 1, :nfreq, 0] = V.real.to(vpart.dtype)
+                vpart[u, e[sl] >> 1, :nfreq, 1] = V.imag.to(vpart.dtype)
+
+
+def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nfreq, S, conj, dApart,
+                  drpart):
+    kc = _kc(sfx)
+    T, kg = _lib.ANT_TILE, _lib.ANT_KG
+    nt, nkg, nblk, nms, _, st, _, _ = Hp.shape
+    pos = torch.as_tensor([ops._xpos(a) for a in range(T)])
+    H = torch.complex(Hp[..., 0].double(), Hp[..., 1].double())[..., pos]   # [...][a in block]
+    # (nt, nkg, nblk, nms, kg, st, T) -> (nt, f, a, m)
+    H = H.permute(0, 1, 4, 2, 6, 3, 5).reshape(nt, nkg * kg, nblk * T, nms * st)
+    Af = _A_rows(A, nfreq).double()
+    sgn = -1.0 if conj else 1.0
+    nfp = nkg * kg
+    for u in range(nunits):
+        t, s0, s1, _ = [int(v) for v in units[u]]
+        E = _ant_E(antv[:na_pad], shat[s0:s1], freqs[:nfreq], conj)         # (na_pad, nf, ns)
+        y = torch.einsum('fam,mfs->afs', H[t, :nfreq], E)
+        p = E.conj() * y
+        if dApart is not None:
+            half = 0.5 * p.real.reshape(nblk, T, nfreq, s1 - s0).sum(1)      # (nblk, nf, ns)
+            full = torch.zeros(nblk, nfp, s1 - s0, dtype=torch.float64)
+            full[:, :nfreq] = half
+            dApart[:, :, s0:s1] = full.reshape(nblk, nfp // kc, kc, s1 - s0).permute(0, 1, 3, 2) \
+                .to(dApart.dtype)
+        if drpart is not None:
+            w = p.imag * (Af[:, s0:s1] * freqs.double()[:nfreq, None])[None]  # (na_pad, nf, ns)
+            wf = torch.zeros(na_pad, nfp, s1 - s0, dtype=torch.float64)
+            wf[:, :nfreq] = w
+            g = torch.einsum('agks,sc->gac', wf.reshape(na_pad, nkg, kg, s1 - s0),
+                             shat[s0:s1, :3].double())
+            drpart[u, :, :, :3] = sgn * 2 * math.pi / C * g
+            drpart[u, :, :, 3] = 0
+
+
 _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
               fringe_sum_bwd_sky=fringe_sum_bwd_sky, fringe_sum_bwd_bl=fringe_sum_bwd_bl,
               pack=pack, unpack=unpack, build_interp=build_interp,
               build_interp_bwd=build_interp_bwd, interp_transpose=interp_transpose,
               gather_times=gather_times,
-              build_airy=build_airy, build_airy_bwd=build_airy_bwd)
+              build_airy=build_airy, build_airy_bwd=build_airy_bwd,
+              antfringe_fwd=antfringe_fwd, antfringe_bwd=antfringe_bwd)
 
 
 @contextlib.contextmanager

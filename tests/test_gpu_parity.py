@@ -127,6 +127,88 @@ def test_fringe_sum_forward_backward(dtype, nbl, nfreq, ns_list, uniform):
         b.grad = None
 
 
+def _antenna_problem(na, seed):
+    g = torch.Generator().manual_seed(seed)
+    antv = (torch.rand(na, 3, generator=g, dtype=torch.float64) - 0.5) * 600.0
+    antv[:, 2] *= 0.01
+    ii, jj = np.triu_indices(na, k=1)
+    flip = (np.arange(len(ii)) % 3) == 0              # every third pair listed as (j, i)
+    i = np.where(flip, jj, ii)
+    j = np.where(flip, ii, jj)
+    autos = np.asarray([0, na // 2, na - 1])
+    return antv, np.concatenate([i, autos]), np.concatenate([j, autos])
+
+
+@pytest.mark.parametrize("na,nfreq,ns_list", [
+    (70, 70, [300, 0, 64]),        # two antenna blocks, empty time, Nf % 64 != 0
+    (130, 20, [520]),              # three blocks (64, 64, 2), several source tiles per unit
+])
+def test_antenna_factorised_fringe_sum(na, nfreq, ns_list):
+    """float32 antenna-factorised kernels (conj(E_i) E_j complex MACs) against the float64
+    oracle: visibilities, dL/dA and dL/d(antenna positions), both fringe signs, baselines in
+    either orientation and autocorrelations."""
+    dtype = torch.float32
+    geom, zen, az, _, freqs, planes = _rand_problem(4, nfreq, ns_list, dtype, seed=na)
+    antv, i, j = _antenna_problem(na, seed=na)
+    til = ops.AntTiling(i, j, na, DEV)
+    assert til.unique and til.ntile == (na + 63) // 64 * ((na + 63) // 64 + 1) // 2
+    f64 = freqs.to(DEV)
+    X = [p.detach().clone().to(device=DEV, dtype=dtype).requires_grad_(True) for p in planes]
+    a = antv.detach().clone().to(DEV).requires_grad_(True)
+    it, jt = torch.as_tensor(i), torch.as_tensor(j)
+    for conj in (False, True):
+        A = ops.pack_planes(geom, X)
+        V = ops.fringe_sum_ant(A, a, til, geom, f64, nfreq, conj=conj)
+        Xo = [p.detach().clone().requires_grad_(True) for p in planes]
+        ao = antv.detach().clone().requires_grad_(True)
+        Vo = _oracle_fringe_sum(Xo, zen, az, ao[jt] - ao[it], freqs, conj=conj)
+        tag = "antfringe/na%d/conj%d" % (na, conj)
+        assert V.shape == Vo.shape
+        assert relmax(V, Vo, tag + "/V") < TOL[dtype]
+        gen = torch.Generator().manual_seed(7)
+        G = torch.complex(torch.randn(Vo.shape, generator=gen, dtype=torch.float64),
+                          torch.randn(Vo.shape, generator=gen, dtype=torch.float64))
+        oc.real_loss(Vo, G).backward()
+        Gd = G.to(device=DEV, dtype=V.dtype)
+        torch.sum(Gd.real * V.real + Gd.imag * V.imag).backward()
+        for t in range(len(ns_list)):
+            if ns_list[t]:
+                assert relmax(X[t].grad, Xo[t].grad, tag + "/dA%d" % t) < TOL[dtype] * 2
+        assert relmax(a.grad, ao.grad, tag + "/dant") < TOL[dtype] * 2
+        for x in X:
+            x.grad = None
+        a.grad = None
+    # one owner per output, fixed summation order: bitwise reproducible
+    with torch.no_grad():
+        A = ops.pack_planes(geom, X)
+        V1 = ops.fringe_sum_ant(A, a, til, geom, f64, nfreq)
+        V2 = ops.fringe_sum_ant(A, a, til, geom, f64, nfreq)
+    assert torch.equal(V1, V2)
+
+
+def test_antenna_path_is_selected_and_matches_baseline_path():
+    """RIME picks the antenna-factorised kernels for an all-pairs HERA-350 group and the
+    baseline-owned kernels otherwise; both give the same visibilities and gradients."""
+    if DOUBLE:
+        pytest.skip("61075-baseline problem is too large for the CPU test double")
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["B200RIME_ANT"] = flag
+        try:
+            rime = workloads.pixel_interp(16, 96, 2, DEV, torch.float32, antpos_param=True)
+            assert (rime._ant_tiling(torch.device(DEV)) is not None) == (flag == "1")
+            V = rime().data
+            gen = torch.Generator().manual_seed(5)
+            G = torch.randn(V.shape, generator=gen, dtype=torch.float64).to(DEV)
+            torch.sum(G.to(V.real.dtype) * (V.real + 0.5 * V.imag)).backward()
+            out[flag] = (V.detach(), rime.sky.params.grad, rime.beam.params.grad,
+                         rime.array.antvecs.grad)
+        finally:
+            os.environ.pop("B200RIME_ANT", None)
+    for x, y, nm in zip(out["1"], out["0"], ("V", "dsky", "dbeam", "dant")):
+        assert relmax(x, y, "ant_vs_bl_path/" + nm) < 2e-5, nm
+
+
 def test_forward_is_bitwise_reproducible():
     geom, zen, az, blv, freqs, planes = _rand_problem(200, 128, [500, 700], torch.float32, seed=3)
     X = [p.to(device=DEV, dtype=torch.float32) for p in planes]
