@@ -49,7 +49,7 @@ for _name, _sig in _SIGS.items():
 
 
 _ANT_SIGS = {
-    "antfringe_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _L, _I, _P, _P],
+    "antfringe_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P],
     "antfringe_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P, _P],
 }
 for _name, _sig in _ANT_SIGS.items():        # float32 only
@@ -78,7 +78,6 @@ SRC_PAD = lib.b200rime_src_pad()
 SRC_TILE = lib.b200rime_src_tile()
 KC = {"f32": lib.b200rime_kc(0), "f64": lib.b200rime_kc(1)}
 ANT_TILE = lib.b200rime_ant_tile()      # antennas per tile side of the antenna-factorised kernels
-ANT_KG = lib.b200rime_ant_kg()          # channels per pass
 ANT_STAGE = lib.b200rime_ant_stage()    # reduction indices per shared-memory stage
 
 

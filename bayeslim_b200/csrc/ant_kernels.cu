@@ -30,428 +30,474 @@
 
 namespace b200rime {
 
+#ifndef B200_ANT_NSTAGE
+#define B200_ANT_NSTAGE 4
+#endif
+#ifndef B200_ANT_DECORR      // consumer warp `half 1` of slot q runs on the SMSP of slot q - 1
+#define B200_ANT_DECORR 1
+#endif
+#ifndef B200_ANT_PROBE       // tuning probes (wrong results): 1 = producers only signal,
+#define B200_ANT_PROBE 0     // 2 = consumers only signal, 3 = no backward epilogue, 4 = no TMA
+#endif
+#ifndef B200_ANT_UNROLL2     // two stages per consumer loop iteration
+#define B200_ANT_UNROLL2 1
+#endif
 constexpr int ANT_TILE = 64;       // antennas per tile side
-constexpr int ANT_KG = 4;          // channels per pass
 constexpr int ANT_ST = 8;          // reduction indices per shared-memory stage
-constexpr int ANT_THREADS = 256;
+constexpr int ANT_NSTAGE = B200_ANT_NSTAGE;   // stages in flight between producer and consumers
+constexpr int ANT_SLOTS = 4;       // independent (tile, channel) pipelines per CTA, one per SMSP
+constexpr int ANT_CONSUMERS = 256; // warps 0..7: multiply-accumulate; warp = half * 4 + slot
+constexpr int ANT_PRODUCERS = 128; // warps 8..11: operand generation; warp = 8 + slot
+constexpr int ANT_THREADS = ANT_CONSUMERS + ANT_PRODUCERS;
+// registers per thread after setmaxnreg; 128 * producer + 256 * consumer = 64512 = the CTA's
+// pool (384 threads * 168): more cannot be granted and setmaxnreg.inc would spin for ever
+constexpr int ANT_PROD_REGS = 72, ANT_CONS_REGS = 216;          // forward
+constexpr int ANT_PROD_REGS_BWD = 72, ANT_CONS_REGS_BWD = 216;  // backward (224 / 56 measured 3% slower)
 constexpr int ANT_KC = B200_KC_F32;
 
 struct AntSmem {
-    static constexpr int X_BYTES = ANT_KG * ANT_ST * ANT_TILE * 8;
-    static constexpr int Y_BYTES = ANT_KG * ANT_ST * ANT_TILE * 4;
-    static constexpr int STAGE_BYTES = X_BYTES + 2 * Y_BYTES;
-    static constexpr int TOTAL = 2 * STAGE_BYTES;
+    static constexpr int X_BYTES = ANT_ST * ANT_TILE * 8;          // 4 KB complex operand rows
+    static constexpr int Y_BYTES = ANT_ST * ANT_TILE * 4;          // 2 KB each (re / im rows)
+    static constexpr int STAGE_BYTES = X_BYTES + 2 * Y_BYTES;      // 8 KB
+    static constexpr int SLOT_BYTES = ANT_NSTAGE * STAGE_BYTES;    // 32 KB
+    static constexpr int FLAG_OFF = ANT_SLOTS * SLOT_BYTES;        // consumer-warp activity flags
+    static constexpr int BAR_OFF = FLAG_OFF + 64;                  // full / empty [slot][stage]
+    static constexpr int TOTAL = BAR_OFF + 2 * ANT_SLOTS * ANT_NSTAGE * 8;
 };
 
-// position of antenna slot a (0..63) inside an X row of 64 complex numbers: the four slots of
-// thread-row ti = a / 4 are split into two 16-byte halves, each half contiguous over ti, so that
-// the 8 distinct ti of a warp read 128 contiguous bytes
+// position of antenna slot a (0..63) inside an X row of 64 complex numbers: the eight slots of
+// thread-row ti = a / 8 are split into four 16-byte quarters, each quarter contiguous over ti,
+// so that the 8 lanes of a quarter-warp read 128 contiguous bytes per LDS.128
 __device__ __forceinline__ int xpos(int a) {
-    return (((a >> 1) & 1) << 5) | ((a >> 2) << 1) | (a & 1);
+    return (((a >> 1) & 3) << 4) | ((a >> 3) << 1) | (a & 1);
+}
+__device__ __forceinline__ int xpos_inv(int p) {      // antenna slot stored at position p
+    return (((p >> 1) & 7) << 3) | ((p >> 4) << 1) | (p & 1);
 }
 
-// acc += conj(x) * y (CONJ) or x * y, for 4 x-values (scalar broadcast) times 4 y-values
-// (two packed pairs); aR / aI hold (re, re) / (im, im) of the pairs [i][jp]
+// acc += conj(x) * y (CONJ) or x * y for 8 x-values (scalar-broadcast operands, negation folded
+// into the operand) times 8 y-values (four packed pairs); aR / aI hold the real / imaginary
+// parts of the output pairs [i][jp]
 template <bool CONJ>
-__device__ __forceinline__ void ant_mac(P2 (&aR)[8], P2 (&aI)[8], const float4 x01,
-                                        const float4 x23, const float4 yr, const float4 yi) {
-    const P2 yr0 = p2(yr.x, yr.y), yr1 = p2(yr.z, yr.w);
-    const P2 yi0 = p2(yi.x, yi.y), yi1 = p2(yi.z, yi.w);
-    const float xr[4] = {x01.x, x01.z, x23.x, x23.z};
-    const float xi[4] = {x01.y, x01.w, x23.y, x23.w};
+__device__ __forceinline__ void ant_mac(P2 (&aR)[8][4], P2 (&aI)[8][4], const float4 (&x)[4],
+                                        const float4 (&yr)[2], const float4 (&yi)[2]) {
+    const P2 YR[4] = {p2(yr[0].x, yr[0].y), p2(yr[0].z, yr[0].w), p2(yr[1].x, yr[1].y),
+                      p2(yr[1].z, yr[1].w)};
+    const P2 YI[4] = {p2(yi[0].x, yi[0].y), p2(yi[0].z, yi[0].w), p2(yi[1].x, yi[1].y),
+                      p2(yi[1].z, yi[1].w)};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const P2 XR = p2(xr[i], xr[i]);
-        const P2 XI = p2(xi[i], xi[i]);
-        const P2 NXI = p2(-xi[i], -xi[i]);
-        p2_mac(aR[2 * i], XR, yr0);
-        p2_mac(aR[2 * i + 1], XR, yr1);
-        p2_mac(aI[2 * i], XR, yi0);
-        p2_mac(aI[2 * i + 1], XR, yi1);
-        if (CONJ) {
-            p2_mac(aR[2 * i], XI, yi0);
-            p2_mac(aR[2 * i + 1], XI, yi1);
-            p2_mac(aI[2 * i], NXI, yr0);
-            p2_mac(aI[2 * i + 1], NXI, yr1);
-        } else {
-            p2_mac(aR[2 * i], NXI, yi0);
-            p2_mac(aR[2 * i + 1], NXI, yi1);
-            p2_mac(aI[2 * i], XI, yr0);
-            p2_mac(aI[2 * i + 1], XI, yr1);
+    for (int h = 0; h < 4; ++h) {
+        const float xr[2] = {x[h].x, x[h].z}, xi[2] = {x[h].y, x[h].w};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = 2 * h + e;
+            const P2 XR = p2(xr[e], xr[e]), XI = p2(xi[e], xi[e]), NXI = p2(-xi[e], -xi[e]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                p2_mac(aR[i][j], XR, YR[j]);
+                p2_mac(aI[i][j], XR, YI[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                p2_mac(aR[i][j], CONJ ? XI : NXI, YI[j]);
+                p2_mac(aI[i][j], CONJ ? NXI : XI, YR[j]);
+            }
         }
     }
 }
 
-// one shared-memory stage of multiply-accumulates: ANT_ST reduction indices x ANT_KG channels
+// one shared-memory stage: ANT_ST reduction indices; the thread's 8 x-values are antenna slots
+// 8 ti .. 8 ti + 7, its 8 y-values are row entries 32 half + 8 tj .. + 7
 template <bool CONJ>
-__device__ __forceinline__ void ant_mac_stage(P2 (&aR)[ANT_KG][8], P2 (&aI)[ANT_KG][8],
-                                              const unsigned char* buf, int ti, int tj) {
+__device__ __forceinline__ void ant_mac_stage(P2 (&aR)[8][4], P2 (&aI)[8][4],
+                                              const unsigned char* buf, int ti, int yq) {
     const float4* X4 = reinterpret_cast<const float4*>(buf);
     const float4* YR4 = reinterpret_cast<const float4*>(buf + AntSmem::X_BYTES);
     const float4* YI4 = reinterpret_cast<const float4*>(buf + AntSmem::X_BYTES + AntSmem::Y_BYTES);
 #pragma unroll
     for (int r = 0; r < ANT_ST; ++r) {
+        float4 x[4], yr[2], yi[2];
 #pragma unroll
-        for (int k = 0; k < ANT_KG; ++k) {
-            const int row = k * ANT_ST + r;
-            const float4 x01 = X4[row * 32 + ti];
-            const float4 x23 = X4[row * 32 + 16 + ti];
-            const float4 yr = YR4[row * 16 + tj];
-            const float4 yi = YI4[row * 16 + tj];
-            ant_mac<CONJ>(aR[k], aI[k], x01, x23, yr, yi);
-        }
+        for (int h = 0; h < 4; ++h) x[h] = X4[r * 32 + h * 8 + ti];
+        yr[0] = YR4[r * 16 + yq];
+        yr[1] = YR4[r * 16 + yq + 1];
+        yi[0] = YI4[r * 16 + yq];
+        yi[1] = YI4[r * 16 + yq + 1];
+        ant_mac<CONJ>(aR, aI, x, yr, yi);
     }
 }
 
-__device__ __forceinline__ double dot3(double ax, double ay, double az, const double* __restrict__ s) {
-    const double2 s01 = __ldg(reinterpret_cast<const double2*>(s));
-    const double s2 = __ldg(s + 2);
-    return __fma_rn(ax, s01.x, __fma_rn(ay, s01.y, az * s2));
+// antenna term E = exp(2 pi i frac(u kappa)), u = r_a . shat [m], kappa = sgn nu / c [cycles/m]
+__device__ __forceinline__ void antenna_term(double u, double kappa, float& c, float& s) {
+    cis_fast((float)frac_cycles(u, kappa), c, s);
+}
+__device__ __forceinline__ double dot3(const double (&a)[3], const double2 s01, const double s2) {
+    return __fma_rn(a[0], s01.x, __fma_rn(a[1], s01.y, a[2] * s2));
+}
+
+// warp -> (slot, half).  Producers: warp 8 + slot.  Consumers: warps 0..3 are `half 0` of slots
+// 0..3; warps 4..7 are `half 1`, by default of the NEXT slot, so that the two consumer warps that
+// share an SM sub-partition belong to different pipelines and do not stall in lockstep.
+__device__ __forceinline__ int ant_slot_of(int warp) {
+    if (warp >= 2 * ANT_SLOTS || warp < ANT_SLOTS || !B200_ANT_DECORR) return warp & (ANT_SLOTS - 1);
+    return (warp + 1) & (ANT_SLOTS - 1);
+}
+
+// one consumer pass over the stages [it0, it1) of a slot
+template <bool CONJ>
+__device__ __forceinline__ void ant_consume(P2 (&aR)[8][4], P2 (&aI)[8][4], const unsigned char* sbuf,
+                                            uint64_t* full, uint64_t* empty, long long g0,
+                                            int nstages, int ti, int yq, int lane) {
+    long long g = g0;
+    int n = nstages;
+#if B200_ANT_UNROLL2
+    for (; n >= 2; n -= 2, g += 2) {
+        const int sa = (int)(g % ANT_NSTAGE), sb = (int)((g + 1) % ANT_NSTAGE);
+        mbar_wait(&full[sa], (uint32_t)((g / ANT_NSTAGE) & 1));
+        if (B200_ANT_PROBE != 2) ant_mac_stage<CONJ>(aR, aI, sbuf + sa * AntSmem::STAGE_BYTES, ti, yq);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[sa]);
+        mbar_wait(&full[sb], (uint32_t)(((g + 1) / ANT_NSTAGE) & 1));
+        if (B200_ANT_PROBE != 2) ant_mac_stage<CONJ>(aR, aI, sbuf + sb * AntSmem::STAGE_BYTES, ti, yq);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[sb]);
+    }
+#endif
+    for (; n > 0; --n, ++g) {
+        const int stage = (int)(g % ANT_NSTAGE);
+        mbar_wait(&full[stage], (uint32_t)((g / ANT_NSTAGE) & 1));
+        if (B200_ANT_PROBE != 2) ant_mac_stage<CONJ>(aR, aI, sbuf + stage * AntSmem::STAGE_BYTES, ti, yq);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+}
+
+// shared prologue: barriers of the four slot pipelines.  flags[w] = consumer warp w takes part.
+__device__ __forceinline__ void ant_init_barriers(unsigned char* smem, int tid, int lane, int warp,
+                                                  bool active, int full_count) {
+    int* flags = reinterpret_cast<int*>(smem + AntSmem::FLAG_OFF);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + AntSmem::BAR_OFF);
+    uint64_t* empty = full + ANT_SLOTS * ANT_NSTAGE;
+    if (warp < ANT_CONSUMERS / 32 && lane == 0)
+        flags[(warp >> 2) * ANT_SLOTS + ant_slot_of(warp)] = active ? 1 : 0;
+    __syncthreads();
+    if (tid < ANT_SLOTS) {
+        const int n = flags[tid] + flags[tid + ANT_SLOTS];
+#pragma unroll
+        for (int st = 0; st < ANT_NSTAGE; ++st) {
+            mbar_init(&full[tid * ANT_NSTAGE + st], full_count);
+            mbar_init(&empty[tid * ANT_NSTAGE + st], n > 0 ? n : 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
 }
 
 // -------------------------------------------------------------------------------------
-// forward.  grid = (ntile, Nfp / 4, nunits), block = 256.
-// Thread (ti, tj) of the 16 x 16 thread grid owns antenna slots 4 ti .. 4 ti + 3 of the tile's
-// X set and 4 tj .. 4 tj + 3 of its Y set.  tile_bl[tile][x][y] = (baseline << 1 | conj) or -1.
+// forward.  grid = (ntile * Nfp / 4, nunits), block = 384.
+// A CTA runs four independent pipelines ("slots", one per SM sub-partition): slot q works on
+// item 4 blockIdx.x + q = (tile, channel), channel fastest, tiles in `tile_order` (tiles that
+// need both consumer warps first).  Per slot: producer warp 8 + q generates, per stage of
+// ANT_ST sources, X = E of the tile's 64 first antennas and Y = A_s E of its 64 second antennas;
+// consumer warps q (second antennas 0..31) and 4 + q (32..63) accumulate conj(X) Y with 8 x 8
+// register tiles.  tile_bl[tile][x][y] = (baseline << 1 | conj) or -1.
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ANT_THREADS, 1)
 ant_fringe_fwd_kernel(const float* __restrict__ A, const double* __restrict__ shat,
                       const double* __restrict__ antv, const double* __restrict__ freqs,
                       const int4* __restrict__ units, const int* __restrict__ tile_ant,
-                      const int* __restrict__ tile_bl, int nbl, int nfreq, long long S,
-                      double sgn_over_c, float* __restrict__ vpart) {
+                      const int* __restrict__ tile_bl, const int* __restrict__ tile_order,
+                      int nitems, int nk, int nbl, int nfreq, long long S, double sgn_over_c,
+                      float* __restrict__ vpart) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
-    const int k0 = blockIdx.y * ANT_KG;
-    const int nfp = gridDim.y * ANT_KG;
-    const int4 un = units[blockIdx.z];
+    const int slot = ant_slot_of(warp);
+    const int half = (warp >> 2) & 1;
+    const int item = blockIdx.x * ANT_SLOTS + slot;
+    const bool valid = item < nitems;
+    const int tile = valid ? __ldg(tile_order + item / nk) : 0;
+    const int k = valid ? item % nk : 0;
+    const int4 un = units[blockIdx.y];
     const int nst = (un.z - un.y) / ANT_ST;
 
-    // multiply-accumulate role
-    const int ti = ((warp >> 2) << 3) | (lane & 7);
-    const int tj = ((warp & 3) << 2) | (lane >> 3);
-    const int* tb = tile_bl + (size_t)tile * (ANT_TILE * ANT_TILE) + (4 * ti) * ANT_TILE + 4 * tj;
+    // consumer role: which outputs are wanted
+    const int ti = lane & 7, tj = lane >> 3;
+    const int* tb = tile_bl + (size_t)tile * (ANT_TILE * ANT_TILE) + (8 * ti) * ANT_TILE +
+                    32 * half + 8 * tj;
     bool mine = false;
+    if (valid && warp < ANT_CONSUMERS / 32) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int4 e = __ldg(reinterpret_cast<const int4*>(tb + i * ANT_TILE));
-        mine |= (e.x >= 0) | (e.y >= 0) | (e.z >= 0) | (e.w >= 0);
+        for (int i = 0; i < 8; ++i) {
+            const int4 e0 = __ldg(reinterpret_cast<const int4*>(tb + i * ANT_TILE));
+            const int4 e1 = __ldg(reinterpret_cast<const int4*>(tb + i * ANT_TILE + 4));
+            mine |= (e0.x >= 0) | (e0.y >= 0) | (e0.z >= 0) | (e0.w >= 0) | (e1.x >= 0) |
+                    (e1.y >= 0) | (e1.z >= 0) | (e1.w >= 0);
+        }
     }
-    const bool active = __any_sync(0xffffffffu, mine);   // warps with no wanted pair only generate
+    const bool active = __any_sync(0xffffffffu, mine) && nst > 0;
+    ant_init_barriers(smem, tid, lane, warp, active, 1);
+    const int* flags = reinterpret_cast<const int*>(smem + AntSmem::FLAG_OFF);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + AntSmem::BAR_OFF) + slot * ANT_NSTAGE;
+    uint64_t* empty = full + ANT_SLOTS * ANT_NSTAGE;
+    unsigned char* sbuf = smem + slot * AntSmem::SLOT_BYTES;
+    const bool slot_live = (flags[slot] + flags[slot + ANT_SLOTS]) > 0;
 
-    // generation role: one antenna slot (X: 0..63, Y: 64..127), sources (tid >> 7) + 2 r
-    const int slot = tid & 127;
-    const bool is_y = slot >= ANT_TILE;
-    const int ant = __ldg(tile_ant + tile * (2 * ANT_TILE) + slot);
-    double ax = 0.0, ay = 0.0, az = 0.0;
-    if (ant >= 0) {
-        ax = antv[4 * (size_t)ant];
-        ay = antv[4 * (size_t)ant + 1];
-        az = antv[4 * (size_t)ant + 2];
-    }
-    double kf[ANT_KG];
+    if (warp >= ANT_CONSUMERS / 32) {
+        // ---------------- producer warp of this slot
+        setmaxnreg_dec<ANT_PROD_REGS>();
+        if (!slot_live) return;
+        // lane owns X positions lane, lane + 32 (conflict-free stores) and Y slots lane, lane + 32
+        double pos[4][3];
+        int xp[2];
 #pragma unroll
-    for (int k = 0; k < ANT_KG; ++k) kf[k] = (k0 + k < nfreq) ? sgn_over_c * freqs[k0 + k] : 0.0;
-    const float* Ak = A + (size_t)(k0 / ANT_KC) * (size_t)S * ANT_KC + (k0 % ANT_KC);
-    const int sl0 = tid >> 7;
-    const int xw = is_y ? (slot - ANT_TILE) : xpos(slot);
-
-    auto generate = [&](int it, unsigned char* buf) {
-        float2* X2 = reinterpret_cast<float2*>(buf);
-        float* YR = reinterpret_cast<float*>(buf + AntSmem::X_BYTES);
-        float* YI = reinterpret_cast<float*>(buf + AntSmem::X_BYTES + AntSmem::Y_BYTES);
-        const long long sbase = (long long)un.y + (long long)it * ANT_ST;
-#pragma unroll
-        for (int r = 0; r < ANT_ST / 2; ++r) {
-            const int sl = sl0 + 2 * r;
-            const long long s = sbase + sl;
-            const double u = dot3(ax, ay, az, shat + 4 * s);
-            float a4[4] = {1.f, 1.f, 1.f, 1.f};
-            if (is_y) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(Ak + s * ANT_KC));
-                a4[0] = t.x, a4[1] = t.y, a4[2] = t.z, a4[3] = t.w;
+        for (int q = 0; q < 4; ++q) {
+            int a;
+            if (q < 2) {
+                xp[q] = lane + 32 * q;
+                a = xpos_inv(xp[q]);
+            } else {
+                a = ANT_TILE + lane + 32 * (q - 2);
             }
-#pragma unroll
-            for (int k = 0; k < ANT_KG; ++k) {
-                float c, sn;
-                cis_fast((float)frac_cycles(u, kf[k]), c, sn);
-                const int row = (k * ANT_ST + sl) * ANT_TILE;
-                if (is_y) {
-                    YR[row + xw] = a4[k] * c;
-                    YI[row + xw] = a4[k] * sn;
-                } else {
-                    X2[row + xw] = make_float2(c, sn);
-                }
+            const int ant = __ldg(tile_ant + tile * (2 * ANT_TILE) + a);
+            pos[q][0] = pos[q][1] = pos[q][2] = 0.0;
+            if (ant >= 0) {
+                pos[q][0] = antv[4 * (size_t)ant];
+                pos[q][1] = antv[4 * (size_t)ant + 1];
+                pos[q][2] = antv[4 * (size_t)ant + 2];
             }
         }
-    };
-
-    P2 aR[ANT_KG][8], aI[ANT_KG][8];
+        const double kappa = (k < nfreq) ? sgn_over_c * freqs[k] : 0.0;
+        const float* Ak = A + (size_t)(k / ANT_KC) * (size_t)S * ANT_KC + (k % ANT_KC);
+        for (int it = 0; it < nst; ++it) {
+            const int stage = it % ANT_NSTAGE;
+            if (it >= ANT_NSTAGE) mbar_wait(&empty[stage], ((it / ANT_NSTAGE) - 1) & 1);
+            unsigned char* buf = sbuf + stage * AntSmem::STAGE_BYTES;
+            float2* X2 = reinterpret_cast<float2*>(buf);
+            float* YR = reinterpret_cast<float*>(buf + AntSmem::X_BYTES);
+            float* YI = reinterpret_cast<float*>(buf + AntSmem::X_BYTES + AntSmem::Y_BYTES);
+            const long long sbase = (long long)un.y + (long long)it * ANT_ST;
+#pragma unroll 2
+            for (int sl = 0; sl < (B200_ANT_PROBE == 1 ? 0 : ANT_ST); ++sl) {
+                const long long s = sbase + sl;
+                const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
+                const double s2 = __ldg(shat + 4 * s + 2);
+                const float a = __ldg(Ak + s * ANT_KC);
+                float c[4], sn[4];
 #pragma unroll
-    for (int k = 0; k < ANT_KG; ++k)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) aR[k][q] = aI[k][q] = p2(0.f, 0.f);
-
-    if (nst > 0) generate(0, smem);
-    __syncthreads();
-    for (int it = 0; it < nst; ++it) {
-        unsigned char* cur = smem + (it & 1) * AntSmem::STAGE_BYTES;
-        unsigned char* nxt = smem + ((it + 1) & 1) * AntSmem::STAGE_BYTES;
-        if (it + 1 < nst) generate(it + 1, nxt);
-        if (active) ant_mac_stage<true>(aR, aI, cur, ti, tj);
-        __syncthreads();
+                for (int q = 0; q < 4; ++q) antenna_term(dot3(pos[q], s01, s2), kappa, c[q], sn[q]);
+                X2[sl * ANT_TILE + xp[0]] = make_float2(c[0], sn[0]);
+                X2[sl * ANT_TILE + xp[1]] = make_float2(c[1], sn[1]);
+                YR[sl * ANT_TILE + lane] = a * c[2];
+                YI[sl * ANT_TILE + lane] = a * sn[2];
+                YR[sl * ANT_TILE + lane + 32] = a * c[3];
+                YI[sl * ANT_TILE + lane + 32] = a * sn[3];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+        }
+        return;
     }
 
+    // ---------------- consumer warps
+    setmaxnreg_inc<ANT_CONS_REGS>();
+    if (!active) return;
+    P2 aR[8][4], aI[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) aR[i][j] = aI[i][j] = p2(0.f, 0.f);
+    const int yq = half * 8 + tj * 2;
+    ant_consume<true>(aR, aI, sbuf, full, empty, 0, nst, ti, yq, lane);
+
     if (!mine) return;
-    float* vp = vpart + (size_t)blockIdx.z * (size_t)nbl * nfp * 2;
+    float* vp = vpart + ((size_t)blockIdx.y * (size_t)nbl * nk + k) * 2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int4 e4 = __ldg(reinterpret_cast<const int4*>(tb + i * ANT_TILE));
-        const int e[4] = {e4.x, e4.y, e4.z, e4.w};
+    for (int i = 0; i < 8; ++i) {
+        const int4 e0 = __ldg(reinterpret_cast<const int4*>(tb + i * ANT_TILE));
+        const int4 e1 = __ldg(reinterpret_cast<const int4*>(tb + i * ANT_TILE + 4));
+        const int e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             if (e[j] < 0) continue;
-            const float sg = (e[j] & 1) ? -1.f : 1.f;
-            float re[ANT_KG], im[ANT_KG];
-#pragma unroll
-            for (int k = 0; k < ANT_KG; ++k) {
-                float r0, r1, i0, i1;
-                p2_get(aR[k][2 * i + (j >> 1)], r0, r1);
-                p2_get(aI[k][2 * i + (j >> 1)], i0, i1);
-                re[k] = (j & 1) ? r1 : r0;
-                im[k] = sg * ((j & 1) ? i1 : i0);
-            }
-            float4* dst = reinterpret_cast<float4*>(vp + ((size_t)(e[j] >> 1) * nfp + k0) * 2);
-            dst[0] = make_float4(re[0], im[0], re[1], im[1]);
-            dst[1] = make_float4(re[2], im[2], re[3], im[3]);
+            float r0, r1, i0, i1;
+            p2_get(aR[i][j >> 1], r0, r1);
+            p2_get(aI[i][j >> 1], i0, i1);
+            const float re = (j & 1) ? r1 : r0;
+            const float im = (j & 1) ? i1 : i0;
+            *reinterpret_cast<float2*>(vp + (size_t)(e[j] >> 1) * nk * 2) =
+                make_float2(re, (e[j] & 1) ? -im : im);
         }
     }
 }
 
 // -------------------------------------------------------------------------------------
-// backward.  grid = (nblk, Nfp / 4, nunits), block = 256.
-// The CTA owns antenna block ib (64 output antennas a), 4 channels and a unit of sources; it
-// walks the unit in tiles of 64 sources and, per tile, reduces over all partner antennas m in
-// stages of ANT_ST.  Thread (ti, tj): antennas 4 ti .. +3 (X = H[a, m], TMA-staged from the
-// pre-arranged Hermitian cotangent), sources 4 tj .. +3 (Y = E_m, generated).
-//   Hp[t][kg][ib][mstage][k][r][64 a (xpos order)] complex64
-//   dApart[ib][chunk][S][KC]            (summed over ib by the caller)
-//   drpart[unit][kg][ib * 64 + a][4]    float64 (summed by the caller)
+// backward.  grid = (nblk * Nfp / 4, nunits), block = 384.
+// Slot item = (antenna block ib, channel k), channel fastest.  The slot walks the unit in tiles
+// of 64 sources and, per tile, reduces over all partner antennas m in stages of ANT_ST:
+//   X = H[a, m] for the 64 antennas a of block ib (TMA-staged from the pre-arranged Hermitian
+//       cotangent), Y = E_m over the 64 sources (generated by the producer warp);
+// consumer warp `half` owns sources 32 half .. + 31, thread (ti, tj) antennas 8 ti .. + 7 and
+// sources 8 tj .. + 7 of those.  After the last stage y_a = sum_m H[a, m] E_m is complete and
+// with p = conj(E_a) y_a the thread adds Re p to dL/dA and shat A kappa Im p to dL/dr_a.
+//   Hp[t][k][ib][mstage][r][64 a (xpos order)] complex64
+//   dApart[ib][chunk][S][KC]                  (summed over ib by the caller)
+//   drpart[unit][k][half][ib * 64 + a][4]     float64 (summed over unit, k, half by the caller)
 // -------------------------------------------------------------------------------------
-struct AntBwdSmem {
-    static constexpr int STAGE_BYTES = AntSmem::STAGE_BYTES;
-    static constexpr int RED_OFF = 2 * STAGE_BYTES;            // cross-warp reduction scratch
-    static constexpr int RED_BYTES = 8 * 32 * 16 * 4;          // 16 KB
-    static constexpr int BAR_OFF = RED_OFF + RED_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 16;
-};
-
 __global__ void __launch_bounds__(ANT_THREADS, 1)
 ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
                       const double* __restrict__ shat, const double* __restrict__ antv,
-                      const double* __restrict__ freqs, const int4* __restrict__ units, int na_pad,
-                      int nfreq, long long S, double sgn_over_c, int need_a, int need_r,
-                      float* __restrict__ dApart, double* __restrict__ drpart) {
+                      const double* __restrict__ freqs, const int4* __restrict__ units, int nitems,
+                      int nk, int na_pad, int nfreq, long long S, double sgn_over_c, int need_a,
+                      int need_r, float* __restrict__ dApart, double* __restrict__ drpart) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AntBwdSmem::BAR_OFF);
-    float* red = reinterpret_cast<float*>(smem + AntBwdSmem::RED_OFF);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ib = blockIdx.x, nblk = gridDim.x;
-    const int kg = blockIdx.y, nkg = gridDim.y;
-    const int k0 = kg * ANT_KG;
-    const int4 un = units[blockIdx.z];
+    const int slot = ant_slot_of(warp);
+    const int half = (warp >> 2) & 1;
+    const int item = blockIdx.x * ANT_SLOTS + slot;
+    const bool valid = item < nitems;
+    const int ib = valid ? item / nk : 0;
+    const int k = valid ? item % nk : 0;
+    const int nblk = na_pad / ANT_TILE;
+    const int4 un = units[blockIdx.y];
     const int nmst = na_pad / ANT_ST;                  // partner-antenna stages per source tile
     const int nsrc_tiles = (un.z - un.y) / ANT_TILE;
-    const long long total = (long long)nsrc_tiles * nmst;
+    const bool active = valid && nsrc_tiles > 0;
 
-    const int ti = ((warp >> 2) << 3) | (lane & 7);    // antennas 4 ti ..
-    const int tj = ((warp & 3) << 2) | (lane >> 3);    // sources  4 tj ..
+    ant_init_barriers(smem, tid, lane, warp, active, 2);     // producer warp + TMA expect_tx
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + AntSmem::BAR_OFF) + slot * ANT_NSTAGE;
+    uint64_t* empty = full + ANT_SLOTS * ANT_NSTAGE;
+    unsigned char* sbuf = smem + slot * AntSmem::SLOT_BYTES;
+    const double kappa = (k < nfreq) ? sgn_over_c * freqs[k] : 0.0;
 
-    double kf[ANT_KG];
-#pragma unroll
-    for (int k = 0; k < ANT_KG; ++k) kf[k] = (k0 + k < nfreq) ? sgn_over_c * freqs[k0 + k] : 0.0;
-
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // H tiles of this (time, channel group, antenna block): nmst consecutive 16 KB blocks
-    const float* Hbase = Hp + ((((size_t)un.x * nkg + kg) * nblk + ib) * (size_t)nmst) *
-                                  (AntSmem::X_BYTES / 4);
-    auto issue = [&](long long g, int stage) {
-        const int ms = (int)(g % nmst);
-        mbar_expect_tx(&bars[stage], AntSmem::X_BYTES);
-        bulk_g2s(smem + stage * AntSmem::STAGE_BYTES, Hbase + (size_t)ms * (AntSmem::X_BYTES / 4),
-                 AntSmem::X_BYTES, &bars[stage]);
-    };
-
-    // generation role: partner antenna m = ms * ANT_ST + (tid >> 6) + 4 r, source tid & 63
-    const int gs = tid & 63;
-    const int gm0 = tid >> 6;
-    auto generate = [&](long long g, unsigned char* buf) {
-        float* YR = reinterpret_cast<float*>(buf + AntSmem::X_BYTES);
-        float* YI = reinterpret_cast<float*>(buf + AntSmem::X_BYTES + AntSmem::Y_BYTES);
-        const int ms = (int)(g % nmst);
-        const long long s = (long long)un.y + (g / nmst) * ANT_TILE + gs;
-        const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
-        const double s2 = __ldg(shat + 4 * s + 2);
-#pragma unroll
-        for (int r = 0; r < ANT_ST / 4; ++r) {
-            const int ml = gm0 + 4 * r;
-            const double* ap = antv + 4 * (size_t)(ms * ANT_ST + ml);
-            const double2 a01 = __ldg(reinterpret_cast<const double2*>(ap));
-            const double a2 = __ldg(ap + 2);
-            const double u = __fma_rn(a01.x, s01.x, __fma_rn(a01.y, s01.y, a2 * s2));
-#pragma unroll
-            for (int k = 0; k < ANT_KG; ++k) {
-                float c, sn;
-                cis_fast((float)frac_cycles(u, kf[k]), c, sn);
-                const int row = (k * ANT_ST + ml) * ANT_TILE;
-                YR[row + gs] = c;
-                YI[row + gs] = sn;
+    if (warp >= ANT_CONSUMERS / 32) {
+        // ---------------- producer warp: lane owns sources lane and lane + 32 of the tile
+        setmaxnreg_dec<ANT_PROD_REGS_BWD>();
+        if (!active) return;
+        const float* Hbase = Hp + ((((size_t)un.x * nk + k) * nblk + ib) * (size_t)nmst) *
+                                      (AntSmem::X_BYTES / 4);
+        long long g = 0;
+        for (int st = 0; st < nsrc_tiles; ++st) {
+            const long long s = (long long)un.y + (long long)st * ANT_TILE + lane;
+            const double2 sa01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
+            const double sa2 = __ldg(shat + 4 * s + 2);
+            const double2 sb01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * (s + 32)));
+            const double sb2 = __ldg(shat + 4 * (s + 32) + 2);
+            for (int ms = 0; ms < nmst; ++ms, ++g) {
+                const int stage = (int)(g % ANT_NSTAGE);
+                if (g >= ANT_NSTAGE)
+                    mbar_wait(&empty[stage], (uint32_t)(((g / ANT_NSTAGE) - 1) & 1));
+                unsigned char* buf = sbuf + stage * AntSmem::STAGE_BYTES;
+                if (lane == 0) {
+                    if (B200_ANT_PROBE == 4 && g > 0) {
+                        mbar_arrive(&full[stage]);
+                    } else {
+                        mbar_expect_tx(&full[stage], AntSmem::X_BYTES);
+                        bulk_g2s(buf, Hbase + (size_t)ms * (AntSmem::X_BYTES / 4),
+                                 AntSmem::X_BYTES, &full[stage]);
+                    }
+                }
+                float* YR = reinterpret_cast<float*>(buf + AntSmem::X_BYTES);
+                float* YI = reinterpret_cast<float*>(buf + AntSmem::X_BYTES + AntSmem::Y_BYTES);
+#pragma unroll 2
+                for (int r = 0; r < (B200_ANT_PROBE == 1 ? 0 : ANT_ST); ++r) {
+                    const double* ap = antv + 4 * (size_t)(ms * ANT_ST + r);
+                    const double2 a01 = __ldg(reinterpret_cast<const double2*>(ap));
+                    const double a2 = __ldg(ap + 2);
+                    const double am[3] = {a01.x, a01.y, a2};
+                    float c0, s0, c1, s1;
+                    antenna_term(dot3(am, sa01, sa2), kappa, c0, s0);
+                    antenna_term(dot3(am, sb01, sb2), kappa, c1, s1);
+                    YR[r * ANT_TILE + lane] = c0;
+                    YI[r * ANT_TILE + lane] = s0;
+                    YR[r * ANT_TILE + lane + 32] = c1;
+                    YI[r * ANT_TILE + lane + 32] = s1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
             }
         }
-    };
-
-    // own antennas: positions, and gradient accumulators over the whole unit
-    double pax[4], pay[4], paz[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double* ap = antv + 4 * (size_t)(ib * ANT_TILE + 4 * ti + i);
-        pax[i] = ap[0], pay[i] = ap[1], paz[i] = ap[2];
+        return;
     }
-    float gx[4], gy[4], gz[4];
+
+    // ---------------- consumer warps
+    setmaxnreg_inc<ANT_CONS_REGS_BWD>();
+    if (!active) return;
+    const int ti = lane & 7, tj = lane >> 3;
+    const int yq = half * 8 + tj * 2;
+    float gx[8], gy[8], gz[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) gx[i] = gy[i] = gz[i] = 0.f;
-    const float* Ak = A + (size_t)(k0 / ANT_KC) * (size_t)S * ANT_KC + (k0 % ANT_KC);
-    float* dAk = dApart + ((size_t)ib * gridDim.y * ANT_KG / ANT_KC + (k0 / ANT_KC)) * (size_t)S * ANT_KC +
-                 (k0 % ANT_KC);
+    for (int i = 0; i < 8; ++i) gx[i] = gy[i] = gz[i] = 0.f;
 
-    P2 aR[ANT_KG][8], aI[ANT_KG][8];
-
-    if (total > 0) {
-        if (tid == 0) issue(0, 0);
-        generate(0, smem);
-    }
-    __syncthreads();
+    P2 aR[8][4], aI[8][4];
     long long g = 0;
     for (int st = 0; st < nsrc_tiles; ++st) {
 #pragma unroll
-        for (int k = 0; k < ANT_KG; ++k)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) aR[k][q] = aI[k][q] = p2(0.f, 0.f);
-        for (int ms = 0; ms < nmst; ++ms, ++g) {
-            const int stage = (int)(g & 1);
-            unsigned char* cur = smem + stage * AntSmem::STAGE_BYTES;
-            if (g + 1 < total) {
-                if (tid == 0) issue(g + 1, stage ^ 1);
-                generate(g + 1, smem + (stage ^ 1) * AntSmem::STAGE_BYTES);
-            }
-            mbar_wait(&bars[stage], (uint32_t)((g >> 1) & 1));
-            ant_mac_stage<false>(aR, aI, cur, ti, tj);
-            __syncthreads();
-        }
+            for (int j = 0; j < 4; ++j) aR[i][j] = aI[i][j] = p2(0.f, 0.f);
+        ant_consume<false>(aR, aI, sbuf, full, empty, g, nmst, ti, yq, lane);
+        g += nmst;
         // ---- epilogue of this source tile: p = conj(E_a) y_a
-        const long long sb = (long long)un.y + (long long)st * ANT_TILE + 4 * tj;
-        float dAacc[4][ANT_KG];        // [source][channel], sum over own 4 antennas of Re p
+        if (B200_ANT_PROBE == 3 && st > 0) continue;
+        const long long sb = (long long)un.y + (long long)st * ANT_TILE + 32 * half + 8 * tj;
+        const float kf = (float)kappa;
+        const float* Ak = A + (size_t)(k / ANT_KC) * (size_t)S * ANT_KC + (k % ANT_KC);
+        float* dAk = dApart + ((size_t)ib * (nk / ANT_KC) + (k / ANT_KC)) * (size_t)S * ANT_KC +
+                     (k % ANT_KC);
+        const double* apos = antv + 4 * (size_t)(ib * ANT_TILE + 8 * ti);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < ANT_KG; ++k) dAacc[j][k] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const long long s = sb + j;
             const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
             const double s2 = __ldg(shat + 4 * s + 2);
-            const float4 a4v = __ldg(reinterpret_cast<const float4*>(Ak + s * ANT_KC));
-            const float a4[4] = {a4v.x, a4v.y, a4v.z, a4v.w};
+            const float wk = __ldg(Ak + s * ANT_KC) * kf;
             const float sx = (float)s01.x, sy = (float)s01.y, sz = (float)s2;
+            float dacc = 0.f;       // sum over own 8 antennas of Re p
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double u = __fma_rn(pax[i], s01.x, __fma_rn(pay[i], s01.y, paz[i] * s2));
-                float w = 0.f;      // sum_k A kappa_k Im p
-#pragma unroll
-                for (int k = 0; k < ANT_KG; ++k) {
-                    float c, sn, r0, r1, i0, i1;
-                    cis_fast((float)frac_cycles(u, kf[k]), c, sn);
-                    p2_get(aR[k][2 * i + (j >> 1)], r0, r1);
-                    p2_get(aI[k][2 * i + (j >> 1)], i0, i1);
-                    const float yr = (j & 1) ? r1 : r0, yi = (j & 1) ? i1 : i0;
-                    dAacc[j][k] += c * yr + sn * yi;            // Re(conj(E) y)
-                    const float pim = c * yi - sn * yr;         // Im(conj(E) y)
-                    w = fmaf(a4[k] * (float)kf[k], pim, w);
-                }
+            for (int i = 0; i < 8; ++i) {
+                const double2 p01 = __ldg(reinterpret_cast<const double2*>(apos + 4 * i));
+                const double pz = __ldg(apos + 4 * i + 2);
+                const double am[3] = {p01.x, p01.y, pz};
+                float c, sn, r0, r1, i0, i1;
+                antenna_term(dot3(am, s01, s2), kappa, c, sn);
+                p2_get(aR[i][j >> 1], r0, r1);
+                p2_get(aI[i][j >> 1], i0, i1);
+                const float yr = (j & 1) ? r1 : r0, yi = (j & 1) ? i1 : i0;
+                dacc = fmaf(c, yr, fmaf(sn, yi, dacc));              // Re(conj(E) y)
+                const float w = wk * fmaf(c, yi, -sn * yr);          // A kappa Im(conj(E) y)
                 gx[i] = fmaf(w, sx, gx[i]);
                 gy[i] = fmaf(w, sy, gy[i]);
                 gz[i] = fmaf(w, sz, gz[i]);
             }
-        }
-        if (need_a) {
-            // sum over the 16 thread-rows ti: lanes (bits 0..2) by shuffle, then the two warp
-            // halves (warp >> 2) through shared memory, fixed order
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int k = 0; k < ANT_KG; ++k) {
-                    float v = dAacc[j][k];
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    dAacc[j][k] = v;
-                }
-            if ((warp >> 2) == 1 && (lane & 7) == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int k = 0; k < ANT_KG; ++k) red[(tj * 4 + j) * ANT_KG + k] = dAacc[j][k];
+            if (need_a) {
+                // sum over the 8 thread-rows ti (lane bits 0..2), fixed order
+                dacc += __shfl_xor_sync(0xffffffffu, dacc, 1);
+                dacc += __shfl_xor_sync(0xffffffffu, dacc, 2);
+                dacc += __shfl_xor_sync(0xffffffffu, dacc, 4);
+                if (ti == 0) dAk[s * ANT_KC] = 0.5f * dacc;
             }
-            __syncthreads();
-            if ((warp >> 2) == 0 && (lane & 7) == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float o[ANT_KG];
-#pragma unroll
-                    for (int k = 0; k < ANT_KG; ++k)
-                        o[k] = 0.5f * (dAacc[j][k] + red[(tj * 4 + j) * ANT_KG + k]);
-                    *reinterpret_cast<float4*>(dAk + (sb + j) * ANT_KC) =
-                        make_float4(o[0], o[1], o[2], o[3]);
-                }
-            }
-            __syncthreads();
         }
     }
 
     if (need_r) {
-        // sum the antenna gradients over the 16 thread-columns tj: lanes (bits 3, 4) by shuffle,
-        // then the four warps of a half through shared memory, in float64
-        double* redd = reinterpret_cast<double*>(red);
+        // sum the antenna gradients over the 4 thread-columns tj (lane bits 3, 4)
+        const double twopi = 6.283185307179586476925286766559;
+        double* dst = drpart + ((((size_t)blockIdx.y * nk + k) * 2 + half) * (size_t)na_pad +
+                                ib * ANT_TILE + 8 * ti) * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             float v[3] = {gx[i], gy[i], gz[i]};
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 v[c] += __shfl_xor_sync(0xffffffffu, v[c], 8);
                 v[c] += __shfl_xor_sync(0xffffffffu, v[c], 16);
             }
-            if ((lane >> 3) == 0) {
-                double* dst = redd + (((warp & 3) * 64 + 4 * ti + i) * 4);
-                dst[0] = v[0], dst[1] = v[1], dst[2] = v[2];
+            if (tj == 0) {
+                dst[4 * i] = twopi * (double)v[0];
+                dst[4 * i + 1] = twopi * (double)v[1];
+                dst[4 * i + 2] = twopi * (double)v[2];
+                dst[4 * i + 3] = 0.0;
             }
-        }
-        __syncthreads();
-        if (tid < ANT_TILE) {
-            double o[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) o[c] += redd[(q * 64 + tid) * 4 + c];
-            const double twopi = 6.283185307179586476925286766559;
-            double* dst = drpart + ((((size_t)blockIdx.z * nkg + kg) * nblk + ib) * ANT_TILE + tid) * 4;
-            dst[0] = twopi * o[0], dst[1] = twopi * o[1], dst[2] = twopi * o[2], dst[3] = 0.0;
         }
     }
 }
@@ -460,22 +506,25 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
 // launchers
 // -------------------------------------------------------------------------------------
 int launch_ant_fwd(const float* A, const double* shat, const double* antv, const double* freqs,
-                   const int* units, int nunits, const int* tile_ant, const int* tile_bl, int ntile,
-                   int nbl, int nfreq, long long S, int conj, float* vpart, cudaStream_t st) {
+                   const int* units, int nunits, const int* tile_ant, const int* tile_bl,
+                   const int* tile_order, int ntile, int nbl, int nfreq, long long S, int conj,
+                   float* vpart, cudaStream_t st) {
     if (nunits <= 0 || ntile <= 0 || nfreq <= 0) return 0;
     if (S % SRC_PAD) return set_error("antfringe_fwd: S must be a multiple of 128");
     const int nfp = ((nfreq + ANT_KC - 1) / ANT_KC) * ANT_KC;
-    if (nfp / ANT_KG > 65535 || nunits > 65535) return set_error("antfringe_fwd: grid too large");
+    const long long nitems = (long long)ntile * nfp;
+    if (nitems / ANT_SLOTS > 2147483647LL || nunits > 65535)
+        return set_error("antfringe_fwd: grid too large");
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(ant_fringe_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              AntSmem::TOTAL);
         attr_set = true;
     }
-    dim3 grid(ntile, nfp / ANT_KG, nunits);
+    dim3 grid((unsigned)((nitems + ANT_SLOTS - 1) / ANT_SLOTS), nunits);
     ant_fringe_fwd_kernel<<<grid, ANT_THREADS, AntSmem::TOTAL, st>>>(
-        A, shat, antv, freqs, reinterpret_cast<const int4*>(units), tile_ant, tile_bl, nbl, nfreq, S,
-        (conj ? -1.0 : 1.0) / C_LIGHT, vpart);
+        A, shat, antv, freqs, reinterpret_cast<const int4*>(units), tile_ant, tile_bl, tile_order,
+        (int)nitems, nfp, nbl, nfreq, S, (conj ? -1.0 : 1.0) / C_LIGHT, vpart);
     return check_launch("antfringe_fwd");
 }
 
@@ -486,17 +535,20 @@ int launch_ant_bwd(const float* Hp, const float* A, const double* shat, const do
     if (S % SRC_PAD) return set_error("antfringe_bwd: S must be a multiple of 128");
     if (na_pad % ANT_TILE) return set_error("antfringe_bwd: antenna count must be padded to 64");
     const int nfp = ((nfreq + ANT_KC - 1) / ANT_KC) * ANT_KC;
-    if (nfp / ANT_KG > 65535 || nunits > 65535) return set_error("antfringe_bwd: grid too large");
+    const long long nitems = (long long)(na_pad / ANT_TILE) * nfp;
+    if (nitems / ANT_SLOTS > 2147483647LL || nunits > 65535)
+        return set_error("antfringe_bwd: grid too large");
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(ant_fringe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             AntBwdSmem::TOTAL);
+                             AntSmem::TOTAL);
         attr_set = true;
     }
-    dim3 grid(na_pad / ANT_TILE, nfp / ANT_KG, nunits);
-    ant_fringe_bwd_kernel<<<grid, ANT_THREADS, AntBwdSmem::TOTAL, st>>>(
-        Hp, A, shat, antv, freqs, reinterpret_cast<const int4*>(units), na_pad, nfreq, S,
-        (conj ? -1.0 : 1.0) / C_LIGHT, dApart != nullptr, drpart != nullptr, dApart, drpart);
+    dim3 grid((unsigned)((nitems + ANT_SLOTS - 1) / ANT_SLOTS), nunits);
+    ant_fringe_bwd_kernel<<<grid, ANT_THREADS, AntSmem::TOTAL, st>>>(
+        Hp, A, shat, antv, freqs, reinterpret_cast<const int4*>(units), (int)nitems, nfp, na_pad,
+        nfreq, S, (conj ? -1.0 : 1.0) / C_LIGHT, dApart != nullptr, drpart != nullptr, dApart,
+        drpart);
     return check_launch("antfringe_bwd");
 }
 
@@ -506,10 +558,12 @@ extern "C" {
 
 int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double* antv,
                                const double* freqs, const int* units, int nunits,
-                               const int* tile_ant, const int* tile_bl, int ntile, int nbl,
-                               int nfreq, long long S, int conj, float* Vpart, void* stream) {
-    return b200rime::launch_ant_fwd(A, shat, antv, freqs, units, nunits, tile_ant, tile_bl, ntile,
-                                    nbl, nfreq, S, conj, Vpart, (cudaStream_t)stream);
+                               const int* tile_ant, const int* tile_bl, const int* tile_order,
+                               int ntile, int nbl, int nfreq, long long S, int conj, float* Vpart,
+                               void* stream) {
+    return b200rime::launch_ant_fwd(A, shat, antv, freqs, units, nunits, tile_ant, tile_bl,
+                                    tile_order, ntile, nbl, nfreq, S, conj, Vpart,
+                                    (cudaStream_t)stream);
 }
 int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* shat,
                                const double* antv, const double* freqs, const int* units,
@@ -519,7 +573,6 @@ int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* sh
                                     dApart, drpart, (cudaStream_t)stream);
 }
 int b200rime_ant_tile(void) { return b200rime::ANT_TILE; }
-int b200rime_ant_kg(void) { return b200rime::ANT_KG; }
 int b200rime_ant_stage(void) { return b200rime::ANT_ST; }
 
 }  // extern "C"

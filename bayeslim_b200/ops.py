@@ -511,7 +511,7 @@ ANT_H_BUDGET = 4 << 30      # bytes of Hermitian cotangent matrix per backward s
 
 def _xpos(a):
     """Position of antenna slot a (0..63) inside a 64-wide operand row (include/b200rime.h)."""
-    return (((a >> 1) & 1) << 5) | ((a >> 2) << 1) | (a & 1)
+    return (((a >> 1) & 3) << 4) | ((a >> 3) << 1) | (a & 1)
 
 
 class AntTiling:
@@ -545,13 +545,20 @@ class AntTiling:
         self.unique = len(np.unique(flat)) == nbl         # a pair listed twice cannot be tiled
         tile_bl = -np.ones(self.ntile * T * T, dtype=np.int32)
         tile_bl[flat] = (np.arange(nbl) << 1) | swap
-        self.fill_fwd = nbl / max(self.ntile * T * T, 1)
+        # tiles whose second antennas all sit in slots 0..31 keep one of the two consumer warps
+        # idle: they go last so that the four pipelines of a CTA get equal work
+        tb = tile_bl.reshape(self.ntile, T, T)
+        both = (tb[:, :, T // 2:] >= 0).any(axis=(1, 2))
+        order = np.concatenate([np.nonzero(both)[0], np.nonzero(~both)[0]]).astype(np.int32)
+        cost = both.sum() + 0.5 * (~both).sum()
+        self.fill_fwd = nbl / max(cost * T * T, 1)
         self.fill_bwd = nbl / float(self.na_pad ** 2)
         self.usable = (self.unique and nbl > 0 and self.fill_fwd >= ANT_FWD_MIN_FILL
                        and self.fill_bwd >= ANT_BWD_MIN_FILL)
         dev = torch.device(device)
         self.tile_ant = torch.as_tensor(tile_ant, device=dev)
         self.tile_bl = torch.as_tensor(tile_bl.reshape(self.ntile, T, T), device=dev)
+        self.tile_order = torch.as_tensor(order, device=dev)
         self.i = torch.as_tensor(i, device=dev)
         self.j = torch.as_tensor(j, device=dev)
         # scatter coordinates of the Hermitian cotangent matrix (see include/b200rime.h):
@@ -573,22 +580,21 @@ class AntTiling:
 
     def hermitian_cotangent(self, G, nfp):
         """G (nbl, nt, nf) complex64 -> Hp in the kernel layout (float32 view)."""
-        kg, st, T = _lib.ANT_KG, _lib.ANT_STAGE, _lib.ANT_TILE
+        st, T = _lib.ANT_STAGE, _lib.ANT_TILE
         nbl, nt, nf = G.shape
-        nkg = nfp // kg
         if nfp != nf:
             G = torch.nn.functional.pad(torch.view_as_real(G), (0, 0, 0, nfp - nf))
             G = torch.view_as_complex(G)
-        Gq = G.reshape(nbl, nt, nkg, kg)
-        H = torch.zeros(nt, nkg, self.nblk, self.na_pad // st, kg, st, T, dtype=G.dtype,
+        Gq = G.permute(1, 2, 0)                                   # (nt, nfp, nbl)
+        H = torch.zeros(nt, nfp, self.nblk, self.na_pad // st, st, T, dtype=G.dtype,
                         device=G.device)
         b, ms, r, pa = self.h_ji
-        H[:, :, b, ms, :, r, pa] = Gq
+        H[:, :, b, ms, r, pa] = Gq
         b, ms, r, pa = self.h_ij
-        H[:, :, b, ms, :, r, pa] = Gq.index_select(0, self.h_cross).conj()
+        H[:, :, b, ms, r, pa] = Gq.index_select(2, self.h_cross).conj()
         if len(self.h_auto):
             b, ms, r, pa = [v.index_select(0, self.h_auto) for v in self.h_ji]
-            H[:, :, b, ms, :, r, pa] = (2 * Gq.index_select(0, self.h_auto).real).to(G.dtype)
+            H[:, :, b, ms, r, pa] = (2 * Gq.index_select(2, self.h_auto).real).to(G.dtype)
         return torch.view_as_real(H)
 
 
@@ -627,8 +633,8 @@ class _AntFringeSum(torch.autograd.Function):
                 ub = torch.as_tensor(np.asarray(ubeg[ta:tb + 1], dtype=np.int32) - u0, device=dev)
                 for p in range(nplane):
                     _call("antfringe_fwd", "f32", A[p], geom.shat, antv, freqs64, units[u0:],
-                          u1 - u0, tiling.tile_ant, tiling.tile_bl, tiling.ntile, nbl, nfreq,
-                          geom.S, int(conj), vpart)
+                          u1 - u0, tiling.tile_ant, tiling.tile_bl, tiling.tile_order,
+                          tiling.ntile, nbl, nfreq, geom.S, int(conj), vpart)
                     _call("reduce_units", "f32", vpart, ub, tb - ta, nbl, nfreq,
                           Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, 0)
         ctx.save_for_backward(A, antv, freqs64)
@@ -643,7 +649,6 @@ class _AntFringeSum(torch.autograd.Function):
         dev = G.device
         nplane, nchunk, _, kc = A.shape
         nfp = nchunk * kc
-        nkg = nfp // _lib.ANT_KG
         nt = geom.nt
         dA = torch.zeros_like(A) if need_A else None
         dr = torch.zeros(tiling.na_pad, 3, dtype=torch.float64, device=dev) if need_r else None
@@ -663,12 +668,12 @@ class _AntFringeSum(torch.autograd.Function):
                     Hp = tiling.hermitian_cotangent(G[p, :, ta:tb], nfp)
                     un = units[u0:u1].clone()
                     un[:, 0] -= ta
-                    drpart = (torch.empty(u1 - u0, nkg, tiling.na_pad, 4, dtype=torch.float64,
+                    drpart = (torch.empty(u1 - u0, nfp, 2, tiling.na_pad, 4, dtype=torch.float64,
                                           device=dev) if need_r else None)
                     _call("antfringe_bwd", "f32", Hp, A[p], geom.shat, antv, freqs64, un,
                           u1 - u0, tiling.na_pad, nfreq, geom.S, conj, dApart, drpart)
                     if need_r:
-                        dr = dr + drpart.sum(dim=(0, 1))[:, :3]
+                        dr = dr + drpart.sum(dim=(0, 1, 2))[:, :3]
                     del Hp
                 if need_A:
                     dA[p] = dApart.sum(0)

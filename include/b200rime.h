@@ -218,29 +218,30 @@ int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, double
  * conj(E_i) E_j, E_a = exp(+-2 pi i r_a . shat nu / c), so one evaluation is one complex
  * multiply-accumulate on the FP32 pipes; antenna terms are generated inside the kernels.
  *
- * antv      [na_pad][4] float64 antenna positions (ENU metres), rows >= na zero
- * tile_ant  [ntile][128] antenna row of X slots 0..63 (first antenna of a pair, conjugated)
- *           and Y slots 64..127 (second antenna); -1 = empty slot
- * tile_bl   [ntile][64][64] (baseline index << 1 | c) or -1; c = 1: the tile holds the pair
- *           swapped and the result is conjugated on output
- * Vpart     [nunits][nbl][Nfp][2]   (same as fringe_sum_fwd; reduce with reduce_units)
- * ant_tile() = 64, ant_kg() = 4 channels per pass, ant_stage() = 8. */
+ * antv       [na_pad][4] float64 antenna positions (ENU metres), rows >= na zero
+ * tile_ant   [ntile][128] antenna row of X slots 0..63 (first antenna of a pair, conjugated)
+ *            and Y slots 64..127 (second antenna); -1 = empty slot
+ * tile_bl    [ntile][64][64] (baseline index << 1 | c) or -1; c = 1: the tile holds the pair
+ *            swapped and the result is conjugated on output
+ * tile_order [ntile] processing order of the tiles (tiles with second antennas only in slots
+ *            0..31 last)
+ * Vpart      [nunits][nbl][Nfp][2]   (same as fringe_sum_fwd; reduce with reduce_units)
+ * ant_tile() = 64 antennas per tile side, ant_stage() = 8 reduction indices per stage. */
 int b200rime_ant_tile(void);
-int b200rime_ant_kg(void);
 int b200rime_ant_stage(void);
 int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double* antv,
                                const double* freqs, const int* units, int nunits,
-                               const int* tile_ant, const int* tile_bl, int ntile, int nbl,
-                               int nfreq, long long S, int conj, float* Vpart,
+                               const int* tile_ant, const int* tile_bl, const int* tile_order,
+                               int ntile, int nbl, int nfreq, long long S, int conj, float* Vpart,
                                b200rime_stream_t stream);
 /* Backward of the same sum to the perceived sky and to the antenna positions in one pass.
- * Hp  [nt][Nfp/4][na_pad/64][na_pad/8][4][8][64][2]: Hermitian cotangent matrix
- *     H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m), 2 Re G_b for a = m = autos,
- *     indexed [time][channel group][block of a][stage of m][channel][m in stage][a in block],
- *     a stored at position ((a >> 1) & 1) * 32 + (a >> 2) * 2 + (a & 1) of its block.
+ * Hp  [nt][Nfp][na_pad/64][na_pad/8][8][64][2]: Hermitian cotangent matrix
+ *     H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m), 2 Re G_b for a = m (autos),
+ *     indexed [time][channel][block of a][stage of m][m in stage][a in block], a stored at
+ *     position ((a >> 1) & 3) * 16 + (a >> 3) * 2 + (a & 1) of its block.
  * dApart [na_pad/64][nchunk][S][KC]    partial dL/dA per antenna block (sum over blocks), or NULL
- * drpart [nunits][Nfp/4][na_pad][4]    float64 partial dL/d(antenna position) (sum over the
- *                                       first two axes), or NULL */
+ * drpart [nunits][Nfp][2][na_pad][4]   float64 partial dL/d(antenna position) (sum over the
+ *                                       first three axes), or NULL */
 int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* shat,
                                const double* antv, const double* freqs, const int* units,
                                int nunits, int na_pad, int nfreq, long long S, int conj,

@@ -207,8 +207,9 @@ def _ant_E(antv, shat, freqs, conj):
     return torch.complex(torch.cos(ph), torch.sin(ph))           # (na, nf, ns)
 
 
-def antfringe_fwd(sfx, A, shat, antv, freqs, units, nunits, tile_ant, tile_bl, ntile, nbl, nfreq,
-                  S, conj, vpart):
+def antfringe_fwd(sfx, A, shat, antv, freqs, units, nunits, tile_ant, tile_bl, tile_order, ntile,
+                  nbl, nfreq, S, conj, vpart):
+    assert sorted(int(v) for v in tile_order) == list(range(ntile))
     T = _lib.ANT_TILE
     Af = _A_rows(A, nfreq).double()
     for u in range(nunits):
@@ -231,15 +232,14 @@ def antfringe_fwd(sfx, A, shat, antv, freqs, units, nunits, tile_ant, tile_bl, n
 def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nfreq, S, conj, dApart,
                   drpart):
     kc = _kc(sfx)
-    T, kg = _lib.ANT_TILE, _lib.ANT_KG
-    nt, nkg, nblk, nms, _, st, _, _ = Hp.shape
+    T = _lib.ANT_TILE
+    nt, nfp, nblk, nms, st, _, _ = Hp.shape
     pos = torch.as_tensor([ops._xpos(a) for a in range(T)])
     H = torch.complex(Hp[..., 0].double(), Hp[..., 1].double())[..., pos]   # [...][a in block]
-    # (nt, nkg, nblk, nms, kg, st, T) -> (nt, f, a, m)
-    H = H.permute(0, 1, 4, 2, 6, 3, 5).reshape(nt, nkg * kg, nblk * T, nms * st)
+    # (nt, nfp, nblk, nms, st, T) -> (nt, f, a, m)
+    H = H.permute(0, 1, 2, 5, 3, 4).reshape(nt, nfp, nblk * T, nms * st)
     Af = _A_rows(A, nfreq).double()
     sgn = -1.0 if conj else 1.0
-    nfp = nkg * kg
     for u in range(nunits):
         t, s0, s1, _ = [int(v) for v in units[u]]
         E = _ant_E(antv[:na_pad], shat[s0:s1], freqs[:nfreq], conj)         # (na_pad, nf, ns)
@@ -253,12 +253,9 @@ def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nfreq, S
                 .to(dApart.dtype)
         if drpart is not None:
             w = p.imag * (Af[:, s0:s1] * freqs.double()[:nfreq, None])[None]  # (na_pad, nf, ns)
-            wf = torch.zeros(na_pad, nfp, s1 - s0, dtype=torch.float64)
-            wf[:, :nfreq] = w
-            g = torch.einsum('agks,sc->gac', wf.reshape(na_pad, nkg, kg, s1 - s0),
-                             shat[s0:s1, :3].double())
-            drpart[u, :, :, :3] = sgn * 2 * math.pi / C * g
-            drpart[u, :, :, 3] = 0
+            g = torch.einsum('afs,sc->fac', w, shat[s0:s1, :3].double())
+            drpart[u].zero_()
+            drpart[u, :nfreq, 0, :, :3] = sgn * 2 * math.pi / C * g
 
 
 _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
