@@ -33,17 +33,17 @@ namespace b200rime {
 #ifndef B200_ANT_NSTAGE
 #define B200_ANT_NSTAGE 4
 #endif
+#ifndef B200_ANT_ST
+#define B200_ANT_ST 8
+#endif
 #ifndef B200_ANT_DECORR      // consumer warp `half 1` of slot q runs on the SMSP of slot q - 1
 #define B200_ANT_DECORR 1
 #endif
 #ifndef B200_ANT_PROBE       // tuning probes (wrong results): 1 = producers only signal,
 #define B200_ANT_PROBE 0     // 2 = consumers only signal, 3 = no backward epilogue, 4 = no TMA
 #endif
-#ifndef B200_ANT_UNROLL2     // two stages per consumer loop iteration
-#define B200_ANT_UNROLL2 1
-#endif
 constexpr int ANT_TILE = 64;       // antennas per tile side
-constexpr int ANT_ST = 8;          // reduction indices per shared-memory stage
+constexpr int ANT_ST = B200_ANT_ST;   // reduction indices per shared-memory stage (8 or 16)
 constexpr int ANT_NSTAGE = B200_ANT_NSTAGE;   // stages in flight between producer and consumers
 constexpr int ANT_SLOTS = 4;       // independent (tile, channel) pipelines per CTA, one per SMSP
 constexpr int ANT_CONSUMERS = 256; // warps 0..7: multiply-accumulate; warp = half * 4 + slot
@@ -148,10 +148,21 @@ template <bool CONJ>
 __device__ __forceinline__ void ant_consume(P2 (&aR)[8][4], P2 (&aI)[8][4], const unsigned char* sbuf,
                                             uint64_t* full, uint64_t* empty, long long g0,
                                             int nstages, int ti, int yq, int lane) {
+    // nstages is even (forward: units are multiples of 64 sources; backward: the partner axis is
+    // padded to 16), so the loop body holds two stages and ptxas amortises its accumulator
+    // fix-up moves over 2048 FFMA2
     long long g = g0;
-    int n = nstages;
-#if B200_ANT_UNROLL2
-    for (; n >= 2; n -= 2, g += 2) {
+    if (ANT_ST >= 16) {                 // one 16-deep stage per iteration
+        for (int n = nstages; n > 0; --n, ++g) {
+            const int sa = (int)(g % ANT_NSTAGE);
+            mbar_wait(&full[sa], (uint32_t)((g / ANT_NSTAGE) & 1));
+            if (B200_ANT_PROBE != 2) ant_mac_stage<CONJ>(aR, aI, sbuf + sa * AntSmem::STAGE_BYTES, ti, yq);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[sa]);
+        }
+        return;
+    }
+    for (int n = nstages; n > 0; n -= 2, g += 2) {
         const int sa = (int)(g % ANT_NSTAGE), sb = (int)((g + 1) % ANT_NSTAGE);
         mbar_wait(&full[sa], (uint32_t)((g / ANT_NSTAGE) & 1));
         if (B200_ANT_PROBE != 2) ant_mac_stage<CONJ>(aR, aI, sbuf + sa * AntSmem::STAGE_BYTES, ti, yq);
@@ -161,14 +172,6 @@ __device__ __forceinline__ void ant_consume(P2 (&aR)[8][4], P2 (&aI)[8][4], cons
         if (B200_ANT_PROBE != 2) ant_mac_stage<CONJ>(aR, aI, sbuf + sb * AntSmem::STAGE_BYTES, ti, yq);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[sb]);
-    }
-#endif
-    for (; n > 0; --n, ++g) {
-        const int stage = (int)(g % ANT_NSTAGE);
-        mbar_wait(&full[stage], (uint32_t)((g / ANT_NSTAGE) & 1));
-        if (B200_ANT_PROBE != 2) ant_mac_stage<CONJ>(aR, aI, sbuf + stage * AntSmem::STAGE_BYTES, ti, yq);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
     }
 }
 
@@ -270,7 +273,7 @@ ant_fringe_fwd_kernel(const float* __restrict__ A, const double* __restrict__ sh
         const float* Ak = A + (size_t)(k / ANT_KC) * (size_t)S * ANT_KC + (k % ANT_KC);
         for (int it = 0; it < nst; ++it) {
             const int stage = it % ANT_NSTAGE;
-            if (it >= ANT_NSTAGE) mbar_wait(&empty[stage], ((it / ANT_NSTAGE) - 1) & 1);
+            if (it >= ANT_NSTAGE) mbar_wait_relaxed(&empty[stage], ((it / ANT_NSTAGE) - 1) & 1);
             unsigned char* buf = sbuf + stage * AntSmem::STAGE_BYTES;
             float2* X2 = reinterpret_cast<float2*>(buf);
             float* YR = reinterpret_cast<float*>(buf + AntSmem::X_BYTES);
@@ -339,7 +342,7 @@ ant_fringe_fwd_kernel(const float* __restrict__ A, const double* __restrict__ sh
 // consumer warp `half` owns sources 32 half .. + 31, thread (ti, tj) antennas 8 ti .. + 7 and
 // sources 8 tj .. + 7 of those.  After the last stage y_a = sum_m H[a, m] E_m is complete and
 // with p = conj(E_a) y_a the thread adds Re p to dL/dA and shat A kappa Im p to dL/dr_a.
-//   Hp[t][k][ib][mstage][r][64 a (xpos order)] complex64
+//   Hp[t][k][ib][mstage][r][64 a (xpos order)] complex64, mstage < nm_pad / 8
 //   dApart[ib][chunk][S][KC]                  (summed over ib by the caller)
 //   drpart[unit][k][half][ib * 64 + a][4]     float64 (summed over unit, k, half by the caller)
 // -------------------------------------------------------------------------------------
@@ -347,8 +350,9 @@ __global__ void __launch_bounds__(ANT_THREADS, 1)
 ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
                       const double* __restrict__ shat, const double* __restrict__ antv,
                       const double* __restrict__ freqs, const int4* __restrict__ units, int nitems,
-                      int nk, int na_pad, int nfreq, long long S, double sgn_over_c, int need_a,
-                      int need_r, float* __restrict__ dApart, double* __restrict__ drpart) {
+                      int nk, int na_pad, int nm_pad, int nfreq, long long S, double sgn_over_c,
+                      int need_a, int need_r, float* __restrict__ dApart,
+                      double* __restrict__ drpart) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = ant_slot_of(warp);
@@ -359,7 +363,7 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
     const int k = valid ? item % nk : 0;
     const int nblk = na_pad / ANT_TILE;
     const int4 un = units[blockIdx.y];
-    const int nmst = na_pad / ANT_ST;                  // partner-antenna stages per source tile
+    const int nmst = nm_pad / ANT_ST;                  // partner-antenna stages per source tile
     const int nsrc_tiles = (un.z - un.y) / ANT_TILE;
     const bool active = valid && nsrc_tiles > 0;
 
@@ -385,7 +389,7 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
             for (int ms = 0; ms < nmst; ++ms, ++g) {
                 const int stage = (int)(g % ANT_NSTAGE);
                 if (g >= ANT_NSTAGE)
-                    mbar_wait(&empty[stage], (uint32_t)(((g / ANT_NSTAGE) - 1) & 1));
+                    mbar_wait_relaxed(&empty[stage], (uint32_t)(((g / ANT_NSTAGE) - 1) & 1));
                 unsigned char* buf = sbuf + stage * AntSmem::STAGE_BYTES;
                 if (lane == 0) {
                     if (B200_ANT_PROBE == 4 && g > 0) {
@@ -529,11 +533,14 @@ int launch_ant_fwd(const float* A, const double* shat, const double* antv, const
 }
 
 int launch_ant_bwd(const float* Hp, const float* A, const double* shat, const double* antv,
-                   const double* freqs, const int* units, int nunits, int na_pad, int nfreq,
-                   long long S, int conj, float* dApart, double* drpart, cudaStream_t st) {
+                   const double* freqs, const int* units, int nunits, int na_pad, int nm_pad,
+                   int nfreq, long long S, int conj, float* dApart, double* drpart,
+                   cudaStream_t st) {
     if (nunits <= 0 || na_pad <= 0 || nfreq <= 0) return 0;
     if (S % SRC_PAD) return set_error("antfringe_bwd: S must be a multiple of 128");
     if (na_pad % ANT_TILE) return set_error("antfringe_bwd: antenna count must be padded to 64");
+    if (nm_pad % (ANT_ST >= 16 ? ANT_ST : 2 * ANT_ST) || nm_pad > na_pad || nm_pad <= 0)
+        return set_error("antfringe_bwd: partner axis must be padded to 16 and fit na_pad");
     const int nfp = ((nfreq + ANT_KC - 1) / ANT_KC) * ANT_KC;
     const long long nitems = (long long)(na_pad / ANT_TILE) * nfp;
     if (nitems / ANT_SLOTS > 2147483647LL || nunits > 65535)
@@ -547,7 +554,7 @@ int launch_ant_bwd(const float* Hp, const float* A, const double* shat, const do
     dim3 grid((unsigned)((nitems + ANT_SLOTS - 1) / ANT_SLOTS), nunits);
     ant_fringe_bwd_kernel<<<grid, ANT_THREADS, AntSmem::TOTAL, st>>>(
         Hp, A, shat, antv, freqs, reinterpret_cast<const int4*>(units), (int)nitems, nfp, na_pad,
-        nfreq, S, (conj ? -1.0 : 1.0) / C_LIGHT, dApart != nullptr, drpart != nullptr, dApart,
+        nm_pad, nfreq, S, (conj ? -1.0 : 1.0) / C_LIGHT, dApart != nullptr, drpart != nullptr, dApart,
         drpart);
     return check_launch("antfringe_bwd");
 }
@@ -567,10 +574,10 @@ int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double*
 }
 int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* shat,
                                const double* antv, const double* freqs, const int* units,
-                               int nunits, int na_pad, int nfreq, long long S, int conj,
-                               float* dApart, double* drpart, void* stream) {
-    return b200rime::launch_ant_bwd(Hp, A, shat, antv, freqs, units, nunits, na_pad, nfreq, S, conj,
-                                    dApart, drpart, (cudaStream_t)stream);
+                               int nunits, int na_pad, int nm_pad, int nfreq, long long S,
+                               int conj, float* dApart, double* drpart, void* stream) {
+    return b200rime::launch_ant_bwd(Hp, A, shat, antv, freqs, units, nunits, na_pad, nm_pad, nfreq,
+                                    S, conj, dApart, drpart, (cudaStream_t)stream);
 }
 int b200rime_ant_tile(void) { return b200rime::ANT_TILE; }
 int b200rime_ant_stage(void) { return b200rime::ANT_ST; }

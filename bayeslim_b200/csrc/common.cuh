@@ -175,6 +175,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// wait that yields the issue slots: try_wait with a suspend-time hint, then a short sleep.  For
+// warps that run far ahead of their partners (producers waiting for a free stage): a bare
+// try_wait loop spins at full rate and takes issue cycles from the consumer warps of the same
+// SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(2000u)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -527,6 +527,8 @@ class AntTiling:
         self.nbl, self.na = nbl, int(na)
         self.nblk = max(1, -(-self.na // T))
         self.na_pad = self.nblk * T
+        mq = max(16, _lib.ANT_STAGE)
+        self.nm_pad = -(-self.na // mq) * mq          # partner axis of the backward, padded to 16
         bi, bj = i // T, j // T
         swap = (bi > bj) | ((bi == bj) & (i > j))        # fold onto the upper triangle
         x = np.where(swap, j, i)
@@ -551,7 +553,8 @@ class AntTiling:
         both = (tb[:, :, T // 2:] >= 0).any(axis=(1, 2))
         order = np.concatenate([np.nonzero(both)[0], np.nonzero(~both)[0]]).astype(np.int32)
         cost = both.sum() + 0.5 * (~both).sum()
-        self.fill_fwd = nbl / max(cost * T * T, 1)
+        self.pair_slots = float(cost * T * T)            # antenna pairs the forward computes
+        self.fill_fwd = nbl / max(self.pair_slots, 1)
         self.fill_bwd = nbl / float(self.na_pad ** 2)
         self.usable = (self.unique and nbl > 0 and self.fill_fwd >= ANT_FWD_MIN_FILL
                        and self.fill_bwd >= ANT_BWD_MIN_FILL)
@@ -586,7 +589,7 @@ class AntTiling:
             G = torch.nn.functional.pad(torch.view_as_real(G), (0, 0, 0, nfp - nf))
             G = torch.view_as_complex(G)
         Gq = G.permute(1, 2, 0)                                   # (nt, nfp, nbl)
-        H = torch.zeros(nt, nfp, self.nblk, self.na_pad // st, st, T, dtype=G.dtype,
+        H = torch.zeros(nt, nfp, self.nblk, self.nm_pad // st, st, T, dtype=G.dtype,
                         device=G.device)
         b, ms, r, pa = self.h_ji
         H[:, :, b, ms, r, pa] = Gq
@@ -654,7 +657,7 @@ class _AntFringeSum(torch.autograd.Function):
         dr = torch.zeros(tiling.na_pad, 3, dtype=torch.float64, device=dev) if need_r else None
         if tiling.nbl > 0 and nt > 0 and geom.S > 0 and (need_A or need_r):
             units, ubeg = geom.units(tiling.nbl, nchunk, sm_count(dev))
-            per_time = nfp * tiling.na_pad ** 2 * 8
+            per_time = nfp * tiling.na_pad * tiling.nm_pad * 8
             tstep = max(1, ANT_H_BUDGET // per_time)
             G = G.contiguous()
             for p in range(nplane):
@@ -671,7 +674,8 @@ class _AntFringeSum(torch.autograd.Function):
                     drpart = (torch.empty(u1 - u0, nfp, 2, tiling.na_pad, 4, dtype=torch.float64,
                                           device=dev) if need_r else None)
                     _call("antfringe_bwd", "f32", Hp, A[p], geom.shat, antv, freqs64, un,
-                          u1 - u0, tiling.na_pad, nfreq, geom.S, conj, dApart, drpart)
+                          u1 - u0, tiling.na_pad, tiling.nm_pad, nfreq, geom.S, conj, dApart,
+                          drpart)
                     if need_r:
                         dr = dr + drpart.sum(dim=(0, 1, 2))[:, :3]
                     del Hp

@@ -374,26 +374,48 @@ def main():
         with open(tpath) as f:
             tj = json.load(f)
         if tj.get("workload") == args.workload:
-            traffic = {kn.split("_kernel")[0]: v["dram_bytes_per_launch"]
-                       for kn, v in tj["kernels"].items()}
-    fwd_tf = rate("fringe_sum_fwd", FLOP_FWD)
-    roofline = dict(bound="fp32", kernel="fringe_sum_fwd_f32", achieved=fwd_tf,
-                    peak=fp32_meas / 1e3, unit="TFLOP/s",
-                    frac=(fwd_tf / (fp32_meas / 1e3)) if fwd_tf else None,
-                    peak_source="b200rime_microbench FFMA chains measured in this run "
-                                "(MEASURED_PEAKS.json has no FP32 figure)",
-                    peak_theoretical=fp32_theory,
-                    frac_of_theoretical=(fwd_tf / fp32_theory) if fwd_tf else None,
-                    flop_per_eval=FLOP_FWD, traffic=traffic.get("fringe_sum_fwd"),
-                    traffic_unit="DRAM bytes per launch (ncu dram__bytes_read+write, 1 time of C3)",
-                    ms_per_launch=k.get("fringe_sum_fwd", {}).get("ms", 0) /
-                    max(k.get("fringe_sum_fwd", {}).get("launches", 1), 1))
-    others = {}
-    for name, fl in (("fringe_sum_bwd_sky", FLOP_BWD_SKY), ("fringe_sum_bwd_bl", FLOP_BWD_BL)):
+            traffic = {kn.split("_kernel")[0].replace("ant_fringe", "antfringe"):
+                       v["dram_bytes_per_launch"] for kn, v in tj["kernels"].items()}
+    # FP32-bound kernels of the step and their ALGORITHMIC flop per evaluation (SURVEY 8(d):
+    # rotation recurrence 6 + multiply-accumulate 4 forward, 10 backward to the sky, 12 backward
+    # to the baseline / antenna vectors).  The antenna-factorised kernels do the same job with
+    # fewer executed flops (one complex multiply-accumulate = 8 flop per computed antenna pair);
+    # `achieved` uses the algorithmic count so that kernels doing the same work are comparable,
+    # `executed_tflops` is what the FP32 pipes actually ran.
+    fp32_kernels = (("fringe_sum_fwd", FLOP_FWD), ("fringe_sum_bwd_sky", FLOP_BWD_SKY),
+                    ("fringe_sum_bwd_bl", FLOP_BWD_BL), ("antfringe_fwd", FLOP_FWD),
+                    ("antfringe_bwd", FLOP_BWD_SKY + FLOP_BWD_BL))
+    executed = {}
+    tilings = [t for t in getattr(rime, "_ant_tilings", {}).values() if t is not None]
+    if tilings:
+        til = tilings[0]
+        nsrc_pad = sum(rec.geom.S for rec in rime._geom_cache.values())
+        nfp = -(-len(rime.array.freqs) // _lib.KC["f32"]) * _lib.KC["f32"]
+        executed["antfringe_fwd"] = 8.0 * til.pair_slots * nsrc_pad * nfp
+        executed["antfringe_bwd"] = 8.0 * til.na_pad * til.nm_pad * nsrc_pad * nfp
+
+    def entry(name, fl):
         r = rate(name, fl)
-        if r:
-            others[name] = dict(achieved=r, unit="TFLOP/s", frac=r / (fp32_meas / 1e3),
-                                frac_of_theoretical=r / fp32_theory, flop_per_eval=fl)
+        if not r:
+            return None
+        d = dict(bound="fp32", kernel=name + "_f32", achieved=r, peak=fp32_meas / 1e3,
+                 unit="TFLOP/s", frac=r / (fp32_meas / 1e3),
+                 peak_source="b200rime_microbench FFMA chains measured in this run "
+                             "(MEASURED_PEAKS.json has no FP32 figure)",
+                 peak_theoretical=fp32_theory, frac_of_theoretical=r / fp32_theory,
+                 flop_per_eval=fl, traffic=traffic.get(name),
+                 traffic_unit="DRAM bytes per launch (ncu dram__bytes_read+write)",
+                 ms_per_launch=k[name]["ms"] / max(k[name]["launches"], 1))
+        if name in executed:
+            ex = executed[name] * args.steps / (k[name]["ms"] * 1e-3) / 1e12
+            d.update(executed_tflops=ex, executed_frac=ex / (fp32_meas / 1e3))
+        return d
+
+    entries = {n: entry(n, fl) for n, fl in fp32_kernels}
+    entries = {n: e for n, e in entries.items() if e}
+    dominant = max(entries, key=lambda n: k[n]["ms"]) if entries else None
+    roofline = entries.get(dominant)
+    others = {n: e for n, e in entries.items() if n != dominant}
     hbm = None
     bname = "build_interp" if args.workload == "c3" else "build_airy"
     if bname in k and k[bname]["ms"] > 0:

@@ -235,7 +235,8 @@ int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double*
                                int ntile, int nbl, int nfreq, long long S, int conj, float* Vpart,
                                b200rime_stream_t stream);
 /* Backward of the same sum to the perceived sky and to the antenna positions in one pass.
- * Hp  [nt][Nfp][na_pad/64][na_pad/8][8][64][2]: Hermitian cotangent matrix
+ * Hp  [nt][Nfp][na_pad/64][nm_pad/8][8][64][2]: Hermitian cotangent matrix (nm_pad = number of
+ *     antennas rounded up to 16: the partner axis m is not padded to a whole block)
  *     H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m), 2 Re G_b for a = m (autos),
  *     indexed [time][channel][block of a][stage of m][m in stage][a in block], a stored at
  *     position ((a >> 1) & 3) * 16 + (a >> 3) * 2 + (a & 1) of its block.
@@ -244,8 +245,9 @@ int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double*
  *                                       first three axes), or NULL */
 int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* shat,
                                const double* antv, const double* freqs, const int* units,
-                               int nunits, int na_pad, int nfreq, long long S, int conj,
-                               float* dApart, double* drpart, b200rime_stream_t stream);
+                               int nunits, int na_pad, int nm_pad, int nfreq, long long S,
+                               int conj, float* dApart, double* drpart,
+                               b200rime_stream_t stream);
 
 /* ---- on-device peak measurements used as roofline denominators ---------------------
  * kind: 0 = FP32 FFMA chains, 1 = FP64 DFMA chains, 2 = MUFU sin+cos, 3 = packed FP32x2

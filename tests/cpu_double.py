@@ -229,11 +229,12 @@ def antfringe_fwd(sfx, A, shat, antv, freqs, units, nunits, tile_ant, tile_bl, t
                 vpart[u, e[sl] >> 1, :nfreq, 1] = V.imag.to(vpart.dtype)
 
 
-def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nfreq, S, conj, dApart,
-                  drpart):
+def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nm_pad, nfreq, S, conj,
+                  dApart, drpart):
     kc = _kc(sfx)
     T = _lib.ANT_TILE
     nt, nfp, nblk, nms, st, _, _ = Hp.shape
+    assert nms * st == nm_pad and nm_pad % 16 == 0
     pos = torch.as_tensor([ops._xpos(a) for a in range(T)])
     H = torch.complex(Hp[..., 0].double(), Hp[..., 1].double())[..., pos]   # [...][a in block]
     # (nt, nfp, nblk, nms, st, T) -> (nt, f, a, m)
@@ -243,7 +244,7 @@ def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nfreq, S
     for u in range(nunits):
         t, s0, s1, _ = [int(v) for v in units[u]]
         E = _ant_E(antv[:na_pad], shat[s0:s1], freqs[:nfreq], conj)         # (na_pad, nf, ns)
-        y = torch.einsum('fam,mfs->afs', H[t, :nfreq], E)
+        y = torch.einsum('fam,mfs->afs', H[t, :nfreq], E[:nm_pad])
         p = E.conj() * y
         if dApart is not None:
             half = 0.5 * p.real.reshape(nblk, T, nfreq, s1 - s0).sum(1)      # (nblk, nf, ns)
