@@ -334,7 +334,7 @@ ant_fringe_fwd_kernel(const float* __restrict__ A, const double* __restrict__ sh
 }
 
 // -------------------------------------------------------------------------------------
-// backward.  grid = (nblk * Nfp / 4, nunits), block = 384.
+// backward.  grid = (nunits, nblk * Nfp / 4), block = 384.
 // Slot item = (antenna block ib, channel k), channel fastest.  The slot walks the unit in tiles
 // of 64 sources and, per tile, reduces over all partner antennas m in stages of ANT_ST:
 //   X = H[a, m] for the 64 antennas a of block ib (TMA-staged from the pre-arranged Hermitian
@@ -357,12 +357,12 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = ant_slot_of(warp);
     const int half = (warp >> 2) & 1;
-    const int item = blockIdx.x * ANT_SLOTS + slot;
+    const int item = blockIdx.y * ANT_SLOTS + slot;
     const bool valid = item < nitems;
     const int ib = valid ? item / nk : 0;
     const int k = valid ? item % nk : 0;
     const int nblk = na_pad / ANT_TILE;
-    const int4 un = units[blockIdx.y];
+    const int4 un = units[blockIdx.x];
     const int nmst = nm_pad / ANT_ST;                  // partner-antenna stages per source tile
     const int nsrc_tiles = (un.z - un.y) / ANT_TILE;
     const bool active = valid && nsrc_tiles > 0;
@@ -486,7 +486,7 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
     if (need_r) {
         // sum the antenna gradients over the 4 thread-columns tj (lane bits 3, 4)
         const double twopi = 6.283185307179586476925286766559;
-        double* dst = drpart + ((((size_t)blockIdx.y * nk + k) * 2 + half) * (size_t)na_pad +
+        double* dst = drpart + ((((size_t)blockIdx.x * nk + k) * 2 + half) * (size_t)na_pad +
                                 ib * ANT_TILE + 8 * ti) * 4;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -543,7 +543,7 @@ int launch_ant_bwd(const float* Hp, const float* A, const double* shat, const do
         return set_error("antfringe_bwd: partner axis must be padded to 16 and fit na_pad");
     const int nfp = ((nfreq + ANT_KC - 1) / ANT_KC) * ANT_KC;
     const long long nitems = (long long)(na_pad / ANT_TILE) * nfp;
-    if (nitems / ANT_SLOTS > 2147483647LL || nunits > 65535)
+    if ((nitems + ANT_SLOTS - 1) / ANT_SLOTS > 65535)
         return set_error("antfringe_bwd: grid too large");
     static bool attr_set = false;
     if (!attr_set) {
@@ -551,7 +551,9 @@ int launch_ant_bwd(const float* Hp, const float* A, const double* shat, const do
                              AntSmem::TOTAL);
         attr_set = true;
     }
-    dim3 grid((unsigned)((nitems + ANT_SLOTS - 1) / ANT_SLOTS), nunits);
+    // units fastest: CTAs that run together share their (antenna block, channel) items, so a
+    // cotangent tile is fetched from HBM once and then served to the other units from L2
+    dim3 grid(nunits, (unsigned)((nitems + ANT_SLOTS - 1) / ANT_SLOTS));
     ant_fringe_bwd_kernel<<<grid, ANT_THREADS, AntSmem::TOTAL, st>>>(
         Hp, A, shat, antv, freqs, reinterpret_cast<const int4*>(units), (int)nitems, nfp, na_pad,
         nm_pad, nfreq, S, (conj ? -1.0 : 1.0) / C_LIGHT, dApart != nullptr, drpart != nullptr, dApart,
