@@ -363,7 +363,12 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
     const int k = valid ? item % nk : 0;
     const int nblk = na_pad / ANT_TILE;
     const int4 un = units[blockIdx.x];
-    const int nmst = nm_pad / ANT_ST;                  // partner-antenna stages per source tile
+    // partner-antenna stages per source tile.  Without the antenna gradient only dL/dA is wanted,
+    // Re(e^H H e) = 2 Re sum_{a > m} conj(E_a) H[a,m] E_m: the caller passes the lower triangle
+    // of H (doubled) and block ib stops after its own antennas -- 21 instead of 36 block products
+    // for six blocks
+    const int nmst_all = nm_pad / ANT_ST;
+    const int nmst = need_r ? nmst_all : min(nmst_all, (ib + 1) * (ANT_TILE / ANT_ST));
     const int nsrc_tiles = (un.z - un.y) / ANT_TILE;
     const bool active = valid && nsrc_tiles > 0;
 
@@ -377,7 +382,7 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
         // ---------------- producer warp: lane owns sources lane and lane + 32 of the tile
         setmaxnreg_dec<ANT_PROD_REGS_BWD>();
         if (!active) return;
-        const float* Hbase = Hp + ((((size_t)un.x * nk + k) * nblk + ib) * (size_t)nmst) *
+        const float* Hbase = Hp + ((((size_t)un.x * nk + k) * nblk + ib) * (size_t)nmst_all) *
                                       (AntSmem::X_BYTES / 4);
         long long g = 0;
         for (int st = 0; st < nsrc_tiles; ++st) {

@@ -575,14 +575,18 @@ class AntTiling:
         self.h_auto = t(np.nonzero(~cross)[0])
         ic, jc = i[cross], j[cross]
         self.h_ij = (t(ic // T), t(jc // st), t(jc % st), t(pos[ic % T]))  # H[a = i][m = j] = conj G
+        self.h_ij_all = (t(i // T), t(j // st), t(j % st), t(pos[i % T]))
+        self.h_jgt = t(np.nonzero(j > i)[0])      # pairs stored at H[j][i] in the lower triangle
+        self.h_igt = t(np.nonzero(i > j)[0])      # pairs stored at H[i][j] (conjugated)
 
     def antv4(self, antvecs):
         out = torch.zeros(self.na_pad, 4, dtype=torch.float64, device=self.tile_ant.device)
         out[:self.na, :3] = antvecs.detach().to(out.device, torch.float64)
         return out
 
-    def hermitian_cotangent(self, G, nfp):
-        """G (nbl, nt, nf) complex64 -> Hp in the kernel layout (float32 view)."""
+    def hermitian_cotangent(self, G, nfp, lower_only=False):
+        """G (nbl, nt, nf) complex64 -> Hp in the kernel layout (float32 view).  lower_only: the
+        doubled lower triangle (a > m), enough for dL/dA alone (include/b200rime.h)."""
         st, T = _lib.ANT_STAGE, _lib.ANT_TILE
         nbl, nt, nf = G.shape
         if nfp != nf:
@@ -591,10 +595,19 @@ class AntTiling:
         Gq = G.permute(1, 2, 0)                                   # (nt, nfp, nbl)
         H = torch.zeros(nt, nfp, self.nblk, self.nm_pad // st, st, T, dtype=G.dtype,
                         device=G.device)
-        b, ms, r, pa = self.h_ji
-        H[:, :, b, ms, r, pa] = Gq
-        b, ms, r, pa = self.h_ij
-        H[:, :, b, ms, r, pa] = Gq.index_select(2, self.h_cross).conj()
+        if lower_only:
+            # pair (i, j): H[j][i] = 2 G if j > i, else H[i][j] = 2 conj(G)
+            for idx, sel, conj in ((self.h_ji, self.h_jgt, False), (self.h_ij_all, self.h_igt, True)):
+                if len(sel) == 0:
+                    continue
+                b, ms, r, pa = [v.index_select(0, sel) for v in idx]
+                val = 2 * Gq.index_select(2, sel)
+                H[:, :, b, ms, r, pa] = val.conj() if conj else val
+        else:
+            b, ms, r, pa = self.h_ji
+            H[:, :, b, ms, r, pa] = Gq
+            b, ms, r, pa = self.h_ij
+            H[:, :, b, ms, r, pa] = Gq.index_select(2, self.h_cross).conj()
         if len(self.h_auto):
             b, ms, r, pa = [v.index_select(0, self.h_auto) for v in self.h_ji]
             H[:, :, b, ms, r, pa] = (2 * Gq.index_select(2, self.h_auto).real).to(G.dtype)
@@ -668,7 +681,7 @@ class _AntFringeSum(torch.autograd.Function):
                     u0, u1 = ubeg[ta], ubeg[tb]
                     if u1 == u0:
                         continue
-                    Hp = tiling.hermitian_cotangent(G[p, :, ta:tb], nfp)
+                    Hp = tiling.hermitian_cotangent(G[p, :, ta:tb], nfp, lower_only=not need_r)
                     un = units[u0:u1].clone()
                     un[:, 0] -= ta
                     drpart = (torch.empty(u1 - u0, nfp, 2, tiling.na_pad, 4, dtype=torch.float64,

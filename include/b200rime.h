@@ -240,6 +240,9 @@ int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double*
  *     H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m), 2 Re G_b for a = m (autos),
  *     indexed [time][channel][block of a][stage of m][m in stage][a in block], a stored at
  *     position ((a >> 1) & 3) * 16 + (a >> 3) * 2 + (a & 1) of its block.
+ *     When drpart is NULL (no antenna gradient) only the part of H with m < 64 (block of a + 1)
+ *     is read: pass the lower triangle H[a][m] = 2 G_b (b = (m, a)) / 2 conj(G_b) (b = (a, m)),
+ *     a > m, and H[a][a] = 2 Re G_b for autos, and the kernel does half the work.
  * dApart [na_pad/64][nchunk][S][KC]    partial dL/dA per antenna block (sum over blocks), or NULL
  * drpart [nunits][Nfp][2][na_pad][4]   float64 partial dL/d(antenna position) (sum over the
  *                                       first three axes), or NULL */

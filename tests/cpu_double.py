@@ -244,7 +244,12 @@ def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nm_pad, 
     for u in range(nunits):
         t, s0, s1, _ = [int(v) for v in units[u]]
         E = _ant_E(antv[:na_pad], shat[s0:s1], freqs[:nfreq], conj)         # (na_pad, nf, ns)
-        y = torch.einsum('fam,mfs->afs', H[t, :nfreq], E[:nm_pad])
+        Ht = H[t, :nfreq]
+        if drpart is None:      # only m < 64 (block of a + 1) is read
+            a_blk = torch.arange(nblk * T) // T
+            m_idx = torch.arange(nm_pad)
+            Ht = Ht * (m_idx[None, :] < (a_blk[:, None] + 1) * T)[None]
+        y = torch.einsum('fam,mfs->afs', Ht, E[:nm_pad])
         p = E.conj() * y
         if dApart is not None:
             half = 0.5 * p.real.reshape(nblk, T, nfreq, s1 - s0).sum(1)      # (nblk, nf, ns)
