@@ -350,8 +350,8 @@ __global__ void __launch_bounds__(ANT_THREADS, 1)
 ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
                       const double* __restrict__ shat, const double* __restrict__ antv,
                       const double* __restrict__ freqs, const int4* __restrict__ units, int nitems,
-                      int nk, int na_pad, int nm_pad, int nfreq, long long S, double sgn_over_c,
-                      int need_a, int need_r, float* __restrict__ dApart,
+                      int nk, int na, int na_pad, int nm_pad, int nfreq, long long S,
+                      double sgn_over_c, int need_a, int need_r, float* __restrict__ dApart,
                       double* __restrict__ drpart) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -370,7 +370,11 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
     const int nmst_all = nm_pad / ANT_ST;
     const int nmst = need_r ? nmst_all : min(nmst_all, (ib + 1) * (ANT_TILE / ANT_ST));
     const int nsrc_tiles = (un.z - un.y) / ANT_TILE;
-    const bool active = valid && nsrc_tiles > 0;
+    // a last block with at most 32 antennas is "narrow": one consumer warp covers its 32 antennas
+    // x all 64 sources (thread: 8 antennas x 8 sources, 4 x 8 threads), the other one retires
+    const bool narrow = na - ib * ANT_TILE <= ANT_TILE / 2;
+    const bool active = valid && nsrc_tiles > 0 &&
+                        !(narrow && half == 1 && warp < ANT_CONSUMERS / 32);
 
     ant_init_barriers(smem, tid, lane, warp, active, 2);     // producer warp + TMA expect_tx
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + AntSmem::BAR_OFF) + slot * ANT_NSTAGE;
@@ -431,8 +435,9 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
     // ---------------- consumer warps
     setmaxnreg_inc<ANT_CONS_REGS_BWD>();
     if (!active) return;
-    const int ti = lane & 7, tj = lane >> 3;
-    const int yq = half * 8 + tj * 2;
+    const int ti = narrow ? (lane & 3) : (lane & 7);
+    const int tj = narrow ? (lane >> 2) : (lane >> 3);
+    const int yq = narrow ? tj * 2 : half * 8 + tj * 2;
     float gx[8], gy[8], gz[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) gx[i] = gy[i] = gz[i] = 0.f;
@@ -448,7 +453,8 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
         g += nmst;
         // ---- epilogue of this source tile: p = conj(E_a) y_a
         if (B200_ANT_PROBE == 3 && st > 0) continue;
-        const long long sb = (long long)un.y + (long long)st * ANT_TILE + 32 * half + 8 * tj;
+        const long long sb = (long long)un.y + (long long)st * ANT_TILE + (narrow ? 0 : 32 * half) +
+                             8 * tj;
         const float kf = (float)kappa;
         const float* Ak = A + (size_t)(k / ANT_KC) * (size_t)S * ANT_KC + (k % ANT_KC);
         float* dAk = dApart + ((size_t)ib * (nk / ANT_KC) + (k / ANT_KC)) * (size_t)S * ANT_KC +
@@ -479,17 +485,21 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
                 gz[i] = fmaf(w, sz, gz[i]);
             }
             if (need_a) {
-                // sum over the 8 thread-rows ti (lane bits 0..2), fixed order
+                // sum over the thread-rows ti (lane bits 0..2, or 0..1 in a narrow block), fixed
+                // order
                 dacc += __shfl_xor_sync(0xffffffffu, dacc, 1);
                 dacc += __shfl_xor_sync(0xffffffffu, dacc, 2);
-                dacc += __shfl_xor_sync(0xffffffffu, dacc, 4);
+                const float d4 = __shfl_xor_sync(0xffffffffu, dacc, 4);
+                if (!narrow) dacc += d4;
                 if (ti == 0) dAk[s * ANT_KC] = 0.5f * dacc;
             }
         }
     }
 
     if (need_r) {
-        // sum the antenna gradients over the 4 thread-columns tj (lane bits 3, 4)
+        // sum the antenna gradients over the thread-columns tj (lane bits 3, 4; 2..4 when narrow);
+        // rows the kernel does not own (second half, antennas 32.. of a narrow block) are zeroed
+        // by the caller
         const double twopi = 6.283185307179586476925286766559;
         double* dst = drpart + ((((size_t)blockIdx.x * nk + k) * 2 + half) * (size_t)na_pad +
                                 ib * ANT_TILE + 8 * ti) * 4;
@@ -498,6 +508,8 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
             float v[3] = {gx[i], gy[i], gz[i]};
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
+                const float v4 = __shfl_xor_sync(0xffffffffu, v[c], 4);
+                if (narrow) v[c] += v4;
                 v[c] += __shfl_xor_sync(0xffffffffu, v[c], 8);
                 v[c] += __shfl_xor_sync(0xffffffffu, v[c], 16);
             }
@@ -538,12 +550,13 @@ int launch_ant_fwd(const float* A, const double* shat, const double* antv, const
 }
 
 int launch_ant_bwd(const float* Hp, const float* A, const double* shat, const double* antv,
-                   const double* freqs, const int* units, int nunits, int na_pad, int nm_pad,
+                   const double* freqs, const int* units, int nunits, int na, int na_pad, int nm_pad,
                    int nfreq, long long S, int conj, float* dApart, double* drpart,
                    cudaStream_t st) {
     if (nunits <= 0 || na_pad <= 0 || nfreq <= 0) return 0;
     if (S % SRC_PAD) return set_error("antfringe_bwd: S must be a multiple of 128");
-    if (na_pad % ANT_TILE) return set_error("antfringe_bwd: antenna count must be padded to 64");
+    if (na_pad % ANT_TILE || na > na_pad || na <= na_pad - ANT_TILE)
+        return set_error("antfringe_bwd: na_pad must be the antenna count rounded up to 64");
     if (nm_pad % (ANT_ST >= 16 ? ANT_ST : 2 * ANT_ST) || nm_pad > na_pad || nm_pad <= 0)
         return set_error("antfringe_bwd: partner axis must be padded to 16 and fit na_pad");
     const int nfp = ((nfreq + ANT_KC - 1) / ANT_KC) * ANT_KC;
@@ -560,7 +573,7 @@ int launch_ant_bwd(const float* Hp, const float* A, const double* shat, const do
     // cotangent tile is fetched from HBM once and then served to the other units from L2
     dim3 grid(nunits, (unsigned)((nitems + ANT_SLOTS - 1) / ANT_SLOTS));
     ant_fringe_bwd_kernel<<<grid, ANT_THREADS, AntSmem::TOTAL, st>>>(
-        Hp, A, shat, antv, freqs, reinterpret_cast<const int4*>(units), (int)nitems, nfp, na_pad,
+        Hp, A, shat, antv, freqs, reinterpret_cast<const int4*>(units), (int)nitems, nfp, na, na_pad,
         nm_pad, nfreq, S, (conj ? -1.0 : 1.0) / C_LIGHT, dApart != nullptr, drpart != nullptr, dApart,
         drpart);
     return check_launch("antfringe_bwd");
@@ -581,10 +594,10 @@ int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double*
 }
 int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* shat,
                                const double* antv, const double* freqs, const int* units,
-                               int nunits, int na_pad, int nm_pad, int nfreq, long long S,
+                               int nunits, int na, int na_pad, int nm_pad, int nfreq, long long S,
                                int conj, float* dApart, double* drpart, void* stream) {
-    return b200rime::launch_ant_bwd(Hp, A, shat, antv, freqs, units, nunits, na_pad, nm_pad, nfreq,
-                                    S, conj, dApart, drpart, (cudaStream_t)stream);
+    return b200rime::launch_ant_bwd(Hp, A, shat, antv, freqs, units, nunits, na, na_pad, nm_pad,
+                                    nfreq, S, conj, dApart, drpart, (cudaStream_t)stream);
 }
 int b200rime_ant_tile(void) { return b200rime::ANT_TILE; }
 int b200rime_ant_stage(void) { return b200rime::ANT_ST; }

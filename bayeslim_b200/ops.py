@@ -684,11 +684,11 @@ class _AntFringeSum(torch.autograd.Function):
                     Hp = tiling.hermitian_cotangent(G[p, :, ta:tb], nfp, lower_only=not need_r)
                     un = units[u0:u1].clone()
                     un[:, 0] -= ta
-                    drpart = (torch.empty(u1 - u0, nfp, 2, tiling.na_pad, 4, dtype=torch.float64,
+                    drpart = (torch.zeros(u1 - u0, nfp, 2, tiling.na_pad, 4, dtype=torch.float64,
                                           device=dev) if need_r else None)
                     _call("antfringe_bwd", "f32", Hp, A[p], geom.shat, antv, freqs64, un,
-                          u1 - u0, tiling.na_pad, tiling.nm_pad, nfreq, geom.S, conj, dApart,
-                          drpart)
+                          u1 - u0, tiling.na, tiling.na_pad, tiling.nm_pad, nfreq, geom.S, conj,
+                          dApart, drpart)
                     if need_r:
                         dr = dr + drpart.sum(dim=(0, 1, 2))[:, :3]
                     del Hp

@@ -245,11 +245,13 @@ int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double*
  *     a > m, and H[a][a] = 2 Re G_b for autos, and the kernel does half the work.
  * dApart [na_pad/64][nchunk][S][KC]    partial dL/dA per antenna block (sum over blocks), or NULL
  * drpart [nunits][Nfp][2][na_pad][4]   float64 partial dL/d(antenna position) (sum over the
- *                                       first three axes), or NULL */
+ *                                       first three axes), or NULL; ZERO it before the call: a last
+ *                                       block of at most 32 antennas (na - 64 (na_pad/64 - 1))
+ *                                       is processed by one warp that writes its own rows only */
 int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* shat,
                                const double* antv, const double* freqs, const int* units,
-                               int nunits, int na_pad, int nm_pad, int nfreq, long long S,
-                               int conj, float* dApart, double* drpart,
+                               int nunits, int na, int na_pad, int nm_pad, int nfreq,
+                               long long S, int conj, float* dApart, double* drpart,
                                b200rime_stream_t stream);
 
 /* ---- on-device peak measurements used as roofline denominators ---------------------

@@ -229,8 +229,9 @@ def antfringe_fwd(sfx, A, shat, antv, freqs, units, nunits, tile_ant, tile_bl, t
                 vpart[u, e[sl] >> 1, :nfreq, 1] = V.imag.to(vpart.dtype)
 
 
-def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nm_pad, nfreq, S, conj,
+def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na, na_pad, nm_pad, nfreq, S, conj,
                   dApart, drpart):
+    assert na_pad - _lib.ANT_TILE < na <= na_pad
     kc = _kc(sfx)
     T = _lib.ANT_TILE
     nt, nfp, nblk, nms, st, _, _ = Hp.shape
@@ -260,8 +261,7 @@ def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na_pad, nm_pad, 
         if drpart is not None:
             w = p.imag * (Af[:, s0:s1] * freqs.double()[:nfreq, None])[None]  # (na_pad, nf, ns)
             g = torch.einsum('afs,sc->fac', w, shat[s0:s1, :3].double())
-            drpart[u].zero_()
-            drpart[u, :nfreq, 0, :, :3] = sgn * 2 * math.pi / C * g
+            drpart[u, :nfreq, 0, :na, :3] = (sgn * 2 * math.pi / C * g)[:, :na]   # caller zeroed
 
 
 _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,

@@ -142,6 +142,7 @@ def _antenna_problem(na, seed):
 @pytest.mark.parametrize("na,nfreq,ns_list", [
     (70, 70, [300, 0, 64]),        # two antenna blocks, empty time, Nf % 64 != 0
     (130, 20, [520]),              # three blocks (64, 64, 2), several source tiles per unit
+    (100, 24, [200]),              # last block of 36 antennas: not narrow (> 32)
 ])
 def test_antenna_factorised_fringe_sum(na, nfreq, ns_list):
     """float32 antenna-factorised kernels (conj(E_i) E_j complex MACs) against the float64
