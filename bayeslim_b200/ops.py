@@ -529,6 +529,8 @@ class AntTiling:
         self.na_pad = self.nblk * T
         mq = max(16, _lib.ANT_STAGE)
         self.nm_pad = -(-self.na // mq) * mq          # partner axis of the backward, padded to 16
+        # output rows the backward computes: a last block of <= 32 antennas runs half-width
+        self.bwd_rows = self.na_pad - (T // 2 if self.na - (self.nblk - 1) * T <= T // 2 else 0)
         bi, bj = i // T, j // T
         swap = (bi > bj) | ((bi == bj) & (i > j))        # fold onto the upper triangle
         x = np.where(swap, j, i)

@@ -392,7 +392,7 @@ def main():
         nsrc_pad = sum(rec.geom.S for rec in rime._geom_cache.values())
         nfp = -(-len(rime.array.freqs) // _lib.KC["f32"]) * _lib.KC["f32"]
         executed["antfringe_fwd"] = 8.0 * til.pair_slots * nsrc_pad * nfp
-        executed["antfringe_bwd"] = 8.0 * til.na_pad * til.nm_pad * nsrc_pad * nfp
+        executed["antfringe_bwd"] = 8.0 * til.bwd_rows * til.nm_pad * nsrc_pad * nfp
 
     def entry(name, fl):
         r = rate(name, fl)
