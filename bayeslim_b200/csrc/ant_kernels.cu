@@ -465,7 +465,7 @@ ant_fringe_bwd_kernel(const float* __restrict__ Hp, const float* __restrict__ A,
             const long long s = sb + j;
             const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
             const double s2 = __ldg(shat + 4 * s + 2);
-            const float wk = __ldg(Ak + s * ANT_KC) * kf;
+            const float wk = need_r ? __ldg(Ak + s * ANT_KC) * kf : 0.f;   // A may be NULL
             const float sx = (float)s01.x, sy = (float)s01.y, sz = (float)s2;
             float dacc = 0.f;       // sum over own 8 antennas of Re p
 #pragma unroll

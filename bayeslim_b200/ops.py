@@ -467,40 +467,49 @@ class _FringeSum(torch.autograd.Function):
         A, blv, freqs64 = ctx.saved_tensors
         geom, nfreq, conj, uniform, bdtype, bdev, ashape = ctx.meta
         need_A, need_bl = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dev = G.device
-        rdtype = _real(G.dtype)
-        sfx = _sfx(G.dtype)
-        nplane, nchunk, _, kc = ashape
-        nfp = nchunk * kc
-        nbl, nt = blv.shape[0], geom.nt
-        dA = torch.zeros(ashape, dtype=rdtype, device=dev) if need_A else None
-        dbl = torch.zeros(nbl, 3, dtype=torch.float64, device=dev) if need_bl else None
-        if nbl > 0 and nt > 0 and geom.S > 0:
-            Gr = torch.view_as_real(G.contiguous())
-            # cotangent in kernel layout [t][chunk][baseline][KC] (zero padded in frequency): a
-            # tile of baselines is one contiguous block for the TMA engine
-            Gp = torch.zeros(nt, nchunk, nbl, kc, 2, dtype=rdtype, device=dev)
-            Gv = Gp.permute(2, 0, 1, 3, 4)                     # (nbl, nt, nchunk, kc, 2) view
-            pad = nfp - nfreq
-            for p in range(nplane):
-                src = Gr[p] if pad == 0 else torch.nn.functional.pad(Gr[p], (0, 0, 0, pad))
-                Gv.copy_(src.reshape(nbl, nt, nchunk, kc, 2))
-                if need_A:
-                    _call("fringe_sum_bwd_sky", sfx, Gp, geom.shat, blv, freqs64,
-                          geom.tile_time, nbl, nt, nfreq, geom.S, conj, uniform, dA[p])
-                if need_bl:
-                    units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
-                    per_unit = nchunk * nbl * 32
-                    step = min(max(1, (VPART_BUDGET // 4) // per_unit), MAX_GRID_UNITS)
-                    for u0 in range(0, units.shape[0], step):
-                        nun = min(step, units.shape[0] - u0)
-                        part = torch.empty(nun, nchunk, nbl, 4, dtype=torch.float64, device=dev)
-                        _call("fringe_sum_bwd_bl", sfx, Gp, A[p], geom.shat, blv,
-                              freqs64, units[u0:], nun, nbl, nt, nfreq, geom.S, conj, uniform,
-                              part)
-                        dbl = dbl + part.sum(dim=(0, 1))[:, :3]
+        dA, dbl = _fringe_backward(G, A, blv, geom, freqs64, nfreq, conj, uniform, ashape, need_A,
+                                   need_bl)
         gbl = dbl.to(device=bdev, dtype=bdtype) if need_bl else None
         return dA, gbl, None, None, None, None, None
+
+
+def _fringe_backward(G, A, blv, geom, freqs64, nfreq, conj, uniform, ashape, need_A, need_bl):
+    """Adjoints of the fringe sum for a cotangent G (nplane, Nbl, Nt, Nf) complex:
+    dA[p, k, s] = sum_b Re(conj(F_bsk) G[p, b, t(s), k]) in the tiled layout and, with the saved
+    perceived sky A, dL/d(blvecs) (Nbl, 3) float64."""
+    dev = G.device
+    rdtype = _real(G.dtype)
+    sfx = _sfx(G.dtype)
+    nplane, nchunk, _, kc = ashape
+    nfp = nchunk * kc
+    nbl, nt = blv.shape[0], geom.nt
+    dA = torch.zeros(ashape, dtype=rdtype, device=dev) if need_A else None
+    dbl = torch.zeros(nbl, 3, dtype=torch.float64, device=dev) if need_bl else None
+    if nbl > 0 and nt > 0 and geom.S > 0:
+        Gr = torch.view_as_real(G.contiguous())
+        # cotangent in kernel layout [t][chunk][baseline][KC] (zero padded in frequency): a
+        # tile of baselines is one contiguous block for the TMA engine
+        Gp = torch.zeros(nt, nchunk, nbl, kc, 2, dtype=rdtype, device=dev)
+        Gv = Gp.permute(2, 0, 1, 3, 4)                     # (nbl, nt, nchunk, kc, 2) view
+        pad = nfp - nfreq
+        for p in range(nplane):
+            src = Gr[p] if pad == 0 else torch.nn.functional.pad(Gr[p], (0, 0, 0, pad))
+            Gv.copy_(src.reshape(nbl, nt, nchunk, kc, 2))
+            if need_A:
+                _call("fringe_sum_bwd_sky", sfx, Gp, geom.shat, blv, freqs64,
+                      geom.tile_time, nbl, nt, nfreq, geom.S, conj, uniform, dA[p])
+            if need_bl:
+                units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
+                per_unit = nchunk * nbl * 32
+                step = min(max(1, (VPART_BUDGET // 4) // per_unit), MAX_GRID_UNITS)
+                for u0 in range(0, units.shape[0], step):
+                    nun = min(step, units.shape[0] - u0)
+                    part = torch.empty(nun, nchunk, nbl, 4, dtype=torch.float64, device=dev)
+                    _call("fringe_sum_bwd_bl", sfx, Gp, A[p], geom.shat, blv,
+                          freqs64, units[u0:], nun, nbl, nt, nfreq, geom.S, conj, uniform,
+                          part)
+                    dbl = dbl + part.sum(dim=(0, 1))[:, :3]
+    return dA, dbl
 
 
 # ----------------------------------------------------------- antenna-factorised fringe sum
@@ -664,44 +673,52 @@ class _AntFringeSum(torch.autograd.Function):
         A, antv, freqs64 = ctx.saved_tensors
         geom, nfreq, conj, tiling, adtype, adev, ashape_ant = ctx.meta
         need_A, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dev = G.device
-        nplane, nchunk, _, kc = A.shape
-        nfp = nchunk * kc
-        nt = geom.nt
-        dA = torch.zeros_like(A) if need_A else None
-        dr = torch.zeros(tiling.na_pad, 3, dtype=torch.float64, device=dev) if need_r else None
-        if tiling.nbl > 0 and nt > 0 and geom.S > 0 and (need_A or need_r):
-            units, ubeg = geom.units(tiling.nbl, nchunk, sm_count(dev))
-            per_time = nfp * tiling.na_pad * tiling.nm_pad * 8
-            tstep = max(1, ANT_H_BUDGET // per_time)
-            G = G.contiguous()
-            for p in range(nplane):
-                dApart = (torch.zeros(tiling.nblk, nchunk, A.shape[2], kc, dtype=torch.float32,
-                                      device=dev) if need_A else None)
-                for ta in range(0, nt, tstep):
-                    tb = min(nt, ta + tstep)
-                    u0, u1 = ubeg[ta], ubeg[tb]
-                    if u1 == u0:
-                        continue
-                    Hp = tiling.hermitian_cotangent(G[p, :, ta:tb], nfp, lower_only=not need_r)
-                    un = units[u0:u1].clone()
-                    un[:, 0] -= ta
-                    drpart = (torch.zeros(u1 - u0, nfp, 2, tiling.na_pad, 4, dtype=torch.float64,
-                                          device=dev) if need_r else None)
-                    _call("antfringe_bwd", "f32", Hp, A[p], geom.shat, antv, freqs64, un,
-                          u1 - u0, tiling.na, tiling.na_pad, tiling.nm_pad, nfreq, geom.S, conj,
-                          dApart, drpart)
-                    if need_r:
-                        dr = dr + drpart.sum(dim=(0, 1, 2))[:, :3]
-                    del Hp
-                if need_A:
-                    dA[p] = dApart.sum(0)
+        dA, dr = _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, A.shape, need_A,
+                               need_r)
         gant = None
         if need_r:
-            gant = torch.zeros(ashape_ant, dtype=torch.float64, device=dev)
+            gant = torch.zeros(ashape_ant, dtype=torch.float64, device=G.device)
             gant[:tiling.na] = dr[:tiling.na]
             gant = gant.to(device=adev, dtype=adtype)
         return dA, gant, None, None, None, None, None
+
+
+def _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, ashape, need_A, need_r):
+    """Antenna-factorised adjoints for a cotangent G (nplane, Nbl, Nt, Nf) complex64: dA in the
+    tiled layout and dL/d(antenna positions) (na_pad, 3) float64 (needs the perceived sky A)."""
+    dev = G.device
+    nplane, nchunk, S, kc = ashape
+    nfp = nchunk * kc
+    nt = geom.nt
+    dA = torch.zeros(ashape, dtype=torch.float32, device=dev) if need_A else None
+    dr = torch.zeros(tiling.na_pad, 3, dtype=torch.float64, device=dev) if need_r else None
+    if tiling.nbl > 0 and nt > 0 and geom.S > 0 and (need_A or need_r):
+        units, ubeg = geom.units(tiling.nbl, nchunk, sm_count(dev))
+        per_time = nfp * tiling.na_pad * tiling.nm_pad * 8
+        tstep = max(1, ANT_H_BUDGET // per_time)
+        G = G.contiguous()
+        for p in range(nplane):
+            dApart = (torch.zeros(tiling.nblk, nchunk, S, kc, dtype=torch.float32, device=dev)
+                      if need_A else None)
+            for ta in range(0, nt, tstep):
+                tb = min(nt, ta + tstep)
+                u0, u1 = ubeg[ta], ubeg[tb]
+                if u1 == u0:
+                    continue
+                Hp = tiling.hermitian_cotangent(G[p, :, ta:tb], nfp, lower_only=not need_r)
+                un = units[u0:u1].clone()
+                un[:, 0] -= ta
+                drpart = (torch.zeros(u1 - u0, nfp, 2, tiling.na_pad, 4, dtype=torch.float64,
+                                      device=dev) if need_r else None)
+                _call("antfringe_bwd", "f32", Hp, A[p] if need_r else None, geom.shat, antv,
+                      freqs64, un, u1 - u0, tiling.na, tiling.na_pad, tiling.nm_pad, nfreq,
+                      geom.S, conj, dApart, drpart)
+                if need_r:
+                    dr = dr + drpart.sum(dim=(0, 1, 2))[:, :3]
+                del Hp
+            if need_A:
+                dA[p] = dApart.sum(0)
+    return dA, dr
 
 
 def fringe_sum_ant(A, antvecs, tiling, geom, freqs64, nfreq, conj=False):
@@ -709,6 +726,40 @@ def fringe_sum_ant(A, antvecs, tiling, geom, freqs64, nfreq, conj=False):
     antvecs (Na, 3), through the antenna-factorised float32 kernels; gradients flow to A and
     straight to antvecs."""
     return _AntFringeSum.apply(A, antvecs, geom, freqs64, nfreq, conj, tiling)
+
+
+def fringe_adjoint(G, geom, freqs64, nfreq, blvecs=None, antvecs=None, tiling=None, conj=False,
+                   uniform=True):
+    """The adjoint (imaging) operator of fringe_sum, without autograd: for visibilities
+    G (nplane, Nbl, Nt, Nf) complex returns D (nplane, nchunk, S, KC) real with
+    D[p, k, s] = sum_b Re(conj(F_bsk) G[p, b, t(s), k]) -- the dirty-map sum of the reference's
+    imaging.make_map (imaging.py:736, A = conj(fringe), imaging.py:293).  With `tiling` (and
+    antenna positions) the antenna-factorised kernel walks one triangle of the Hermitian matrix."""
+    _need_cuda(G, freqs64)
+    nchunk = nchunks(nfreq, G.dtype)
+    ashape = (G.shape[0], nchunk, max(geom.S, 1), _lib.KC[_sfx(G.dtype)])
+    if tiling is not None and G.dtype == torch.complex64:
+        return _ant_backward(G, None, tiling.antv4(antvecs), geom, freqs64, nfreq, int(conj),
+                             tiling, ashape, True, False)[0]
+    blv = _blv4(blvecs, G.device)
+    return _fringe_backward(G, None, blv, geom, freqs64, nfreq, int(conj), int(uniform), ashape,
+                            True, False)[0]
+
+
+def unpack_planes(geom, A, nfreq):
+    """Tiled A (nplane, nchunk, S, KC) -> list over times of row-major (nplane, Nf, Ns_t)."""
+    _need_cuda(A)
+    sfx = _sfx(A.dtype)
+    A = A.contiguous()
+    out = []
+    for t in range(geom.nt):
+        X = torch.zeros(A.shape[0], nfreq, geom.ns[t], dtype=A.dtype, device=A.device)
+        if geom.ns[t]:
+            for p in range(A.shape[0]):
+                _call("unpack", sfx, A[p], geom.ns[t], nfreq, geom.ns[t], geom.toff[t], geom.S,
+                      X[p])
+        out.append(X)
+    return out
 
 
 def fringe_sum(A, blvecs, geom, freqs64, nfreq, conj=False, uniform=True):

@@ -243,6 +243,7 @@ int b200rime_antfringe_fwd_f32(const float* A, const double* shat, const double*
  *     When drpart is NULL (no antenna gradient) only the part of H with m < 64 (block of a + 1)
  *     is read: pass the lower triangle H[a][m] = 2 G_b (b = (m, a)) / 2 conj(G_b) (b = (a, m)),
  *     a > m, and H[a][a] = 2 Re G_b for autos, and the kernel does half the work.
+ *     A is only read for the antenna gradient and may be NULL together with drpart.
  * dApart [na_pad/64][nchunk][S][KC]    partial dL/dA per antenna block (sum over blocks), or NULL
  * drpart [nunits][Nfp][2][na_pad][4]   float64 partial dL/d(antenna position) (sum over the
  *                                       first three axes), or NULL; ZERO it before the call: a last

@@ -534,3 +534,67 @@ def rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=180.0, powerbeam=T
             v = torch.index_select(v, 2, sim2data)
         vis.append(v)
     return torch.stack(vis, dim=3)
+
+
+# --------------------------------------------------------------------------
+# imaging: the adjoint of the same operator
+# --------------------------------------------------------------------------
+def imaging_matrix(blvecs, zen, az, freqs, beam=None):
+    """A (Nbl, Nf, Ns) = conj(fringe) * beam: VisMapper.build_A, imaging.py:289-296."""
+    A = gen_fringe(blvecs, zen, az, freqs, conj=True)
+    if beam is not None:
+        A = A * beam.to(A.dtype)[None]
+    return A
+
+
+def vismapper_make_map(v, w, blvecs, zenaz, freqs, npix, beam_fn=None, fov=180.0, method='A2w',
+                       clip=1e-8):
+    """VisMapper.make_map with contract='diag' (imaging.py:362-478) restated.
+
+    v (Nbl, Nt, Nf) complex visibilities, w (Nbl, Nt, Nf) weights or None (= 1), zenaz list over
+    times of (zen, az) [deg] of all Npix pixels, beam_fn(zen_cut, az_cut) -> (Nf, Ns) power beam
+    or None.  With a beam the cut is the beam's strict zen < fov/2 (beam_model.py:221-224),
+    without it zen <= fov/2 (imaging.py:285).  Returns (maps, P, D), each (Nf, Npix)."""
+    freqs = torch.as_tensor(freqs, dtype=torch.float64)
+    nf = len(freqs)
+    maps = torch.zeros(nf, npix, dtype=torch.float64)
+    P = torch.zeros(nf, npix, dtype=torch.float64)
+    Aw = torch.zeros(nf, 1 if method == 'w' else npix, dtype=torch.float64)
+    for t, (zen, az) in enumerate(zenaz):
+        zen, az = torch.as_tensor(zen), torch.as_tensor(az)
+        if beam_fn is not None:
+            cut = fov_cut(zen, fov)
+            beam = beam_fn(zen[cut], az[cut])
+        else:
+            cut = torch.where(zen <= fov / 2)[0]
+            beam = None
+        A = imaging_matrix(blvecs, zen[cut], az[cut], freqs, beam)
+        wt = torch.ones(v.shape[0], nf, dtype=torch.float64) if w is None else w[:, t].double()
+        vt = v[:, t].to(A.dtype)
+        maps[:, cut] += torch.einsum('vfp,vf->fp', A, vt * wt).real          # imaging.py:736
+        P[:, cut] += (wt[..., None] * A.abs().pow(2)).sum(0).real           # imaging.py:850
+        if method == 'w':
+            Aw += wt.sum(0)[:, None]                                         # imaging.py:460
+        elif method == 'Aw':
+            Aw[:, cut] += (wt[:, :, None] * A.abs()).sum(0)                  # imaging.py:462
+        else:
+            Aw[:, cut] += (wt[:, :, None] * A.pow(2).real).sum(0)            # imaging.py:464
+    D = 1 / Aw.clip(clip)                                                    # imaging.py:469
+    return maps * D, P * D, D
+
+
+def vismapper_compute_Am(maps, blvecs, zenaz, freqs, beam_fn=None, fov=180.0):
+    """VisMapper.compute_Am (imaging.py:480-540): v[m, b, t, f] = sum_p conj(A[b, f, p]) maps[m, f, p]."""
+    freqs = torch.as_tensor(freqs, dtype=torch.float64)
+    out = []
+    for zen, az in zenaz:
+        zen, az = torch.as_tensor(zen), torch.as_tensor(az)
+        if beam_fn is not None:
+            cut = fov_cut(zen, fov)
+            beam = beam_fn(zen[cut], az[cut])
+        else:
+            cut = torch.where(zen <= fov / 2)[0]
+            beam = None
+        A = imaging_matrix(blvecs, zen[cut], az[cut], freqs, beam)
+        out.append(torch.einsum("vfp,mfp->mvf", A.conj(), maps[..., cut].to(A.dtype)))
+    return torch.stack(out, dim=2)

@@ -240,7 +240,7 @@ def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na, na_pad, nm_p
     H = torch.complex(Hp[..., 0].double(), Hp[..., 1].double())[..., pos]   # [...][a in block]
     # (nt, nfp, nblk, nms, st, T) -> (nt, f, a, m)
     H = H.permute(0, 1, 2, 5, 3, 4).reshape(nt, nfp, nblk * T, nms * st)
-    Af = _A_rows(A, nfreq).double()
+    Af = _A_rows(A, nfreq).double() if A is not None else None
     sgn = -1.0 if conj else 1.0
     for u in range(nunits):
         t, s0, s1, _ = [int(v) for v in units[u]]

@@ -397,6 +397,65 @@ def gold_rime_databls():
          sky_params=sparams, beam_params=bp, vis=vd.data, G=G, grad_sky=sky.params.grad, fov=180.0)
 
 
+def gold_vismapper():
+    """imaging.VisMapper: dirty maps, PSF diagonal and normalisation for the
+    three normalisation methods, weighted and unweighted, and compute_Am, hex-7 x 6 freqs x 3
+    times x 80 pixels, Airy power beam with a 150 deg field of view."""
+    rng = np.random.default_rng(77)
+    freqs = torch.linspace(120e6, 180e6, 6)
+    times = np.linspace(2458148.15, 2458148.25, 3)
+    ants, vecs, array = hera_array(2, freqs)
+    bls = [(ants[i], ants[j]) for i in range(len(ants)) for j in range(i + 1, len(ants))]
+    Npix = 80
+    ra = rng.uniform(0, 360, Npix)
+    dec = np.degrees(np.arcsin(rng.uniform(-1, np.sin(np.radians(29)), Npix)))
+    tel = ba.telescope_model.TelescopeModel(LOC)
+    data = cotangent((1, 1, len(bls), len(times), len(freqs)), 5)
+    icov = torch.as_tensor(rng.uniform(0.5, 2.0, data.shape))
+    vd = ba.dataset.VisData()
+    vd.setup_meta(telescope=tel, antpos=ba.utils.AntposDict(ants, torch.as_tensor(vecs)))
+    vd.setup_data(bls, times, freqs, pol='ee', data=data, icov=icov, cov_axis=None)
+    bp = torch.ones(1, 1, 1, 1, 1) * 14.0
+    beam = ba.beam_model.PixelBeam(bp.clone(), freqs, R=ba.beam_model.AiryResponse(powerbeam=True),
+                                   pol='e', powerbeam=True, fov=150, parameter=False)
+    zen_az = []
+    for t in times:
+        zen, az = orc.eq2top_synth(t, ra, dec, lat=LOC[1])
+        zen_az.append(np.stack([zen, az]))
+
+    def mapper(*args, **kwargs):
+        # the mapper works on its own copy of the VisData metadata: inject (zen, az) there
+        vm = ba.imaging.VisMapper(*args, **kwargs)
+        for t, za in zip(vm.times, zen_az):
+            vm.telescope.conv_cache[vm.telescope.hash(t, ra)] = torch.as_tensor(za)
+        return vm
+
+    out = {}
+    for weighted in (True, False):
+        vdw = vd if weighted else vd.copy()
+        if not weighted:
+            vdw.icov = None
+        vm = mapper(vdw, ra, dec, beam=beam)
+        for method in ('w', 'Aw', 'A2w'):
+            vm.set_normalization(method)
+            maps, P = vm.make_map(return_P=True, contract='diag')
+            tag = "%s_%s" % (method, 'icov' if weighted else 'ones')
+            out["maps_" + tag], out["P_" + tag], out["D_" + tag] = maps, P, vm.D
+    vm_nobeam = mapper(vd, ra, dec, beam=None, fov=120)
+    vm_nobeam.set_normalization('A2w')
+    maps_nb, P_nb = vm_nobeam.make_map(return_P=True, contract='diag')
+    test_maps = torch.as_tensor(rng.normal(size=(2, len(freqs), Npix)))
+    vm = mapper(vd, ra, dec, beam=beam)
+    Am = vm.compute_Am(test_maps)
+    vm.set_normalization('A2w')
+    vm.make_map(return_P=False)
+    Pm = vm.compute_Pm(test_maps, D=vm.D)
+    save("vismapper", antvecs=vecs, ants=ants, bls=bls, freqs=freqs, times=times, ra=ra, dec=dec,
+         zen_az=np.asarray(zen_az), vis=data, icov=icov, beam_params=bp, fov=150.0,
+         fov_nobeam=120.0, maps_nobeam=maps_nb, P_nobeam=P_nb, test_maps=test_maps, Am=Am, Pm=Pm,
+         **out)
+
+
 if __name__ == "__main__":
     gold_fringe()
     gold_airy()
@@ -408,3 +467,4 @@ if __name__ == "__main__":
     gold_rime_4pol()
     gold_rime_multimodel()
     gold_rime_databls()
+    gold_vismapper()
