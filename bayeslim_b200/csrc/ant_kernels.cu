@@ -2,26 +2,38 @@
 //
 // The fringe of baseline (i, j) is a product of two antenna terms,
 //     exp(2 pi i sgn (r_j - r_i).shat nu / c) = conj(E_i) E_j,   E_a = exp(2 pi i sgn r_a.shat nu / c),
-// so for a dense set of antenna pairs the source sum is, per channel, V = E^H diag(A) E.  A CTA
-// owns a 64 x 64 block of antenna pairs and 4 channels; every thread keeps a 4 x 4 block of
-// complex visibilities per channel in registers (128 accumulator registers) and the antenna
-// terms are generated on the fly by the CTA itself, straight from float64 phases (r_a.shat in
-// registers, fraction of a cycle in float64, MUFU sine/cosine), into a double-buffered shared
-// memory stage.  One source.baseline.channel evaluation is then a single complex
-// multiply-accumulate = 2 packed FFMA2 (4 FP32-pipe lane-cycles) instead of the 3 packed
-// instructions (6 lane-cycles) of the rotation-recurrence kernels in fringe_kernels.cu, and no
-// fringe -- per baseline or per antenna -- ever reaches HBM.  Still FP32 FMA pipes only: the
-// tensor cores are not used.
+// so for a dense set of antenna pairs the source sum is, per channel, V = E^H diag(A) E and one
+// source.baseline.channel evaluation is a single complex multiply-accumulate = 2 packed FFMA2
+// (4 FP32-pipe lane-cycles, every product a fused multiply-add) instead of the 3 packed
+// instructions (6 lane-cycles) of the rotation-recurrence kernels in fringe_kernels.cu.  The
+// antenna terms are generated on the fly inside the CTA, straight from float64 phases (r_a.shat
+// and the fraction of a cycle in float64, MUFU sine / cosine), so no fringe -- per baseline or per
+// antenna -- ever reaches HBM.  FP32 FMA pipes only: the tensor cores are not used.
 //
-// Operand layout in shared memory (per stage, per channel k and reduction index r):
-//   X[k][r][64]  complex (re, im) pairs, read as two warp-conflict-free LDS.128 per thread and
-//                used as scalar-broadcast FFMA2 operands (negation folded into the operand),
-//   YR/YI[k][r][64]  split real / imaginary rows, read as one LDS.128 each and used as packed
-//                pairs: accumulators pair two neighbouring outputs (re_j0, re_j1), (im_j0, im_j1).
+// Execution model (both kernels).  A CTA has 384 threads: warps 0..7 are consumers, warps 8..11
+// producers, with setmaxnreg moving registers from the producer warpgroup to the two consumer
+// warpgroups.  It runs four independent pipelines ("slots"), one per SM sub-partition: slot q owns
+// one (tile, channel) work item, a 4-stage shared-memory ring (8 KB per stage) and full / empty
+// mbarriers; its producer warp fills stages, its two consumer warps drain them.  A consumer thread
+// keeps an 8 x 8 block of complex outputs in 128 accumulator registers and reads, per reduction
+// index, 8 x-values and 8 y-values (8 LDS.128 per 128 FFMA2; a 4 x 4 tile would need exactly the
+// shared-memory bandwidth the SM has).
+//
+// Operand layout of a stage (ANT_ST reduction indices r):
+//   X[r][64]      complex (re, im) pairs in `xpos` order: a thread's 8 values are four 16-byte
+//                 quarters, each quarter contiguous over the 8 thread-rows of a quarter-warp, so
+//                 every LDS.128 phase reads 128 contiguous bytes.  Used as scalar-broadcast FFMA2
+//                 operands with the negation folded into the operand.
+//   YR/YI[r][64]  split real / imaginary rows, read as packed pairs: accumulators pair two
+//                 neighbouring outputs (re_j0, re_j1), (im_j0, im_j1), so the complex product
+//                 needs no swap, no negate and no extra instruction.
 // Forward:  X = E_i (conjugated in the product), Y = A_s E_j, reduction over sources.
-// Backward: X = H[a, m] (Hermitian cotangent matrix), Y = E_m over 64 sources, reduction over
-//           partner antennas m:  y_a = sum_m H[a, m] E_m, then with p = conj(E_a) y_a
-//           dA[s, k] = 1/2 sum_a Re p   and   dr_a = sum_{s,k} shat_s A[s,k] (2 pi sgn nu_k / c) Im p.
+// Backward: X = H[a, m] (Hermitian cotangent matrix, TMA bulk copies), Y = E_m over 64 sources,
+//           reduction over partner antennas m:  y_a = sum_m H[a, m] E_m, then with
+//           p = conj(E_a) y_a:  dL/dA[s, k] = 1/2 sum_a Re p  and
+//           dL/dr_a = sum_{s,k} shat_s A[s,k] (2 pi sgn nu_k / c) Im p.
+//           (H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m): sum_b Re(conj(F_b) G_b)
+//           = 1/2 e^H H e, and d/dr_a of it is the imaginary part of the same products.)
 //
 // Replaces, like fringe_kernels.cu, telescope_model.py:310-358 + rime_model.py:426-429 and their
 // autograd backward.  Every output has one owner and a fixed summation order.
