@@ -403,8 +403,10 @@ def main():
                  peak_source="b200rime_microbench FFMA chains measured in this run "
                              "(MEASURED_PEAKS.json has no FP32 figure)",
                  peak_theoretical=fp32_theory, frac_of_theoretical=r / fp32_theory,
-                 flop_per_eval=fl, traffic=traffic.get(name),
-                 traffic_unit="DRAM bytes per launch (ncu dram__bytes_read+write)",
+                 flop_per_eval=fl,
+                 traffic=(traffic[name] * nt if name in traffic else None),
+                 traffic_unit="DRAM bytes per launch: ncu dram__bytes_read+write of a 1-time launch "
+                              "(profiles/r01_traffic.json) x times per launch",
                  ms_per_launch=k[name]["ms"] / max(k[name]["launches"], 1))
         if name in executed:
             ex = executed[name] * args.steps / (k[name]["ms"] * 1e-3) / 1e12
