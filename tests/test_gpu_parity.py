@@ -212,6 +212,47 @@ def test_antenna_path_is_selected_and_matches_baseline_path(antpos):
         assert relmax(x, y, "ant_vs_bl_path/antpos%d/%s" % (antpos, nm)) < 2e-5, nm
 
 
+def test_c4_reduced_polarised_paths_agree():
+    """BASELINE config 4 at reduced size (HERA-350 all pairs, 4-pol Jones beams, nside-16 sky with
+    Stokes I, Q, U, 96 channels, 2 times): the tiled polarised route through the antenna-
+    factorised kernels against the same through the baseline-owned kernels, and a baseline /
+    channel subset against the float64 oracle."""
+    if DOUBLE:
+        pytest.skip("61075-baseline problem is too large for the CPU test double")
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["B200RIME_ANT"] = flag
+        try:
+            rime = workloads.pixel_interp_pol(16, 96, 2, DEV, torch.float32)
+            V = rime().data
+            assert tuple(V.shape) == (2, 2, 61075, 2, 96)
+            gen = torch.Generator().manual_seed(11)
+            G = torch.randn(V.shape, generator=gen, dtype=torch.float64).to(DEV)
+            torch.sum(G.to(V.real.dtype) * (V.real - 0.3 * V.imag)).backward()
+            out[flag] = (V.detach(), rime.sky.sky.params.grad, rime.beam.params.grad)
+        finally:
+            os.environ.pop("B200RIME_ANT", None)
+    for x, y, nm in zip(out["1"], out["0"], ("V", "dsky", "dbeam")):
+        assert relmax(x, y, "c4_reduced/ant_vs_bl/" + nm) < 2e-5, nm
+    # oracle on a subset: 40 baselines, all polarisations
+    sel = list(range(0, 61075, 1600))
+    with torch.no_grad():
+        sky = rime.sky.forward().data.cpu().double()                     # (2, 2, Nf, Npix)
+        bmap = rime.beam.params.detach().cpu().double()
+    freqs = rime.array.freqs.cpu().double()
+    R = rime.beam.R
+    theta, phi = R.theta_grid.cpu().double(), R.phi_grid.cpu().double()
+    zenaz = [(za[0].cpu().double(), za[1].cpu().double()) for za in workloads.zenaz_of(rime)]
+
+    def beam_fn(z, a):
+        inds, wgts = orc.rect_interp_weights(theta, phi, z, a, 'linear')
+        return orc.interp_map(bmap, inds, wgts)
+    bls = [rime.sim_bls[i] for i in sel]
+    Vo = orc.rime_forward(sky, zenaz, beam_fn, bls, rime.sim_blvecs.cpu().double()[sel], freqs,
+                          fov=180.0, powerbeam=False)
+    assert relmax(out["1"][0][:, :, sel], Vo, "c4_reduced/float32/V_vs_oracle") < 1e-5
+
+
 def test_forward_is_bitwise_reproducible():
     geom, zen, az, blv, freqs, planes = _rand_problem(200, 128, [500, 700], torch.float32, seed=3)
     X = [p.to(device=DEV, dtype=torch.float32) for p in planes]

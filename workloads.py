@@ -8,6 +8,8 @@ layouts, skies and beams are generated from fixed seeds.
   C2  HERA-37, 10k point sources, 256 freqs, 60 times, grads to sky
   C3  HERA-350, HEALPix nside-128 PixelSky, rect-grid interpolated PixelBeam, 1024 freqs,
       grads to sky, beam (and optionally antenna positions)
+  C4  HERA-350, 4-pol Jones beams, PixelSky with Stokes I, Q, U (pixel_interp_pol; parity-test
+      case at reduced nside, not a bench line)
 """
 import itertools
 import math
@@ -126,6 +128,62 @@ def pixel_interp(nside, n_freq, n_time, device, dtype=torch.float32, n_bl=None, 
     times = np.linspace(2458148.15, 2458148.25, n_time)
     rime = ba.RIME(sky, tel, beam, array, sim_bls, times, freqs, device=device)
     return rime
+
+
+class _CoherencySky(ba.utils.Module):
+    """PixelSky (Stokes I and polarisation fractions) followed by Stokes2Coherency: the
+    documented way to feed a polarised RIME (sky_model.py:1160-1353)."""
+
+    def __init__(self, sky):
+        super().__init__(name=sky.name)
+        self.sky = sky
+        self.s2c = ba.sky_model.Stokes2Coherency()
+        self.device = sky.device
+        self.angs = sky.angs
+
+    def forward(self, prior_cache=None):
+        return self.s2c(self.sky(prior_cache=prior_cache))
+
+
+def pixel_interp_pol(nside, n_freq, n_time, device, dtype=torch.float32, n_bl=None, seed=0,
+                     antpos_param=False, layout='hera350', dgrid=2.0):
+    """C4 family: 4-pol real Jones beams (2 feeds x 2 sky vectors) interpolated from rect-grid
+    maps, PixelSky with Stokes I, Q, U fractions -> real coherency."""
+    gen = torch.Generator(device='cpu').manual_seed(seed)
+    freqs = torch.linspace(100e6, 200e6, n_freq, dtype=torch.float64, device=device)
+    ants, vecs = hera350() if layout == 'hera350' else hera37()
+    array = make_array(ants, vecs, freqs, device, antpos_param)
+    sim_bls = all_cross_bls(ants)
+    if n_bl is not None:
+        step = max(1, len(sim_bls) // n_bl)
+        sim_bls = sim_bls[::step][:n_bl]
+    ra, dec = healpix_sky_angles(nside)
+    npix = len(ra)
+    spec = (freqs / 150e6) ** -2.5
+    base = torch.randn(npix, generator=gen).abs()
+    params = torch.zeros(3, 1, n_freq, npix, dtype=dtype)
+    params[0, 0] = (spec[:, None].cpu() * base[None, :]).to(dtype)
+    params[1, 0] = 0.1 * torch.randn(npix, generator=gen).to(dtype)[None]      # Q / I
+    params[2, 0] = 0.1 * torch.randn(npix, generator=gen).to(dtype)[None]      # U / I
+    pix = ba.sky_model.PixelSky(params.to(device), torch.as_tensor(np.stack([ra, dec]), device=device),
+                                ba.healpix.nside2pixarea(nside),
+                                R=ba.sky_model.PixelSkyResponse(freqs.to(dtype), device=device),
+                                parameter=True)
+    sky = _CoherencySky(pix)
+    theta, phi, airy = rect_airy_map(freqs, dgrid, dgrid, 14.0, dtype, device)
+    # voltage-like Jones maps: co-polar sqrt(Airy), cross-polar leakage with an azimuthal pattern
+    co = airy.clamp(min=0).sqrt()
+    b_phi, _ = torch.meshgrid(phi, theta, indexing='xy')
+    leak = 0.05 * torch.sin(2 * b_phi.ravel() * ba.D2R).to(dtype)[None] * co
+    jones = torch.stack([torch.stack([co, leak]), torch.stack([-leak, co])])[:, :, None]
+    R = ba.beam_model.PixelResponse(freqs, 'rect', interp_mode='linear', theta_grid=theta,
+                                    phi_grid=phi, freq_mode='channel', powerbeam=False,
+                                    realbeam=True, log=False, device=device)
+    beam = ba.beam_model.PixelBeam(jones.contiguous(), freqs, R=R, powerbeam=False, fov=180,
+                                   parameter=True)
+    tel = ba.telescope_model.TelescopeModel(LOCATION, device=device)
+    times = np.linspace(2458148.15, 2458148.25, n_time)
+    return ba.RIME(sky, tel, beam, array, sim_bls, times, freqs, device=device)
 
 
 def count_evals(rime):
