@@ -37,6 +37,9 @@ _SIGS = {
     "build_interp_bwd": [_P, _P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _L, _L, _P, _P, _L, _P, _P],
     "gather_times": [_P, _L, _P, _I, _I, _I, _P, _L, _P],
     "interp_transpose": [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P],
+    "apply_cal": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "apply_cal_bwd_gains": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P,
+                            _P],
     "build_airy": [_D, _D, _D, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P, _L, _P],
     "build_airy_bwd": [_P, _D, _D, _D, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _L, _L, _P, _P, _P,
                        _L, _P],

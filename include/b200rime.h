@@ -255,6 +255,39 @@ int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* sh
                                long long S, int conj, float* dApart, double* drpart,
                                b200rime_stream_t stream);
 
+/* ---- gain application --------------------------------------
+ * V_out = g_1 V g_2^H per baseline: reference calibration._apply_cal (calibration.py:2412-2487),
+ * the step that follows the RIME in a BayesLIM Sequential.
+ *   vis / out [npol][npol][nbl][nt][nf] complex; gains [npol][npol][nant][ntg][nfg] complex with
+ *   ntg in {1, nt}, nfg in {1, nf}; g1 / g2 [nbl] gain-table row of the first / second antenna.
+ *   full = 0: 1pol, or 2pol (4pol data, diagonal gains; off-diagonal outputs are zeroed as
+ *   linalg.diag_matmul does, linalg.py:116-149); full = 1 (npol = 2): 2x2 Jones products.
+ *   cov / cov_out: optional real variance of the data's shape, scaled by |g_1 conj(g_2)|^2
+ *   (diagonal modes only), else NULL. */
+int b200rime_apply_cal_f32(const float* vis, const float* gains, const int* g1, const int* g2,
+                           int npol, int full, int nbl, int nt, int nf, int nant, int ntg, int nfg,
+                           const float* cov, float* out, float* cov_out,
+                           b200rime_stream_t stream);
+int b200rime_apply_cal_f64(const double* vis, const double* gains, const int* g1, const int* g2,
+                           int npol, int full, int nbl, int nt, int nf, int nant, int ntg, int nfg,
+                           const double* cov, double* out, double* cov_out,
+                           b200rime_stream_t stream);
+/* Adjoint of the same product to the gains for a cotangent gout of the output's shape (the
+ * adjoint to vis is apply_cal itself with conjugate-transposed gains).  p1/b1 (p2/b2): CSR lists
+ * of the baselines in which an antenna is the first (second) one: p* [nant + 1], b* [nbl].
+ * dg [npol][npol][nant][nt][nf] complex: full time / frequency axes, fixed summation order; the
+ * caller sums the axes along which the gains broadcast. */
+int b200rime_apply_cal_bwd_gains_f32(const float* vis, const float* gains, const float* gout,
+                                     const int* g1, const int* g2, const int* p1, const int* b1,
+                                     const int* p2, const int* b2, int npol, int full, int nbl,
+                                     int nt, int nf, int nant, int ntg, int nfg, float* dg,
+                                     b200rime_stream_t stream);
+int b200rime_apply_cal_bwd_gains_f64(const double* vis, const double* gains, const double* gout,
+                                     const int* g1, const int* g2, const int* p1, const int* b1,
+                                     const int* p2, const int* b2, int npol, int full, int nbl,
+                                     int nt, int nf, int nant, int ntg, int nfg, double* dg,
+                                     b200rime_stream_t stream);
+
 /* ---- on-device peak measurements used as roofline denominators ---------------------
  * kind: 0 = FP32 FFMA chains, 1 = FP64 DFMA chains, 2 = MUFU sin+cos, 3 = packed FP32x2
  * FFMA2 chains.  Runs `iters`

@@ -598,3 +598,37 @@ def vismapper_compute_Am(maps, blvecs, zenaz, freqs, beam_fn=None, fov=180.0):
         A = imaging_matrix(blvecs, zen[cut], az[cut], freqs, beam)
         out.append(torch.einsum("vfp,mfp->mvf", A.conj(), maps[..., cut].to(A.dtype)))
     return torch.stack(out, dim=2)
+
+
+# --------------------------------------------------------------------------
+# gain application
+# --------------------------------------------------------------------------
+def apply_cal(vis, gains, g1_idx, g2_idx, cal_2pol=False, cov=None, undo=False):
+    """calibration._apply_cal for complex visibilities (calibration.py:2412-2487):
+    1pol / 2pol: vout[p][p] = g1[p][p] conj(g2[p][p]) vis[p][p] with the off-diagonal outputs zeroed
+    (linalg.diag_matmul, linalg.py:116-149), cov_out = |g1 conj g2|^2 cov (:2470-2476);
+    4pol: vout[a][d] = sum_{b,c} g1[a][b] vis[b][c] conj(g2[d][c]) (:2485).
+    undo (diagonal modes): gains -> 1 / gains on the diagonal, zero elsewhere (linalg.diag_inv)."""
+    polmode = '1pol' if tuple(vis.shape[:2]) == (1, 1) else ('2pol' if cal_2pol else '4pol')
+    if undo:
+        assert polmode != '4pol', "the reference's 4pol undo does not run (torch.pinv)"
+        inv = torch.zeros_like(gains)
+        for p in range(gains.shape[0]):
+            inv[p, p] = 1 / gains[p, p]
+        gains = inv
+    g1 = gains.index_select(2, g1_idx)
+    g2 = gains.index_select(2, g2_idx)
+    cov_out = cov
+    if polmode in ('1pol', '2pol'):
+        G = g1 * g2.conj()
+        vout = torch.zeros_like(vis)
+        for p in range(vis.shape[0]):
+            vout[p, p] = G[p, p] * vis[p, p]
+        if cov is not None:
+            GG = (G * G.conj()).real
+            cov_out = torch.zeros_like(cov)
+            for p in range(vis.shape[0]):
+                cov_out[p, p] = GG[p, p] * cov[p, p]
+    else:
+        vout = torch.einsum("ab...,bc...,dc...->ad...", g1, vis, g2.conj())
+    return vout, cov_out

@@ -264,13 +264,53 @@ def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na, na_pad, nm_p
             drpart[u, :nfreq, 0, :na, :3] = (sgn * 2 * math.pi / C * g)[:, :na]   # caller zeroed
 
 
+def _cplx(x):
+    return torch.complex(x[..., 0].double(), x[..., 1].double())
+
+
+def _cal_product(v, gains, g1, g2, full):
+    a = gains.index_select(2, g1.long())
+    c = gains.index_select(2, g2.long())
+    if full:
+        return torch.einsum("ab...,bc...,dc...->ad...", a, v, c.conj())
+    out = torch.zeros_like(v)
+    for p in range(v.shape[0]):
+        out[p, p] = a[p, p] * c[p, p].conj() * v[p, p]
+    return out
+
+
+def apply_cal(sfx, vis, gains, g1, g2, npol, full, nbl, nt, nf, nant, ntg, nfg, cov, out, cov_out):
+    v, g = _cplx(vis), _cplx(gains)
+    o = _cal_product(v, g, g1, g2, full)
+    out[..., 0], out[..., 1] = o.real.to(out.dtype), o.imag.to(out.dtype)
+    if cov is not None:
+        G = g.index_select(2, g1.long()) * g.index_select(2, g2.long()).conj()
+        cov_out.zero_()
+        for p in range(npol):
+            cov_out[p, p] = ((G[p, p].abs() ** 2) * cov[p, p].double()).to(cov_out.dtype)
+
+
+def apply_cal_bwd_gains(sfx, vis, gains, gout, g1, g2, p1, b1, p2, b2, npol, full, nbl, nt, nf, nant,
+                        ntg, nfg, dg):
+    # CSR lists must enumerate every baseline once per role
+    assert sorted(int(x) for x in b1) == list(range(nbl)) and int(p1[-1]) == nbl
+    assert sorted(int(x) for x in b2) == list(range(nbl)) and int(p2[-1]) == nbl
+    with torch.enable_grad():
+        g = _cplx(gains.detach()).expand(npol, npol, nant, nt, nf).clone().requires_grad_(True)
+        o = _cal_product(_cplx(vis.detach()), g, g1, g2, full)
+        G = _cplx(gout.detach())
+        (G.real * o.real + G.imag * o.imag).sum().backward()
+    dg[..., 0], dg[..., 1] = g.grad.real.to(dg.dtype), g.grad.imag.to(dg.dtype)
+
+
 _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
               fringe_sum_bwd_sky=fringe_sum_bwd_sky, fringe_sum_bwd_bl=fringe_sum_bwd_bl,
               pack=pack, unpack=unpack, build_interp=build_interp,
               build_interp_bwd=build_interp_bwd, interp_transpose=interp_transpose,
               gather_times=gather_times,
               build_airy=build_airy, build_airy_bwd=build_airy_bwd,
-              antfringe_fwd=antfringe_fwd, antfringe_bwd=antfringe_bwd)
+              antfringe_fwd=antfringe_fwd, antfringe_bwd=antfringe_bwd,
+              apply_cal=apply_cal, apply_cal_bwd_gains=apply_cal_bwd_gains)
 
 
 @contextlib.contextmanager

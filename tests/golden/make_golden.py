@@ -456,6 +456,41 @@ def gold_vismapper():
          **out)
 
 
+def gold_apply_cal():
+    """calibration._apply_cal: 1pol, 2pol (cal_2pol) and 4pol products, the
+    undo direction, broadcast gains, the covariance update and autograd gradients to vis and gains
+    for a fixed cotangent."""
+    rng = np.random.default_rng(21)
+    ants = [0, 1, 2, 3, 4, 5, 6]
+    bls = [(a, b) for a in ants for b in ants if a <= b][::2]          # crosses and autos
+    nbl, nt, nf = len(bls), 3, 5
+    c = lambda *shape: torch.as_tensor(rng.normal(size=shape) + 1j * rng.normal(size=shape))
+    out = dict(ants=ants, bls=bls)
+    for tag, npol, cal_2pol, gshape_tf in (("1pol", 1, False, (nt, nf)), ("2pol", 2, True, (nt, nf)),
+                                           ("4pol", 2, False, (nt, nf)), ("1pol_bcast", 1, False, (1, nf)),
+                                           ("4pol_bcast", 2, False, (nt, 1))):
+        vis = c(npol, npol, nbl, nt, nf).requires_grad_(True)
+        gains = (c(npol, npol, len(ants), *gshape_tf) * 0.3 + torch.eye(npol)[:, :, None, None, None]
+                 ).requires_grad_(True)
+        cov = torch.as_tensor(rng.uniform(0.5, 2, size=(npol, npol, nbl, nt, nf))) \
+            if tag in ("1pol", "2pol") else None
+        vout, cov_out = ba.calibration.apply_cal(vis, bls, gains, ants, cal_2pol=cal_2pol, cov=cov)
+        G = cotangent(vout.shape, 300 + npol)
+        backward_with(vout, G)
+        out.update({tag + "_vis": vis, tag + "_gains": gains, tag + "_out": vout, tag + "_G": G,
+                    tag + "_dvis": vis.grad, tag + "_dgains": gains.grad})
+        if not tag.startswith("4pol"):
+            # the reference's 4pol undo calls torch.pinv, which torch 2.11 does not have
+            # (calibration.py:2444), so only the diagonal modes have a reference answer
+            with torch.no_grad():
+                vundo, _ = ba.calibration.apply_cal(vis, bls, gains, ants, cal_2pol=cal_2pol,
+                                                    undo=True)
+            out[tag + "_undo"] = vundo
+        if cov is not None:
+            out.update({tag + "_cov": cov, tag + "_cov_out": cov_out})
+    save("apply_cal", **out)
+
+
 if __name__ == "__main__":
     gold_fringe()
     gold_airy()
@@ -468,3 +503,4 @@ if __name__ == "__main__":
     gold_rime_multimodel()
     gold_rime_databls()
     gold_vismapper()
+    gold_apply_cal()
