@@ -91,6 +91,69 @@ apply_cal_kernel(const CalC<T>* __restrict__ vis, const CalC<T>* __restrict__ ga
     }
 }
 
+// diagonal modes, two channels per thread (16-byte accesses for complex64) and two rows in flight:
+// a streaming kernel needs tens of KB of loads outstanding per SM to approach the HBM rate
+template <typename T> struct __align__(2 * sizeof(CalC<T>)) CalC2 { CalC<T> a, b; };
+template <typename T> struct __align__(2 * sizeof(T)) CalR2 { T a, b; };
+
+template <typename T, int NPOL>
+__global__ void __launch_bounds__(CAL_THREADS)
+apply_cal_diag2_kernel(const CalC<T>* __restrict__ vis, const CalC<T>* __restrict__ gains,
+                       const int* __restrict__ g1, const int* __restrict__ g2, int nbl, int nt,
+                       int nf, int nant, int ntg, int nfg, const T* __restrict__ cov,
+                       CalC<T>* __restrict__ out, T* __restrict__ cov_out) {
+    const int f = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (f >= nf) return;
+    const size_t vplane = (size_t)nbl * nt * nf;
+    const size_t gplane = (size_t)nant * ntg * nfg;
+    const long long rows = (long long)nbl * nt;
+#pragma unroll 2
+    for (long long row = blockIdx.y; row < rows; row += gridDim.y) {
+        const int b = (int)(row / nt), t = (int)(row % nt);
+        const int tg = ntg == 1 ? 0 : t;
+        const size_t vo = ((size_t)b * nt + t) * nf + f;
+        const size_t r1 = ((size_t)g1[b] * ntg + tg) * nfg, r2 = ((size_t)g2[b] * ntg + tg) * nfg;
+#pragma unroll
+        for (int p = 0; p < NPOL; ++p) {
+            const size_t pp = (size_t)(p * NPOL + p);
+            CalC<T> ga, gb, ha, hb;
+            if (nfg == 1) {
+                ga = gb = gains[pp * gplane + r1];
+                ha = hb = gains[pp * gplane + r2];
+            } else {
+                const CalC2<T> x = *reinterpret_cast<const CalC2<T>*>(gains + pp * gplane + r1 + f);
+                const CalC2<T> y = *reinterpret_cast<const CalC2<T>*>(gains + pp * gplane + r2 + f);
+                ga = x.a, gb = x.b, ha = y.a, hb = y.b;
+            }
+            const CalC<T> Ga = cmulc(ga, ha), Gb = cmulc(gb, hb);
+            const CalC2<T> v = *reinterpret_cast<const CalC2<T>*>(vis + pp * vplane + vo);
+            CalC2<T> o;
+            o.a = cmul(Ga, v.a);
+            o.b = cmul(Gb, v.b);
+            *reinterpret_cast<CalC2<T>*>(out + pp * vplane + vo) = o;
+            if (cov != nullptr) {
+                const CalR2<T> c = *reinterpret_cast<const CalR2<T>*>(cov + pp * vplane + vo);
+                CalR2<T> co;
+                co.a = (Ga.re * Ga.re + Ga.im * Ga.im) * c.a;
+                co.b = (Gb.re * Gb.re + Gb.im * Gb.im) * c.b;
+                *reinterpret_cast<CalR2<T>*>(cov_out + pp * vplane + vo) = co;
+            }
+        }
+        if (NPOL == 2) {
+            CalC2<T> z;
+            z.a = z.b = {0, 0};
+            *reinterpret_cast<CalC2<T>*>(out + 1 * vplane + vo) = z;
+            *reinterpret_cast<CalC2<T>*>(out + 2 * vplane + vo) = z;
+            if (cov != nullptr) {
+                CalR2<T> zr;
+                zr.a = zr.b = 0;
+                *reinterpret_cast<CalR2<T>*>(cov_out + 1 * vplane + vo) = zr;
+                *reinterpret_cast<CalR2<T>*>(cov_out + 2 * vplane + vo) = zr;
+            }
+        }
+    }
+}
+
 // adjoint to the gains: one thread per (antenna, t, f) walks the antenna's baselines in a fixed
 // order (CSR lists built by the caller: baselines where it is the first / the second antenna).
 //   dg[p][q][ant][t][f] (full time / frequency axes; the caller sums broadcast axes)
@@ -205,7 +268,19 @@ int launch_apply_cal(const T* vis, const T* gains, const int* g1, const int* g2,
     auto V = reinterpret_cast<const CalC<T>*>(vis);
     auto G = reinterpret_cast<const CalC<T>*>(gains);
     auto O = reinterpret_cast<CalC<T>*>(out);
-    if (npol == 1)
+    auto aligned = [](const void* q, size_t a) { return q == nullptr || ((uintptr_t)q % a) == 0; };
+    const size_t ca = 2 * sizeof(CalC<T>), ra = 2 * sizeof(T);
+    if (!full && nf % 2 == 0 && aligned(vis, ca) && aligned(gains, ca) && aligned(out, ca) &&
+        aligned(cov, ra) && aligned(cov_out, ra)) {
+        // even channel count and aligned bases: every row starts aligned, two channels per thread
+        dim3 grid2((nf / 2 + CAL_THREADS - 1) / CAL_THREADS, grid.y);
+        if (npol == 1)
+            apply_cal_diag2_kernel<T, 1><<<grid2, CAL_THREADS, 0, st>>>(V, G, g1, g2, nbl, nt, nf, nant,
+                                                                        ntg, nfg, cov, O, cov_out);
+        else
+            apply_cal_diag2_kernel<T, 2><<<grid2, CAL_THREADS, 0, st>>>(V, G, g1, g2, nbl, nt, nf, nant,
+                                                                        ntg, nfg, cov, O, cov_out);
+    } else if (npol == 1)
         apply_cal_kernel<T, 1, false><<<grid, CAL_THREADS, 0, st>>>(V, G, g1, g2, nbl, nt, nf, nant,
                                                                     ntg, nfg, cov, O, cov_out);
     else if (!full)
