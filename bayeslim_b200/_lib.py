@@ -34,6 +34,7 @@ _SIGS = {
     "pack": [_P, _L, _I, _I, _I, _L, _L, _P, _P],
     "unpack": [_P, _L, _I, _I, _L, _L, _P, _P],
     "build_interp": [_P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P],
+    "build_interp_t": [_P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P],
     "build_interp_bwd": [_P, _P, _L, _P, _P, _I, _P, _L, _P, _I, _I, _L, _L, _P, _P, _L, _P, _P],
     "gather_times": [_P, _L, _P, _I, _I, _I, _P, _L, _P],
     "interp_transpose": [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P],

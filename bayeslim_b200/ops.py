@@ -286,10 +286,18 @@ class _BuildInterp(torch.autograd.Function):
         kc = _lib.KC[sfx]
         S = max(geom.S, 1)
         A = torch.empty(1, nchunks(nfreq, dtype), S, kc, dtype=dtype, device=ref.device)
-        if geom.S > 0:
-            _call("build_interp", sfx, bmap, bmap.shape[1] if bmap is not None else 0, tab.inds,
-                  tab.wgts, tab.nnn, sky, sky.shape[1] if sky is not None else 0, tab.cut, nfreq,
-                  geom.S, geom.S, 0, geom.S, A[0])
+        if geom.S > 0 and bmap is not None:
+            # channel-major copy of the beam map (zero padded to whole chunks): neighbour reads
+            # become full 128-byte lines instead of 32 scattered pixels per load
+            nfp = A.shape[1] * kc
+            bT = torch.zeros(bmap.shape[1], nfp, dtype=dtype, device=ref.device)
+            bT[:, :nfreq] = bmap.t()
+            _call("build_interp_t", sfx, bT, nfp, tab.inds, tab.wgts, tab.nnn, sky,
+                  sky.shape[1] if sky is not None else 0, tab.cut, nfreq, geom.S, geom.S, 0,
+                  geom.S, A[0])
+        elif geom.S > 0:
+            _call("build_interp", sfx, None, 0, tab.inds, tab.wgts, tab.nnn, sky, sky.shape[1],
+                  tab.cut, nfreq, geom.S, geom.S, 0, geom.S, A[0])
         else:
             A.zero_()
         ctx.save_for_backward(sky, bmap)

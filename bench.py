@@ -419,14 +419,17 @@ def main():
     roofline = entries.get(dominant)
     others = {n: e for n, e in entries.items() if n != dominant}
     hbm = None
-    bname = "build_interp" if args.workload == "c3" else "build_airy"
+    bname = "build_airy"
+    if args.workload == "c3":
+        bname = "build_interp_t" if "build_interp_t" in k else "build_interp"
     if bname in k and k[bname]["ms"] > 0:
         rec = list(rime._geom_cache.values())[0]
         nf = len(rime.array.freqs)
         nsrc = sum(rec.geom.ns)
         npb = rime.beam.params.shape[-1] if args.workload == "c3" else 0
-        # per time: read beam map once, read sky at the cut, write A, read 4 idx + 4 wgt
-        bytes_step = 4 * nf * (npb * rec.geom.nt + 2 * nsrc) + 32 * nsrc
+        # per launch (all times of the step): read the beam map once, read sky at the cut,
+        # write A, read 4 idx + 4 wgt
+        bytes_step = 4 * nf * (npb + 2 * nsrc) + 32 * nsrc
         gbs = bytes_step * args.steps / (k[bname]["ms"] * 1e-3) / 1e9
         hbm = dict(bound="hbm", kernel=bname + "_f32", achieved=gbs, peak=peaks["hbm_gbs"],
                    unit="GB/s", frac=gbs / peaks["hbm_gbs"], peak_source=peaks["source"],

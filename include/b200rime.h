@@ -132,6 +132,17 @@ int b200rime_unpack_f64(const double* A, long long ldx, int nfreq, int ns, long 
  * polarised modes, beam_model.py:343-363, which torch then combines element-wise in the tiled
  * layout).  inds int32 [ns][nnn], wgts real [ns][nnn], cut int32 [ns]; cut[s] < 0 marks a padding entry
  * (A = 0), so one call with ns = ns_pad = S, soff = 0 builds every time of a group at once. */
+/* The same product from a channel-major beam map bmapT[npix_beam][ldt], ldt >= nchunk * KC, the
+ * channels beyond nfreq zero (bmapT must not be NULL; sky may be): every neighbour read is a full
+ * 128-byte line instead of 32 scattered pixels per load.  Same outputs as build_interp. */
+int b200rime_build_interp_t_f32(const float* bmapT, long long ldt, const int* inds,
+                                const float* wgts, int nnn, const float* sky, long long lds,
+                                const int* cut, int nfreq, int ns, int ns_pad, long long soff,
+                                long long S, float* A, b200rime_stream_t stream);
+int b200rime_build_interp_t_f64(const double* bmapT, long long ldt, const int* inds,
+                                const double* wgts, int nnn, const double* sky, long long lds,
+                                const int* cut, int nfreq, int ns, int ns_pad, long long soff,
+                                long long S, double* A, b200rime_stream_t stream);
 int b200rime_build_interp_f32(const float* bmap, long long ldb, const int* inds,
                               const float* wgts, int nnn, const float* sky, long long lds,
                               const int* cut, int nfreq, int ns, int ns_pad, long long soff,

@@ -127,6 +127,12 @@ def build_interp(sfx, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, ns_p
     pack(sfx, X.contiguous(), ns, nfreq, ns, ns_pad, soff, S, A)
 
 
+def build_interp_t(sfx, bmapT, ldt, inds, wgts, nnn, sky, lds, cut, nfreq, ns, ns_pad, soff, S, A):
+    assert bmapT.shape[1] == ldt and ldt % _kc(sfx) == 0 and float(bmapT[:, nfreq:].abs().sum()) == 0
+    build_interp(sfx, bmapT[:, :nfreq].t().contiguous(), bmapT.shape[0], inds, wgts, nnn, sky, lds,
+                 cut, nfreq, ns, ns_pad, soff, S, A)
+
+
 def build_interp_bwd(sfx, dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns, soff, S, dsky,
                      dBI, ldd, dIs):
     live, c = _live(cut, ns)
@@ -305,7 +311,7 @@ def apply_cal_bwd_gains(sfx, vis, gains, gout, g1, g2, p1, b1, p2, b2, npol, ful
 
 _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
               fringe_sum_bwd_sky=fringe_sum_bwd_sky, fringe_sum_bwd_bl=fringe_sum_bwd_bl,
-              pack=pack, unpack=unpack, build_interp=build_interp,
+              pack=pack, unpack=unpack, build_interp=build_interp, build_interp_t=build_interp_t,
               build_interp_bwd=build_interp_bwd, interp_transpose=interp_transpose,
               gather_times=gather_times,
               build_airy=build_airy, build_airy_bwd=build_airy_bwd,

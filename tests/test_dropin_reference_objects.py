@@ -89,5 +89,5 @@ def test_reference_objects_through_b200_rime(kind):
     assert vd.bls == vd_ref.bls and np.allclose(vd.times, vd_ref.times) and vd.pol == vd_ref.pol
     for p, g0 in zip((sky.params, beam.params, array.antvecs), gref):
         assert float((p.grad - g0).abs().max() / g0.abs().max()) < 1e-9
-    expected = {"airy": "build_airy", "interp": "build_interp", "gauss": "pack"}[kind]
+    expected = {"airy": "build_airy", "interp": "build_interp_t", "gauss": "pack"}[kind]
     assert expected in calls and "fringe_sum_fwd" in calls

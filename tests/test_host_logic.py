@@ -60,9 +60,9 @@ def test_golden_cases_through_host_logic(name):
     if name == "rime_point_airy":
         assert "build_airy" in calls and "pack" not in calls
     if name == "rime_pixel_interp":
-        assert "build_interp" in calls and "interp_transpose" in calls and "pack" not in calls
+        assert "build_interp_t" in calls and "interp_transpose" in calls and "pack" not in calls
     if name == "rime_4pol":            # Jones / coherency planes built by the CUDA interpolator
-        assert "build_interp" in calls and "gather_times" in calls and "pack" not in calls
+        assert "build_interp_t" in calls and "build_interp" in calls and "gather_times" in calls and "pack" not in calls
     if name == "rime_multimodel":      # Airy voltage beams: torch response + pack
         assert "pack" in calls and "unpack" in calls
 
