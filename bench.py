@@ -433,7 +433,8 @@ def main():
         gbs = bytes_step * args.steps / (k[bname]["ms"] * 1e-3) / 1e9
         hbm = dict(bound="hbm", kernel=bname + "_f32", achieved=gbs, peak=peaks["hbm_gbs"],
                    unit="GB/s", frac=gbs / peaks["hbm_gbs"], peak_source=peaks["source"],
-                   traffic=traffic.get(bname))
+                   traffic=traffic.get(bname),
+                   traffic_unit="DRAM bytes of a 1-time launch (ncu, profiles/r01_traffic.json)")
 
     line = dict(
         metric="rime_evals_per_sec_fwd_bwd", value=evals_total / (ms_step * 1e-3), unit=unit,
