@@ -426,6 +426,20 @@ def _blv4(blvecs, device):
     return b
 
 
+def _time_batches(ubeg, nt, bytes_per_unit):
+    """Sub-batches (t0, t1) of whole times whose unit partials fit the workspace budget, and the
+    largest number of units in one of them."""
+    max_units = min(max(1, VPART_BUDGET // bytes_per_unit), MAX_GRID_UNITS)
+    t0, batches = 0, []
+    while t0 < nt:
+        t1 = t0 + 1
+        while t1 < nt and ubeg[t1 + 1] - ubeg[t0] <= max_units:
+            t1 += 1
+        batches.append((t0, t1))
+        t0 = t1
+    return batches, max(ubeg[b] - ubeg[a] for a, b in batches)
+
+
 class _FringeSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, blvecs, geom, freqs64, nfreq, conj, uniform):
@@ -442,18 +456,7 @@ class _FringeSum(torch.autograd.Function):
         if nbl > 0 and nt > 0 and geom.S > 0:
             units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
             esize = 8 if sfx == "f32" else 16
-            per_unit = nbl * nfp * esize
-            max_units = min(max(1, VPART_BUDGET // per_unit), MAX_GRID_UNITS)
-            # sub-batches of whole times whose unit partials fit the workspace budget
-            t0 = 0
-            batches = []
-            while t0 < nt:
-                t1 = t0 + 1
-                while t1 < nt and ubeg[t1 + 1] - ubeg[t0] <= max_units:
-                    t1 += 1
-                batches.append((t0, t1))
-                t0 = t1
-            nu_max = max(ubeg[b] - ubeg[a] for a, b in batches)
+            batches, nu_max = _time_batches(ubeg, nt, nbl * nfp * esize)
             vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=dtype, device=dev)
             Vr = torch.view_as_real(V)
             for (ta, tb) in batches:
@@ -649,17 +652,7 @@ class _AntFringeSum(torch.autograd.Function):
         V = torch.zeros(nplane, nbl, nt, nfreq, dtype=torch.complex64, device=dev)
         if nbl > 0 and nt > 0 and geom.S > 0:
             units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
-            per_unit = nbl * nfp * 8
-            max_units = min(max(1, VPART_BUDGET // per_unit), MAX_GRID_UNITS)
-            t0 = 0
-            batches = []
-            while t0 < nt:
-                t1 = t0 + 1
-                while t1 < nt and ubeg[t1 + 1] - ubeg[t0] <= max_units:
-                    t1 += 1
-                batches.append((t0, t1))
-                t0 = t1
-            nu_max = max(ubeg[b] - ubeg[a] for a, b in batches)
+            batches, nu_max = _time_batches(ubeg, nt, nbl * nfp * 8)
             # pairs outside the tiling keep their zero: every wanted pair has exactly one owner
             vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=torch.float32, device=dev)
             Vr = torch.view_as_real(V)
