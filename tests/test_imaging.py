@@ -142,6 +142,31 @@ def test_mapper_host_logic_with_emulated_kernels(dtype, monkeypatch):
         assert "antfringe_bwd" in calls and "fringe_sum_bwd_sky" not in calls
 
 
+def test_mapper_selections_match_oracle_on_the_subset():
+    """set_freq_inds / set_time_inds / set_bl_inds (imaging.py:100-226): mapping a subset equals
+    the oracle run on the subset."""
+    from tests.cpu_double import emulated_kernels
+    g = load()
+    freqs, blvecs, zenaz, beam_fn = _oracle_inputs(g)
+    fsel, tsel, bsel = [1, 2, 4], [0, 2], list(range(0, len(g["bls"]), 2))
+    with emulated_kernels():
+        vm = build_mapper(g, 'cpu', torch.float64)
+        vm.set_freq_inds(fsel)
+        vm.set_time_inds(times=g["times"][tsel])
+        vm.set_bl_inds(bls=[tuple(int(x) for x in g["bls"][i]) for i in bsel])
+        assert (vm.Nfreqs, vm.Ntimes, vm.Nbls) == (3, 2, len(bsel))
+        vm.set_normalization('Aw')
+        maps, P = vm.make_map()
+    p = torch.as_tensor(g["beam_params"])
+    fs = freqs[fsel]
+    beam_sub = lambda z, a: orc.airy_response(p, z, a, fs, powerbeam=True)[0, 0, 0]
+    v = torch.as_tensor(g["vis"])[0, 0][bsel][:, tsel][:, :, fsel]
+    w = torch.as_tensor(g["icov"])[0, 0][bsel][:, tsel][:, :, fsel]
+    mo, Po, Do = orc.vismapper_make_map(v, w, blvecs[bsel], [zenaz[t] for t in tsel], fs,
+                                        len(g["ra"]), beam_sub, fov=float(g["fov"]), method='Aw')
+    assert relmax(maps, mo) < 1e-11 and relmax(P, Po) < 1e-11 and relmax(vm.D, Do) < 1e-11
+
+
 def test_mapper_needs_cuda():
     g = load()
     vm = build_mapper(g, 'cpu', torch.float64)
