@@ -55,6 +55,7 @@ for _name, _sig in _SIGS.items():
 _ANT_SIGS = {
     "antfringe_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P],
     "antfringe_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _I, _P, _P, _P],
+    "tcfringe_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _I, _P, _P],
 }
 for _name, _sig in _ANT_SIGS.items():        # float32 only
     _fn = getattr(lib, "b200rime_%s_f32" % _name)
@@ -83,6 +84,8 @@ SRC_TILE = lib.b200rime_src_tile()
 KC = {"f32": lib.b200rime_kc(0), "f64": lib.b200rime_kc(1)}
 ANT_TILE = lib.b200rime_ant_tile()      # antennas per tile side of the antenna-factorised kernels
 ANT_STAGE = lib.b200rime_ant_stage()    # reduction indices per shared-memory stage
+TC_ROWS = lib.b200rime_tc_rows()        # first antennas per item of the tensor-core kernels
+TC_COLS_MAX = lib.b200rime_tc_cols_max()  # second antennas per item, at most
 
 
 def device_info(device=0):

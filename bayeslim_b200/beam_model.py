@@ -101,11 +101,7 @@ class PixelBeam(utils.Module):
             zen._arr_hash = zen_hash
         p = self.total_params()
         new_zen, new_az = zen, az
-        if self.theta_x > 0 or self.theta_y > 0:
-            nz, na = pointing_offset(utils.tensor2numpy(zen) * D2R, utils.tensor2numpy(az) * D2R,
-                                     self.theta_x, self.theta_y)
-            new_zen = torch.as_tensor(nz) / D2R
-            new_az = torch.as_tensor(na) / D2R
+        new_zen, new_az = offset_zen_az(self, zen, az)
         beam = self.R(p, new_zen, new_az, self.freqs)
         if getattr(self, '_hook_registry', None) is not None:
             bc = getattr(self.R, 'beam_cache', None)
@@ -410,17 +406,48 @@ def airy_disk(zen, az, Dew, freqs, Dns=None, freq_ratio=1.0, square=True, Ntau=1
     return beam ** 2 if square else beam
 
 
-def pointing_offset(zen, az, theta_x, theta_y):
-    """Small-angle rotation of (zen, az) [rad] about the x and y axes (beam_model.py:1631-1678)."""
-    x = np.sin(zen) * np.sin(az)
-    y = np.sin(zen) * np.cos(az)
-    z = np.cos(zen)
-    Rx = np.array([[1, 0, 0], [0, np.cos(theta_x), -np.sin(theta_x)],
-                   [0, np.sin(theta_x), np.cos(theta_x)]])
-    Ry = np.array([[np.cos(theta_y), 0, np.sin(theta_y)], [0, 1, 0],
-                   [-np.sin(theta_y), 0, np.cos(theta_y)]])
-    v = Ry @ Rx @ np.stack([x, y, z])
-    return np.arccos(np.clip(v[2], -1, 1)), np.mod(np.arctan2(v[0], v[1]), 2 * np.pi)
+def pointing_offset(theta, phi, theta_x=0, theta_y=0):
+    """Small-angle pointing offset of (zenith, azimuth) [rad], reference conventions
+    (beam_model.py:1631-1678): the direction is put on the unit sphere as
+    (sin t cos p, sin t sin p, cos t), rotated about x-hat by theta_x, then about y-hat by
+    theta_y (each only when > 0, `rotation` beam_model.py:1514-1545), and converted back with
+    the reference's quadrant rules (new_phi in [0, 2 pi))."""
+    theta = np.asarray(theta, dtype=np.float64)
+    phi = np.asarray(phi, dtype=np.float64)
+    r = np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)])
+    if theta_x > 0:
+        c, s = np.cos(theta_x), np.sin(theta_x)
+        r = np.array([[1.0, 0, 0], [0, c, -s], [0, s, c]]) @ r
+    if theta_y > 0:
+        c, s = np.cos(theta_y), np.sin(theta_y)
+        r = np.array([[c, 0, s], [0, 1.0, 0], [-s, 0, c]]) @ r
+    new_theta = np.arccos(r[2])
+    xzero, yzero = np.isclose(r[0], 0), np.isclose(r[1], 0)
+    xneg, ypos = r[0] < 0, r[1] > 0
+    new_phi = np.zeros_like(new_theta)
+    new_phi[~xzero] = np.arctan(r[1][~xzero] / r[0][~xzero])
+    new_phi[xneg & ypos] += np.pi
+    new_phi[xneg & ~ypos] -= np.pi
+    new_phi[xzero & yzero] = 0.0
+    new_phi[xzero & ypos] = np.pi / 2
+    new_phi[xzero & ~ypos] = -np.pi / 2
+    return new_theta, new_phi % (2 * np.pi)
+
+
+def offset_zen_az(beam, zen, az):
+    """(zen, az) [deg] at which the response of `beam` is evaluated: the pointing-offset branch
+    of PixelBeam.gen_beam (beam_model.py:244-256).  Works on reference beam objects as well."""
+    theta_x, theta_y = getattr(beam, 'theta_x', 0), getattr(beam, 'theta_y', 0)
+    if not (theta_x > 0 or theta_y > 0):
+        return zen, az
+    nz, na = pointing_offset(utils.tensor2numpy(zen) * D2R, utils.tensor2numpy(az) * D2R,
+                             theta_x, theta_y)
+    if isinstance(zen, torch.Tensor):
+        nz = (torch.as_tensor(nz) / D2R).to(zen.device)
+        na = (torch.as_tensor(na) / D2R).to(zen.device)
+    else:
+        nz, na = nz / D2R, na / D2R
+    return nz, na
 
 
 def cut_sky_fov(sky, cut):

@@ -548,11 +548,10 @@ int launch_ant_fwd(const float* A, const double* shat, const double* antv, const
     const long long nitems = (long long)ntile * nfp;
     if (nitems / ANT_SLOTS > 2147483647LL || nunits > 65535)
         return set_error("antfringe_fwd: grid too large");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(ant_fringe_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              AntSmem::TOTAL);
-        attr_set = true;
     }
     dim3 grid((unsigned)((nitems + ANT_SLOTS - 1) / ANT_SLOTS), nunits);
     ant_fringe_fwd_kernel<<<grid, ANT_THREADS, AntSmem::TOTAL, st>>>(
@@ -575,11 +574,10 @@ int launch_ant_bwd(const float* Hp, const float* A, const double* shat, const do
     const long long nitems = (long long)(na_pad / ANT_TILE) * nfp;
     if ((nitems + ANT_SLOTS - 1) / ANT_SLOTS > 65535)
         return set_error("antfringe_bwd: grid too large");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(ant_fringe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              AntSmem::TOTAL);
-        attr_set = true;
     }
     // units fastest: CTAs that run together share their (antenna block, channel) items, so a
     // cotangent tile is fetched from HBM once and then served to the other units from L2

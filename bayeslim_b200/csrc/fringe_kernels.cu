@@ -493,13 +493,12 @@ int launch_fwd(const T* A, const double* shat, const double* blv, const double* 
     dim3 grid((nbl + nthr - 1) / nthr, nchunk, nunits);
     const double sgn_over_c = (conj ? -1.0 : 1.0) / C_LIGHT;
     const int smem = FwdSmem<T>::TOTAL;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(fringe_sum_fwd_kernel<T, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fringe_sum_fwd_kernel<T, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
     }
     if (uniform)
         fringe_sum_fwd_kernel<T, true><<<grid, nthr, smem, st>>>(
@@ -538,13 +537,12 @@ int launch_bwd_sky(const T* Gp, const double* shat, const double* blv, const dou
     dim3 grid((unsigned)(S / SKY_THREADS), nchunk);
     const double sgn_over_c = (conj ? -1.0 : 1.0) / C_LIGHT;
     const int smem = SkySmem<T>::TOTAL;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(fringe_sum_bwd_sky_kernel<T, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fringe_sum_bwd_sky_kernel<T, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
     }
     if (uniform)
         fringe_sum_bwd_sky_kernel<T, true><<<grid, SKY_THREADS, smem, st>>>(
@@ -568,13 +566,12 @@ int launch_bwd_bl(const T* Gp, const T* A, const double* shat, const double* blv
     dim3 grid((nbl + nthr - 1) / nthr, nchunk, nunits);
     const double sgn_over_c = (conj ? -1.0 : 1.0) / C_LIGHT;
     const int smem = FwdSmem<T>::TOTAL;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(fringe_sum_bwd_bl_kernel<T, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(fringe_sum_bwd_bl_kernel<T, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
     }
     if (uniform)
         fringe_sum_bwd_bl_kernel<T, true><<<grid, nthr, smem, st>>>(

@@ -51,8 +51,8 @@ def _cplx(dtype):
     return torch.complex64 if _sfx(dtype) == "f32" else torch.complex128
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _need_cuda(*tensors):
@@ -80,9 +80,20 @@ def _call(name, sfx, *args):
     (None -> NULL); the trailing stream argument is appended here."""
     global _launches
     _launches += 1
+    dev = None
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise RuntimeError("b200rime_%s: tensors live on different devices (%s, %s)"
+                                   % (name, dev, a.device))
     conv = [ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor)
             else (ctypes.c_void_p(0) if a is None else a) for a in args]
-    _lib.call(name, sfx, *conv, _stream())
+    # launch on the device that owns the tensors and on torch's current stream OF THAT DEVICE
+    # (not on whatever device happens to be current in the process)
+    with torch.cuda.device(dev):
+        _lib.call(name, sfx, *conv, _stream(dev))
 
 
 def freqs_uniform(freqs, blmax, dtype):
@@ -636,9 +647,63 @@ class AntTiling:
         return torch.view_as_real(H)
 
 
+TC_MIN_FILL = 0.12        # wanted pairs / computed pairs below which the tensor-core items lose
+
+
+class TcTiling:
+    """Items of the tensor-core fringe-sum kernel for a baseline list: blocks of 128 first
+    antennas against ranges of at most 256 second antennas, and the antenna-pair -> baseline
+    table (include/b200rime.h, tcfringe_fwd).  Pairs are folded onto i <= j (a baseline listed
+    as (j, i) is computed as (i, j) and conjugated on output)."""
+
+    def __init__(self, i_idx, j_idx, na, device):
+        M, NMAX = _lib.TC_ROWS, _lib.TC_COLS_MAX
+        i = np.asarray(i_idx, dtype=np.int64)
+        j = np.asarray(j_idx, dtype=np.int64)
+        nbl = len(i)
+        self.nbl, self.na = nbl, int(na)
+        self.ldp = max(32, -(-self.na // 32) * 32)
+        swap = i > j
+        x = np.where(swap, j, i)
+        y = np.where(swap, i, j)
+        flat = x * self.ldp + y
+        self.unique = len(np.unique(flat)) == nbl
+        pair = -np.ones(self.ldp * self.ldp, dtype=np.int32)
+        pair[flat] = (np.arange(nbl) << 1) | swap
+        items, slots = [], 0
+        for ib in range(-(-self.na // M)):
+            sel = (x // M) == ib
+            if not sel.any():
+                continue
+            lo = int(y[sel].min() // 32) * 32
+            hi = int(-(-(y[sel].max() + 1) // 32)) * 32
+            npiece = -(-(hi - lo) // NMAX)
+            per = -(-(hi - lo) // (npiece * 32)) * 32
+            j0 = lo
+            while j0 < hi:
+                n = min(per, hi - j0)
+                items.append((ib * M, j0, n, 0))
+                slots += M * n
+                j0 += n
+        self.nitems = len(items)
+        self.pair_slots = float(slots)
+        self.fill = nbl / max(self.pair_slots, 1.0)
+        self.usable = self.unique and nbl > 0 and self.fill >= TC_MIN_FILL
+        dev = torch.device(device)
+        self.items = torch.as_tensor(np.asarray(items, dtype=np.int32).reshape(-1, 4), device=dev)
+        self.pair_bl = torch.as_tensor(pair.reshape(self.ldp, self.ldp), device=dev)
+
+
+def tc_scale(A):
+    """Per-plane power of two that brings max|A| into [2^14, 2^15): the float16 range of the
+    tensor-core operands A E (device tensor, no host synchronisation)."""
+    amax = A.detach().abs().reshape(A.shape[0], -1).amax(dim=1).clamp_min(1e-30)
+    return torch.exp2(14.0 - torch.floor(torch.log2(amax))).to(torch.float32).contiguous()
+
+
 class _AntFringeSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, A, antvecs, geom, freqs64, nfreq, conj, tiling):
+    def forward(ctx, A, antvecs, geom, freqs64, nfreq, conj, tiling, tc=None):
         _need_cuda(A, freqs64)
         if A.dtype != torch.float32:
             raise TypeError("fringe_sum_ant is float32 only")
@@ -656,13 +721,19 @@ class _AntFringeSum(torch.autograd.Function):
             # pairs outside the tiling keep their zero: every wanted pair has exactly one owner
             vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=torch.float32, device=dev)
             Vr = torch.view_as_real(V)
+            ascale = tc_scale(A) if tc is not None else None
             for (ta, tb) in batches:
                 u0, u1 = ubeg[ta], ubeg[tb]
                 ub = torch.as_tensor(np.asarray(ubeg[ta:tb + 1], dtype=np.int32) - u0, device=dev)
                 for p in range(nplane):
-                    _call("antfringe_fwd", "f32", A[p], geom.shat, antv, freqs64, units[u0:],
-                          u1 - u0, tiling.tile_ant, tiling.tile_bl, tiling.tile_order,
-                          tiling.ntile, nbl, nfreq, geom.S, int(conj), vpart)
+                    if tc is not None:
+                        _call("tcfringe_fwd", "f32", A[p], ascale[p:p + 1], geom.shat, antv,
+                              freqs64, units[u0:], u1 - u0, tc.items, tc.nitems, tc.pair_bl,
+                              tc.ldp, tc.na, nbl, nfreq, geom.S, int(conj), vpart)
+                    else:
+                        _call("antfringe_fwd", "f32", A[p], geom.shat, antv, freqs64, units[u0:],
+                              u1 - u0, tiling.tile_ant, tiling.tile_bl, tiling.tile_order,
+                              tiling.ntile, nbl, nfreq, geom.S, int(conj), vpart)
                     _call("reduce_units", "f32", vpart, ub, tb - ta, nbl, nfreq,
                           Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, 0)
         ctx.save_for_backward(A, antv, freqs64)
@@ -681,7 +752,7 @@ class _AntFringeSum(torch.autograd.Function):
             gant = torch.zeros(ashape_ant, dtype=torch.float64, device=G.device)
             gant[:tiling.na] = dr[:tiling.na]
             gant = gant.to(device=adev, dtype=adtype)
-        return dA, gant, None, None, None, None, None
+        return dA, gant, None, None, None, None, None, None
 
 
 def _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, ashape, need_A, need_r):
@@ -722,11 +793,12 @@ def _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, ashape, need_A
     return dA, dr
 
 
-def fringe_sum_ant(A, antvecs, tiling, geom, freqs64, nfreq, conj=False):
+def fringe_sum_ant(A, antvecs, tiling, geom, freqs64, nfreq, conj=False, tc=None):
     """Same sum as fringe_sum for the baselines (tiling.i, tiling.j) of antenna positions
     antvecs (Na, 3), through the antenna-factorised float32 kernels; gradients flow to A and
-    straight to antvecs."""
-    return _AntFringeSum.apply(A, antvecs, geom, freqs64, nfreq, conj, tiling)
+    straight to antvecs.  tc (TcTiling of the same baseline list): the forward sum runs on the
+    tensor cores (tcgen05) instead of the FP32 pipes."""
+    return _AntFringeSum.apply(A, antvecs, geom, freqs64, nfreq, conj, tiling, tc)
 
 
 def fringe_adjoint(G, geom, freqs64, nfreq, blvecs=None, antvecs=None, tiling=None, conj=False,

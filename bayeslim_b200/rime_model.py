@@ -321,11 +321,12 @@ class RIME(utils.Module):
         b, R = self.beam, self.beam.R
         if not (b.powerbeam and b.Nvec == 1 and b.Nmodel == 1 and sky.shape[:2] == (1, 1)):
             return None
-        if sky.is_complex() or getattr(b, 'theta_x', 0) > 0 or getattr(b, 'theta_y', 0) > 0:
+        if sky.is_complex():
             return None
+        offset = getattr(b, 'theta_x', 0) > 0 or getattr(b, 'theta_y', 0) > 0
         rname = R.__class__.__name__
         if rname == 'AiryResponse' and not getattr(R, 'brute_force', False) \
-                and getattr(R, 'taper_kwargs', None) is None:
+                and getattr(R, 'taper_kwargs', None) is None and not offset:
             return 'airy'
         if rname == 'PixelResponse' and getattr(R, 'Rchi', None) is None:
             return 'interp'
@@ -336,8 +337,7 @@ class RIME(utils.Module):
         mode: Jones and coherency planes are then built by the CUDA interpolation / gather
         kernels directly in the tiled layout and combined element-wise."""
         b, R = self.beam, self.beam.R
-        return (R.__class__.__name__ == 'PixelResponse' and getattr(R, 'Rchi', None) is None
-                and not (getattr(b, 'theta_x', 0) > 0 or getattr(b, 'theta_y', 0) > 0))
+        return R.__class__.__name__ == 'PixelResponse' and getattr(R, 'Rchi', None) is None
 
     def _build_airy(self, sky, rec, dev):
         b, R = self.beam, self.beam.R
@@ -357,6 +357,7 @@ class RIME(utils.Module):
         dtype = sky.dtype
         if R.beam_cache is None:
             R.set_beam_cache(_beam_params(b))
+        self._register_beam_hooks()
         bmap = R.beam_cache.to(dev)
         tab = self._interp_table(sky, rec, bmap, dtype)
         planes = [ops.build_interp(sky[0, 0], bmap[ipol, 0, 0], rec.geom, tab)
@@ -371,18 +372,33 @@ class RIME(utils.Module):
         modelpairs, mp_idx = _beam_model_pairs(b, self.sim_bls)
         per_time = []
         for cut, zen, az in zip(rec.cuts, rec.zen, rec.az):
-            beam = b.R(p, zen, az, b.freqs)
+            # the response is evaluated at the pointing-offset directions, the fringe keeps the
+            # true ones (beam_model.py:244-259)
+            bzen, baz = beam_model.offset_zen_az(b, zen, az)
+            beam = b.R(p, bzen, baz, b.freqs)
+            self._register_beam_hooks()
             beam = torch.as_tensor(beam).to(dev)
             cut_sky = sky.index_select(-1, cut)
             per_time.append(beam_model.perceived_sky(beam, cut_sky, modelpairs, b.Npol, b.Nvec,
                                                      b.powerbeam))
         return per_time, modelpairs, mp_idx
 
+    def _register_beam_hooks(self):
+        """Gradient hooks of the beam on R.beam_cache (beam_model.py:262-266)."""
+        hooks = getattr(self.beam, '_hook_registry', None)
+        bc = getattr(self.beam.R, 'beam_cache', None)
+        if hooks is not None and bc is not None and bc.requires_grad:
+            for hook in hooks:
+                bc.register_hook(hook)
+
     def _interp_table(self, sky, rec, bmap, dtype):
-        R = self.beam.R
-        key = (id(R), R.interp_mode, dtype)
+        R, b = self.beam.R, self.beam
+        key = (id(R), R.interp_mode, dtype, float(getattr(b, 'theta_x', 0)),
+               float(getattr(b, 'theta_y', 0)))
         if key not in rec.interp:
-            tabs = [R.get_interp(z, a) for z, a in zip(rec.zen, rec.az)]
+            # interpolation weights at the pointing-offset directions (beam_model.py:244-259)
+            tabs = [R.get_interp(*beam_model.offset_zen_az(b, z, a))
+                    for z, a in zip(rec.zen, rec.az)]
             rec.interp[key] = ops.InterpTable(rec.geom, rec.cuts, [t[0] for t in tabs],
                                               [t[1] for t in tabs], sky.shape[-1], bmap.shape[-1],
                                               dtype)
@@ -399,6 +415,7 @@ class RIME(utils.Module):
         rdtype = ops._real(sky.dtype)
         if R.beam_cache is None:
             R.set_beam_cache(_beam_params(b))
+        self._register_beam_hooks()
         bmap = R.beam_cache.to(dev)
         tab = self._interp_table(sky, rec, bmap, rdtype)
 

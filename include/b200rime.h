@@ -266,6 +266,29 @@ int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* sh
                                long long S, int conj, float* dApart, double* drpart,
                                b200rime_stream_t stream);
 
+/* ---- tensor-core fringe sum (tcgen05 / TMEM) ---------------------------------------------
+ * The same antenna-factorised sum as antfringe_fwd (reference telescope_model.py:310-358 +
+ * rime_model.py:426-429) as a batched complex GEMM V = E^H diag(A) E on the 5th-generation
+ * tensor cores: operands generated in shared memory (float64 phases, MUFU sine / cosine), split
+ * into float16 hi + lo pairs (three MMAs per real product, float32-grade results), FP32
+ * accumulators in tensor memory.
+ *   ascale   float [1]   power of two s with max|A| s in [2^14, 2^15) (float16 range of A E)
+ *   antv     f64 [>= na][4]   antenna positions (ENU metres)
+ *   items    int32 [nitems][4]   {i0, j0, N, 0}: first antennas i0 .. i0 + 127 (tc_rows()) against
+ *            second antennas j0 .. j0 + N - 1, N a multiple of 32, <= tc_cols_max() = 256;
+ *            i0 + 128 and j0 + N may exceed na (rows beyond na are skipped)
+ *   pair_bl  int32 [ldp][ldp]    (baseline << 1 | c) of the pair (first i, second j), or -1;
+ *            c = 1: the baseline is (j, i) and the result is conjugated on output; ldp = na
+ *            rounded up to 32.  Every wanted baseline must be covered by exactly one item.
+ *   Vpart    [nunits][nbl][Nfp][2]   (as fringe_sum_fwd; reduce with reduce_units) */
+int b200rime_tc_rows(void);
+int b200rime_tc_cols_max(void);
+int b200rime_tcfringe_fwd_f32(const float* A, const float* ascale, const double* shat,
+                              const double* antv, const double* freqs, const int* units,
+                              int nunits, const int* items, int nitems, const int* pair_bl,
+                              int ldp, int na, int nbl, int nfreq, long long S, int conj,
+                              float* Vpart, b200rime_stream_t stream);
+
 /* ---- gain application --------------------------------------
  * V_out = g_1 V g_2^H per baseline: reference calibration._apply_cal (calibration.py:2412-2487),
  * the step that follows the RIME in a BayesLIM Sequential.
