@@ -17,12 +17,27 @@
 //   * the complex product needs four real ones; the minus sign of Im = Er.Yi - Ei.Yr is the
 //     negate-A bit of the instruction descriptor, so X and Y are stored once.
 //
-// Forward item = (block of 128 first antennas i0.., range of N <= 256 second antennas j0..,
-// channel k, unit of sources).  Warps 0..11 are producers (thread <-> operand row = antenna,
-// 16 sources per stage = one UMMA K step), warp 12 issues the MMAs (one elected lane) and owns
-// the TMEM allocation; full / empty mbarriers per stage, tcgen05.commit releases stages and
-// signals the epilogue, in which the producer warps read the accumulators back with tcgen05.ld
-// and scatter them through the antenna-pair table into Vpart[unit][baseline][channel].
+// Accumulation.  The tensor core adds into its FP32 accumulator with truncation (measured on
+// B200: a chain of n MMAs loses ~0.75 * 2^-24 * n of a coherent sum -- 6e-5 after 8192 sources,
+// profiles/r02_tc_v1_truncation_study.jsonl), so a TMEM chain is kept short (TC_FLUSH stages =
+// 64 sources by default) and then added, with ordinary round-to-nearest FADDs, to float32
+// accumulators held in the registers of eight dedicated warps; two TMEM accumulator sets
+// alternate so that the MMAs of chain c + 1 overlap the read-out of chain c.
+//
+// Forward item = (block of 128 first antennas i0.., range of N <= 128 second antennas j0..,
+// channel k, unit of sources).  The CTA is four whole warpgroups (setmaxnreg moves registers
+// from the producers to the accumulator warps):
+//   warps 0..7   accumulators (128 registers each: TMEM lane quarter x column half); warp 0
+//                also issues the MMAs (one elected lane) -- it issues chain c, then reads out
+//                chain c - 1 while the tensor core works -- and stages the source data (unit
+//                vectors, channel row of the perceived sky) ahead of the producers with 1-D TMA
+//                bulk copies;
+//   warps 8..15  producers: thread <-> one X row and one Y row, 8 of the 16 sources of a stage
+//                (= one UMMA K step); a diagonal item computes each antenna term once for both
+//                roles.
+// full / empty mbarriers per operand stage, sfull per source slot, tfull / tempty per TMEM set;
+// tcgen05.commit releases stages and hands chains to the accumulator warps, which finally
+// scatter their registers through the antenna-pair table into Vpart[unit][baseline][channel].
 //
 // Replaces telescope_model.py:310-358 (gen_fringe) + rime_model.py:426-429 (multiply, sum).
 #include <cuda_fp16.h>
@@ -31,28 +46,45 @@
 
 namespace b200rime {
 
+#ifndef B200_TC_FLUSH
+#define B200_TC_FLUSH 4            // stages (of 16 sources) per TMEM accumulation chain
+#endif
 constexpr int TC_M = 128;            // X rows (first antennas) per item = UMMA M
-constexpr int TC_NMAX = 256;         // Y rows (second antennas) per item <= UMMA N max
+constexpr int TC_NMAX = 128;         // Y rows (second antennas) per item = UMMA N, at most
 constexpr int TC_KS = 16;            // sources per stage = one kind::f16 UMMA K step
-constexpr int TC_NSTAGE = 4;
-constexpr int TC_PROD_WARPS = (TC_M + TC_NMAX) / 32;         // 12
-constexpr int TC_THREADS = (TC_PROD_WARPS + 1) * 32;         // + the MMA warp
+constexpr int TC_NSTAGE = 6;         // operand stages
+constexpr int TC_NSRC = 8;           // source-data slots (staged TC_NSRC stages ahead)
+constexpr int TC_FLUSH = B200_TC_FLUSH;
+constexpr int TC_ACC_WARPS = 8;      // warps 0..7: TMEM -> register accumulators; warp 0 issues
+constexpr int TC_PROD_WARPS = 8;     // warps 8..15: operand generation
+constexpr int TC_THREADS = (TC_ACC_WARPS + TC_PROD_WARPS) * 32;   // 512 = four whole warpgroups
+// registers after setmaxnreg: 256 * 168 + 256 * 88 = 512 * 128 = the CTA's pool (the launcher
+// checks the kernel's register count: asking for more than the pool makes setmaxnreg.inc spin)
+#ifndef B200_TC_ACCREGS
+#define B200_TC_ACCREGS 168
+#endif
+#ifndef B200_TC_PV
+#define B200_TC_PV 1               // producer code variant (0: one pass over X and Y, 1: X pass then Y pass)
+#endif
+constexpr int TC_ACC_REGS = B200_TC_ACCREGS, TC_PROD_REGS = 256 - B200_TC_ACCREGS, TC_LAUNCH_REGS = 128;
 constexpr int TC_KC = B200_KC_F32;
-constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_IM_COL = 256;       // column offset of the imaginary accumulator
+constexpr int TC_TMEM_COLS = 512;    // two accumulator sets of (re, im) x 128 columns
+constexpr int TC_SET_COLS = 256, TC_IM_COL = 128;
 
 struct TcSmem {
-    // one operand array = rows x 16 float16 in the canonical no-swizzle K-major layout:
+    // one operand array = 128 rows x 16 float16 in the canonical no-swizzle K-major layout:
     //   byte offset(row, kgroup of 8) = (row / 8) * 256 + kgroup * 128 + (row % 8) * 16
     // i.e. 8 x 16-byte core matrices, LBO (K direction) = 128 B, SBO (row direction) = 256 B
-    static constexpr int X_ARR = TC_M * TC_KS * 2;            // 4 KB
-    static constexpr int Y_ARR = TC_NMAX * TC_KS * 2;         // 8 KB
-    static constexpr int XR_H = 0, XR_L = X_ARR, XI_H = 2 * X_ARR, XI_L = 3 * X_ARR;
-    static constexpr int YR_H = 4 * X_ARR, YR_L = YR_H + Y_ARR, YI_H = YR_H + 2 * Y_ARR,
-                         YI_L = YR_H + 3 * Y_ARR;
-    static constexpr int STAGE = 4 * X_ARR + 4 * Y_ARR;       // 48 KB
-    static constexpr int BAR_OFF = TC_NSTAGE * STAGE;         // full[NSTAGE], empty[NSTAGE], done
-    static constexpr int TMEM_OFF = BAR_OFF + (2 * TC_NSTAGE + 1) * 8;
+    static constexpr int ARR = TC_M * TC_KS * 2;              // 4 KB
+    static constexpr int XR_H = 0, XR_L = ARR, XI_H = 2 * ARR, XI_L = 3 * ARR;
+    static constexpr int YR_H = 4 * ARR, YR_L = 5 * ARR, YI_H = 6 * ARR, YI_L = 7 * ARR;
+    static constexpr int STAGE = 8 * ARR;                     // 32 KB
+    // source slot: 16 x (x, y, z, 0) float64 unit vectors, then 16 float32 sky values
+    static constexpr int SRC_SHAT = TC_KS * 32, SRC_A = TC_KS * 4, SRC_SLOT = SRC_SHAT + SRC_A;
+    static constexpr int SRC_OFF = TC_NSTAGE * STAGE;
+    // full[NSTAGE], empty[NSTAGE], sfull[NSRC], tfull[2], tempty[2]
+    static constexpr int BAR_OFF = SRC_OFF + TC_NSRC * SRC_SLOT;
+    static constexpr int TMEM_OFF = BAR_OFF + (2 * TC_NSTAGE + TC_NSRC + 4) * 8;
     static constexpr int TOTAL = TMEM_OFF + 16;
 };
 
@@ -95,22 +127,17 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 8 consecutive columns of the warp's 32 TMEM lanes -> 8 registers per thread (issue only)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[7])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // mbarrier wait with a bound: a protocol error traps instead of hanging the GPU
@@ -132,11 +159,11 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     }
 }
 
-// exp(2 pi i frac(u kappa)): the phase fraction is read as a 32-bit fixed-point number from the
-// low mantissa word of fma(u, kappa, 1.5 * 2^20) (ulp 2^-32 cycles, |u kappa| < 2^19), turned
-// into a float in [-2^22, 2^22) with an exponent trick, scaled to radians for MUFU sin / cos.
-__device__ __forceinline__ void antenna_cis(double u, double kappa, float& c, float& s) {
-    const double t = __fma_rn(u, kappa, 1572864.0);
+// exp(2 pi i frac(p)) for t = p + 1.5 * 2^20, p the phase in cycles (|p| < 2^19) summed onto the
+// offset with FMAs: the offset makes the ulp of t 2^-32 cycles, so the low mantissa word of t is
+// the phase fraction as a 32-bit fixed-point number.  It is turned into a float in
+// [-2^22, 2^22) with an exponent trick and scaled to radians for MUFU sine / cosine.
+__device__ __forceinline__ void antenna_cis(double t, float& c, float& s) {
     const uint32_t lo = (uint32_t)__double2loint(t);
     const float fb = __uint_as_float((lo >> 9) ^ 0x4B400000u) - 12582912.0f;
     const float ang = fb * 7.4901405e-07f;          // 2 pi / 2^23
@@ -160,14 +187,89 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 }
 
 // -------------------------------------------------------------------------------------
-// forward.  grid = (nitems * nfreq, nunits), block = 416.
+// forward.  grid = (nitems * nfreq, nunits), block = 512.
+//   Acm      float [Nfp][S]     perceived sky, channel-major (row k = channel k over the packed
+//                                source axis): the 16 values of a stage are one 64-byte bulk copy
 //   items    int32 [nitems][4]  {i0, j0, N, 0}: X rows = antennas i0 .. i0 + 127, Y rows =
-//                                antennas j0 .. j0 + N - 1 (N a multiple of 32, <= 256)
+//                                antennas j0 .. j0 + N - 1 (N a multiple of 32, <= 128)
 //   pair_bl  int32 [ldp][ldp]   (baseline << 1 | conj) of V_ij = sum conj(E_i) A E_j, or -1
 //   ascale   float [1]          power of two that brings max |A| into [2^14, 2^15)
 // -------------------------------------------------------------------------------------
+// one producer thread, one stage: antenna terms of operand row `row` (X role: position xp, Y role:
+// position yp times the sky values a) for the 8 sources sh[0..8)
+template <bool DIAG>
+__device__ __forceinline__ void tc_produce_rows(unsigned char* row, const double4* sh,
+                                                const float (&a)[8], const double (&xp)[3],
+                                                const double (&yp)[3], bool xlive, bool ylive) {
+    float c[8], s[8];
+    uint4 hi, lo;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const double4 sv = sh[e];
+        antenna_cis(__fma_rn(xp[0], sv.x, __fma_rn(xp[1], sv.y, __fma_rn(xp[2], sv.z, 1572864.0))),
+                    c[e], s[e]);
+    }
+    if (xlive) {
+        split8(c, hi, lo);
+        *reinterpret_cast<uint4*>(row + TcSmem::XR_H) = hi;
+        *reinterpret_cast<uint4*>(row + TcSmem::XR_L) = lo;
+        split8(s, hi, lo);
+        *reinterpret_cast<uint4*>(row + TcSmem::XI_H) = hi;
+        *reinterpret_cast<uint4*>(row + TcSmem::XI_L) = lo;
+    }
+    if (!DIAG) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const double4 sv = sh[e];
+            antenna_cis(__fma_rn(yp[0], sv.x, __fma_rn(yp[1], sv.y, __fma_rn(yp[2], sv.z, 1572864.0))),
+                        c[e], s[e]);
+        }
+    }
+    if (ylive) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            c[e] *= a[e];
+            s[e] *= a[e];
+        }
+        split8(c, hi, lo);
+        *reinterpret_cast<uint4*>(row + TcSmem::YR_H) = hi;
+        *reinterpret_cast<uint4*>(row + TcSmem::YR_L) = lo;
+        split8(s, hi, lo);
+        *reinterpret_cast<uint4*>(row + TcSmem::YI_H) = hi;
+        *reinterpret_cast<uint4*>(row + TcSmem::YI_L) = lo;
+    }
+}
+
+struct TcIssue {                 // state of the issuing lane
+    uint32_t tmem, id_pos, id_neg, smem_base;
+};
+
+__device__ __forceinline__ void tc_issue_stage(const TcIssue& q, int stage, int set, bool first) {
+    const uint32_t d_re = q.tmem + set * TC_SET_COLS, d_im = d_re + TC_IM_COL;
+    const uint32_t b = q.smem_base + stage * TcSmem::STAGE;
+    const uint64_t xrh = umma_desc_kmajor(b + TcSmem::XR_H), xrl = umma_desc_kmajor(b + TcSmem::XR_L),
+                   xih = umma_desc_kmajor(b + TcSmem::XI_H), xil = umma_desc_kmajor(b + TcSmem::XI_L),
+                   yrh = umma_desc_kmajor(b + TcSmem::YR_H), yrl = umma_desc_kmajor(b + TcSmem::YR_L),
+                   yih = umma_desc_kmajor(b + TcSmem::YI_H), yil = umma_desc_kmajor(b + TcSmem::YI_L);
+    const uint32_t acc = first ? 0u : 1u;
+    // Re V = Er.Yr + Ei.Yi
+    umma_f16(d_re, xrh, yrh, q.id_pos, acc);
+    umma_f16(d_re, xrh, yrl, q.id_pos, 1u);
+    umma_f16(d_re, xrl, yrh, q.id_pos, 1u);
+    umma_f16(d_re, xih, yih, q.id_pos, 1u);
+    umma_f16(d_re, xih, yil, q.id_pos, 1u);
+    umma_f16(d_re, xil, yih, q.id_pos, 1u);
+    // Im V = Er.Yi - Ei.Yr
+    umma_f16(d_im, xrh, yih, q.id_pos, acc);
+    umma_f16(d_im, xrh, yil, q.id_pos, 1u);
+    umma_f16(d_im, xrl, yih, q.id_pos, 1u);
+    umma_f16(d_im, xih, yrh, q.id_neg, 1u);
+    umma_f16(d_im, xih, yrl, q.id_neg, 1u);
+    umma_f16(d_im, xil, yrh, q.id_neg, 1u);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_fringe_fwd_kernel(const float* __restrict__ A, const float* __restrict__ ascale,
+tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ ascale,
                      const double* __restrict__ shat, const double* __restrict__ antv,
                      const double* __restrict__ freqs, const int4* __restrict__ units,
                      const int4* __restrict__ items, const int* __restrict__ pair_bl, int ldp,
@@ -181,22 +283,24 @@ tc_fringe_fwd_kernel(const float* __restrict__ A, const float* __restrict__ asca
     const int4 un = units[blockIdx.y];
     const int nst = (un.z - un.y) / TC_KS;
     if (nst <= 0) return;
+    const int nchain = (nst + TC_FLUSH - 1) / TC_FLUSH;
 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TcSmem::BAR_OFF);
     uint64_t* empty = full + TC_NSTAGE;
-    uint64_t* done = empty + TC_NSTAGE;
+    uint64_t* sfull = empty + TC_NSTAGE;
+    uint64_t* tfull = sfull + TC_NSRC;
+    uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcSmem::TMEM_OFF);
 
-    // producer warps with at least one real antenna row take part in the pipeline
+    // producer warp w (0..7) owns operand rows 32 (w & 3) .. + 31 and sources 8 (w >> 2) .. + 7 of
+    // every stage; it takes part when one of its rows is a real antenna in either role
+    const int nx = min(TC_M, na - i0), ny = min(N, na - j0);      // live X / Y rows
     int nactive = 0;
 #pragma unroll
-    for (int w = 0; w < TC_PROD_WARPS; ++w) {
-        const int r0 = 32 * w;
-        const bool act = (r0 < TC_M) ? (i0 + r0 < na) : (r0 - TC_M < N && j0 + r0 - TC_M < na);
-        nactive += act ? 1 : 0;
-    }
+    for (int w = 0; w < TC_PROD_WARPS; ++w) nactive += (32 * (w & 3) < max(nx, ny)) ? 1 : 0;
+
     // rows nobody writes must still hold finite numbers (their products land in rows / columns
-    // of the accumulator that the epilogue skips)
+    // of the accumulator that are never stored)
     for (int o = tid * 16; o < TC_NSTAGE * TcSmem::STAGE; o += TC_THREADS * 16)
         *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
@@ -204,10 +308,14 @@ tc_fringe_fwd_kernel(const float* __restrict__ A, const float* __restrict__ asca
             mbar_init(&full[st], nactive);
             mbar_init(&empty[st], 1);
         }
-        mbar_init(done, 1);
+        for (int st = 0; st < TC_NSRC; ++st) mbar_init(&sfull[st], 1);
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(&tfull[q], 1);
+            mbar_init(&tempty[q], TC_ACC_WARPS);
+        }
         mbar_fence_init();
     }
-    if (warp == TC_PROD_WARPS) {
+    if (warp == TC_ACC_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
                      "r"(TC_TMEM_COLS)
@@ -219,140 +327,498 @@ tc_fringe_fwd_kernel(const float* __restrict__ A, const float* __restrict__ asca
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const float* Ak = Acm + (size_t)k * (size_t)S;
 
-    if (warp == TC_PROD_WARPS) {
-        // ---------------- MMA issuer
-        if (lane == 0) {
-            const uint32_t id_pos = umma_idesc_f16(N, false), id_neg = umma_idesc_f16(N, true);
-            const uint32_t d_re = tmem, d_im = tmem + TC_IM_COL;
-            for (int it = 0; it < nst; ++it) {
-                const int stage = it % TC_NSTAGE;
-                mbar_wait_bounded(&full[stage], (uint32_t)((it / TC_NSTAGE) & 1));
-                tc_fence_after();
-                const uint32_t b = smem_u32(smem + stage * TcSmem::STAGE);
-                const uint64_t xrh = umma_desc_kmajor(b + TcSmem::XR_H),
-                               xrl = umma_desc_kmajor(b + TcSmem::XR_L),
-                               xih = umma_desc_kmajor(b + TcSmem::XI_H),
-                               xil = umma_desc_kmajor(b + TcSmem::XI_L),
-                               yrh = umma_desc_kmajor(b + TcSmem::YR_H),
-                               yrl = umma_desc_kmajor(b + TcSmem::YR_L),
-                               yih = umma_desc_kmajor(b + TcSmem::YI_H),
-                               yil = umma_desc_kmajor(b + TcSmem::YI_L);
-                const uint32_t acc = it > 0 ? 1u : 0u;
-                // Re V = Er.Yr + Ei.Yi
-                umma_f16(d_re, xrh, yrh, id_pos, acc);
-                umma_f16(d_re, xrh, yrl, id_pos, 1u);
-                umma_f16(d_re, xrl, yrh, id_pos, 1u);
-                umma_f16(d_re, xih, yih, id_pos, 1u);
-                umma_f16(d_re, xih, yil, id_pos, 1u);
-                umma_f16(d_re, xil, yih, id_pos, 1u);
-                // Im V = Er.Yi - Ei.Yr
-                umma_f16(d_im, xrh, yih, id_pos, acc);
-                umma_f16(d_im, xrh, yil, id_pos, 1u);
-                umma_f16(d_im, xrl, yih, id_pos, 1u);
-                umma_f16(d_im, xih, yrh, id_neg, 1u);
-                umma_f16(d_im, xih, yrl, id_neg, 1u);
-                umma_f16(d_im, xil, yrh, id_neg, 1u);
-                umma_commit(&empty[stage]);       // stage free once these MMAs have read it
-            }
-            umma_commit(done);
-        }
-        __syncwarp();
-    } else {
-        // ---------------- producers: thread <-> operand row
-        const bool isY = tid >= TC_M;
-        const int rloc = isY ? tid - TC_M : tid;
-        const int ant = isY ? j0 + rloc : i0 + rloc;
-        const bool wact = isY ? (32 * (rloc >> 5) < N && j0 + 32 * (rloc >> 5) < na)
-                              : (i0 + 32 * (rloc >> 5) < na);
-        if (wact) {
-            const bool live = ant < na && (!isY || rloc < N);
-            double px = 0.0, py = 0.0, pz = 0.0;
-            if (live) {
-                px = antv[4 * (size_t)ant];
-                py = antv[4 * (size_t)ant + 1];
-                pz = antv[4 * (size_t)ant + 2];
-            }
+    if (warp >= TC_ACC_WARPS) {
+        // ---------------- producers
+        setmaxnreg_dec<TC_PROD_REGS>();
+        const int pw = warp - TC_ACC_WARPS;
+        const int r = 32 * (pw & 3) + lane, hh = pw >> 2;
+        if (32 * (pw & 3) < max(nx, ny)) {
+            const bool xlive = r < nx, ylive = r < ny, diag = (i0 == j0);
             const double kappa = sgn_over_c * freqs[k];
-            const float sc = isY ? __ldg(ascale) : 1.f;
-            const float* Ak = A + (size_t)(k / TC_KC) * (size_t)S * TC_KC + (k % TC_KC);
-            const int roff = (isY ? TcSmem::YR_H : TcSmem::XR_H) + (rloc >> 3) * 256 + (rloc & 7) * 16;
-            const int arr = isY ? TcSmem::Y_ARR : TcSmem::X_ARR;
+            // antenna positions in cycles per unit direction cosine: phase = r' . shat
+            double xp[3] = {0.0, 0.0, 0.0}, yp[3] = {0.0, 0.0, 0.0};
+            if (xlive) {
+                const double* a = antv + 4 * (size_t)(i0 + r);
+                xp[0] = kappa * a[0], xp[1] = kappa * a[1], xp[2] = kappa * a[2];
+            }
+            if (ylive) {
+                const double* a = antv + 4 * (size_t)(j0 + r);
+                yp[0] = kappa * a[0], yp[1] = kappa * a[1], yp[2] = kappa * a[2];
+            }
+            const float sc = __ldg(ascale);
+            const int roff = (r >> 3) * 256 + hh * 128 + (r & 7) * 16;
             for (int it = 0; it < nst; ++it) {
-                const int stage = it % TC_NSTAGE;
+                const int stage = it % TC_NSTAGE, slot = it % TC_NSRC;
+                mbar_wait_bounded(&sfull[slot], (uint32_t)((it / TC_NSRC) & 1));
+                const unsigned char* src = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
+                const double4* sh = reinterpret_cast<const double4*>(src) + hh * 8;
+                const float4* av = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT) + hh * 2;
+                const float4 a0 = av[0], a1 = av[1];
+                const float a[8] = {a0.x * sc, a0.y * sc, a0.z * sc, a0.w * sc,
+                                    a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc};
+#if B200_TC_PV == 1
                 if (it >= TC_NSTAGE)
                     mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
                 unsigned char* row = smem + stage * TcSmem::STAGE + roff;
-                const long long sbase = (long long)un.y + (long long)it * TC_KS;
+                if (diag) tc_produce_rows<true>(row, sh, a, xp, yp, xlive, ylive);
+                else tc_produce_rows<false>(row, sh, a, xp, yp, xlive, ylive);
+#else
+                float cx[8], sx[8], cy[8], sy[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float c[8], s[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const long long src = sbase + h * 8 + e;
-                        const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * src));
-                        const double s2 = __ldg(shat + 4 * src + 2);
-                        const double u = __fma_rn(px, s01.x, __fma_rn(py, s01.y, pz * s2));
-                        antenna_cis(u, kappa, c[e], s[e]);
-                        if (isY) {
-                            const float a = __ldg(Ak + src * TC_KC) * sc;
-                            c[e] *= a;
-                            s[e] *= a;
-                        }
+                for (int e = 0; e < 8; ++e) {
+                    const double4 sv = sh[e];
+                    antenna_cis(__fma_rn(xp[0], sv.x, __fma_rn(xp[1], sv.y,
+                                __fma_rn(xp[2], sv.z, 1572864.0))), cx[e], sx[e]);
+                    if (diag) {
+                        cy[e] = cx[e];
+                        sy[e] = sx[e];
+                    } else {
+                        antenna_cis(__fma_rn(yp[0], sv.x, __fma_rn(yp[1], sv.y,
+                                    __fma_rn(yp[2], sv.z, 1572864.0))), cy[e], sy[e]);
                     }
-                    uint4 hi, lo;
-                    split8(c, hi, lo);
-                    *reinterpret_cast<uint4*>(row + h * 128) = hi;
-                    *reinterpret_cast<uint4*>(row + arr + h * 128) = lo;
-                    split8(s, hi, lo);
-                    *reinterpret_cast<uint4*>(row + 2 * arr + h * 128) = hi;
-                    *reinterpret_cast<uint4*>(row + 3 * arr + h * 128) = lo;
+                    cy[e] *= a[e];
+                    sy[e] *= a[e];
                 }
+                if (it >= TC_NSTAGE)
+                    mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
+                unsigned char* row = smem + stage * TcSmem::STAGE + roff;
+                uint4 hi, lo;
+                if (xlive) {
+                    split8(cx, hi, lo);
+                    *reinterpret_cast<uint4*>(row + TcSmem::XR_H) = hi;
+                    *reinterpret_cast<uint4*>(row + TcSmem::XR_L) = lo;
+                    split8(sx, hi, lo);
+                    *reinterpret_cast<uint4*>(row + TcSmem::XI_H) = hi;
+                    *reinterpret_cast<uint4*>(row + TcSmem::XI_L) = lo;
+                }
+                if (ylive) {
+                    split8(cy, hi, lo);
+                    *reinterpret_cast<uint4*>(row + TcSmem::YR_H) = hi;
+                    *reinterpret_cast<uint4*>(row + TcSmem::YR_L) = lo;
+                    split8(sy, hi, lo);
+                    *reinterpret_cast<uint4*>(row + TcSmem::YI_H) = hi;
+                    *reinterpret_cast<uint4*>(row + TcSmem::YI_L) = lo;
+                }
+#endif
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[stage]);
             }
         }
-        // ---------------- epilogue: TMEM -> registers -> Vpart through the pair table
-        mbar_wait_bounded(done, 0u);
-        tc_fence_after();
-        const int q = warp & 3, cg = warp >> 2;
-        const int ai = i0 + 32 * q + lane;
-        const float inv = 1.f / __ldg(ascale);
-        float2* vp = reinterpret_cast<float2*>(vpart) + (size_t)blockIdx.y * (size_t)nbl * nfp + k;
-        for (int cb = cg; cb < N / 32; cb += TC_PROD_WARPS / 4) {
-            float re[32], im[32];
-            const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(cb * 32);
-            tmem_ld32(ta, re);
-            tmem_ld32(ta + TC_IM_COL, im);
-            if (ai < na) {
-                const int* pb = pair_bl + (size_t)ai * ldp + j0 + cb * 32;
+    } else {
+        // ---------------- accumulator warps: lane quarter q (TMEM lanes 32 q ..), column half h
+        setmaxnreg_inc<TC_ACC_REGS>();
+        const int q = warp & 3, h = warp >> 2;
+        float aR[64], aI[64];
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const int4 e4 = __ldg(reinterpret_cast<const int4*>(pb) + j4);
-                    const int e[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        if (e[jj] < 0) continue;
-                        const int j = 4 * j4 + jj;
-                        vp[(size_t)(e[jj] >> 1) * nfp] =
-                            make_float2(re[j] * inv, (e[jj] & 1) ? -im[j] * inv : im[j] * inv);
+        for (int c = 0; c < 64; ++c) aR[c] = aI[c] = 0.f;
+        const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * h);
+        TcIssue iq;
+        iq.tmem = tmem;
+        iq.id_pos = umma_idesc_f16(N, false);
+        iq.id_neg = umma_idesc_f16(N, true);
+        iq.smem_base = smem_u32(smem);
+        // source data of stage st -> slot st % TC_NSRC (issued by lane 0 of warp 0)
+        auto stage_sources = [&](int st) {
+            const int slot = st % TC_NSRC;
+            unsigned char* dst = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
+            const long long s0 = (long long)un.y + (long long)st * TC_KS;
+            mbar_expect_tx(&sfull[slot], TcSmem::SRC_SLOT);
+            bulk_g2s(dst, shat + 4 * s0, TcSmem::SRC_SHAT, &sfull[slot]);
+            bulk_g2s(dst + TcSmem::SRC_SHAT, Ak + s0, TcSmem::SRC_A, &sfull[slot]);
+        };
+        if (warp == 0 && lane == 0)
+            for (int st = 0; st < min(nst, TC_NSRC); ++st) stage_sources(st);
+
+        for (int chain = 0; chain <= nchain; ++chain) {
+            if (warp == 0 && chain < nchain) {
+                // ---- issue the MMAs of this chain (stages chain * TC_FLUSH ..)
+                const int set = chain & 1;
+                if (chain >= 2)                // the set's previous chain has been read out
+                    mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
+                const int it1 = min(nst, (chain + 1) * TC_FLUSH);
+                for (int it = chain * TC_FLUSH; it < it1; ++it) {
+                    const int stage = it % TC_NSTAGE;
+                    mbar_wait_bounded(&full[stage], (uint32_t)((it / TC_NSTAGE) & 1));
+                    tc_fence_after();
+                    if (lane == 0) {
+                        tc_issue_stage(iq, stage, set, it == chain * TC_FLUSH);
+                        umma_commit(&empty[stage]);   // stage free once these MMAs have read it
+                        if (it == it1 - 1) umma_commit(&tfull[set]);
+                        // every producer has consumed the source slot of this stage: refill it
+                        if (it + TC_NSRC < nst) stage_sources(it + TC_NSRC);
                     }
+                    __syncwarp();
+                }
+            }
+            // ---- read out the previous chain (warp 0: while the tensor core works on this one)
+            const int rc = warp == 0 ? chain - 1 : chain;
+            if (rc < 0 || rc >= nchain) continue;
+            const int set = rc & 1;
+            mbar_wait_bounded(&tfull[set], (uint32_t)((rc >> 1) & 1));
+            tc_fence_after();
+            const uint32_t ta = ta0 + (uint32_t)(set * TC_SET_COLS);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                uint32_t vr[8], vi[8];
+                tmem_ld8(ta + 8 * g, vr);
+                tmem_ld8(ta + TC_IM_COL + 8 * g, vi);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    aR[8 * g + c] += __uint_as_float(vr[c]);
+                    aI[8 * g + c] += __uint_as_float(vi[c]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[set]);
+        }
+        // ---- scatter through the pair table
+        const int ai = i0 + 32 * q + lane;
+        if (ai < na) {
+            const float inv = 1.f / __ldg(ascale);
+            float2* vp = reinterpret_cast<float2*>(vpart) + (size_t)blockIdx.y * (size_t)nbl * nfp + k;
+            const int* pb = pair_bl + (size_t)ai * ldp + j0 + 64 * h;
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                if (64 * h + 4 * c4 >= N) break;
+                const int4 e4 = __ldg(reinterpret_cast<const int4*>(pb) + c4);
+                const int e[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (e[cc] < 0) continue;
+                    const int c = 4 * c4 + cc;
+                    vp[(size_t)(e[cc] >> 1) * nfp] =
+                        make_float2(aR[c] * inv, (e[cc] & 1) ? -aI[c] * inv : aI[c] * inv);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_PROD_WARPS) {
+    if (warp == TC_ACC_WARPS) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                      "r"(TC_TMEM_COLS)
                      : "memory");
     }
 }
 
+// -------------------------------------------------------------------------------------
+// backward.  grid = (nunits, nitem * nfreq), block = 512 (units fastest: CTAs that run together
+// share the cotangent operand of their (antenna block, channel) through L2).
+//
+// With the Hermitian cotangent matrix H[a][m] (ant_kernels.cu) the adjoints are
+//   y_a[s] = sum_m H[a][m] E_m[s],  p = conj(E_a[s]) y_a[s],
+//   dL/dA[s] = 1/2 sum_a Re p,      dL/dr_a = sum_s shat_s A_s (2 pi sgn nu / c) Im p.
+// y is a GEMM with M = sources (tiles of 128), N = antennas a (items of at most 128), K = partner
+// antennas m: the A operand E_m[s] is generated in shared memory (thread <-> source row, 8 of the
+// 16 antennas of a stage), the B operand H is fetched by TMA from a copy the host has scaled,
+// split into float16 hi / lo parts and laid out in the UMMA canonical order
+//   Hq[t][k][item][stage of 16 m][re_hi | re_lo | im_hi | im_lo][128 rows a x 16 m, canonical].
+// Chains of TC_FLUSH stages are added to register accumulators as in the forward kernel; after
+// the last stage of a source tile the accumulator warps regenerate E_a for their 64 antennas,
+// form p and reduce: dL/dA over the thread's own columns (one float per source, written
+// channel-major, partial per (item, column half)), dL/dr over the 32 sources of the warp with a
+// transposed shuffle reduction (lane <-> antenna), accumulated over the tiles of the unit.
+//   lower_only: H holds the doubled lower triangle (a > m; enough for dL/dA) and item ib stops
+//   after its own antennas.
+//   dAcm   [nitem * 2][Nfp][S]                 partial dL/dA, channel-major (sum over axis 0)
+//   drpart [nunits][Nfp][4][nitem * 128][4]    partial dL/dr (float32; sum over the first three)
+// -------------------------------------------------------------------------------------
+struct TcBwdSmem {
+    static constexpr int POS_MAX = 512;                        // antennas the position table holds
+    static constexpr int POS_OFF = TC_NSTAGE * TcSmem::STAGE;  // [POS_MAX][4] float64, kappa-scaled
+    // full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2]
+    static constexpr int BAR_OFF = POS_OFF + POS_MAX * 32;
+    static constexpr int TMEM_OFF = BAR_OFF + (2 * TC_NSTAGE + 4) * 8;
+    static constexpr int TOTAL = TMEM_OFF + 16;
+    static constexpr int H_BYTES = 4 * TcSmem::ARR;            // one stage of the cotangent operand
+};
 
-int launch_tc_fwd(const float* A, const float* ascale, const double* shat, const double* antv,
+__device__ __forceinline__ void tc_issue_stage_bwd(const TcIssue& q, int stage, int set, bool first) {
+    const uint32_t d_re = q.tmem + set * TC_SET_COLS, d_im = d_re + TC_IM_COL;
+    const uint32_t b = q.smem_base + stage * TcSmem::STAGE;
+    const uint64_t erh = umma_desc_kmajor(b + TcSmem::XR_H), erl = umma_desc_kmajor(b + TcSmem::XR_L),
+                   eih = umma_desc_kmajor(b + TcSmem::XI_H), eil = umma_desc_kmajor(b + TcSmem::XI_L),
+                   hrh = umma_desc_kmajor(b + TcSmem::YR_H), hrl = umma_desc_kmajor(b + TcSmem::YR_L),
+                   hih = umma_desc_kmajor(b + TcSmem::YI_H), hil = umma_desc_kmajor(b + TcSmem::YI_L);
+    const uint32_t acc = first ? 0u : 1u;
+    // Re y = Er.Hr - Ei.Hi
+    umma_f16(d_re, erh, hrh, q.id_pos, acc);
+    umma_f16(d_re, erh, hrl, q.id_pos, 1u);
+    umma_f16(d_re, erl, hrh, q.id_pos, 1u);
+    umma_f16(d_re, eih, hih, q.id_neg, 1u);
+    umma_f16(d_re, eih, hil, q.id_neg, 1u);
+    umma_f16(d_re, eil, hih, q.id_neg, 1u);
+    // Im y = Er.Hi + Ei.Hr
+    umma_f16(d_im, erh, hih, q.id_pos, acc);
+    umma_f16(d_im, erh, hil, q.id_pos, 1u);
+    umma_f16(d_im, erl, hih, q.id_pos, 1u);
+    umma_f16(d_im, eih, hrh, q.id_pos, 1u);
+    umma_f16(d_im, eih, hrl, q.id_pos, 1u);
+    umma_f16(d_im, eil, hrh, q.id_pos, 1u);
+}
+
+// v[i] summed over the 32 lanes, result for index i = lane left in v[0] (31 shuffles)
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restrict__ hscale,
+                     const float* __restrict__ Acm, const double* __restrict__ shat,
+                     const double* __restrict__ antv, const double* __restrict__ freqs,
+                     const int4* __restrict__ units, int nitem, int na, int nm_pad, int nfreq,
+                     int nfp, long long S, double sgn_over_c, int need_a, int need_r,
+                     int lower_only, float* __restrict__ dAcm, float* __restrict__ drpart) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ai = blockIdx.y / nfreq, k = blockIdx.y % nfreq;
+    const int4 un = units[blockIdx.x];
+    const int a0 = ai * TC_M;
+    // all 128 columns are computed: the operand rows of antennas >= na are zero, so are their
+    // sums, and the epilogue needs no column mask (the MMAs are not the bottleneck)
+    const int N = TC_NMAX;
+    const int nmst_all = nm_pad / TC_KS;
+    const int nmst = lower_only ? min(nmst_all, (ai + 1) * (TC_M / TC_KS)) : nmst_all;
+    const int ntile = (un.z - un.y + TC_M - 1) / TC_M;
+    if (ntile <= 0 || N <= 0) return;
+    const int nct = (nmst + TC_FLUSH - 1) / TC_FLUSH;                 // chains per source tile
+    const int nchain = ntile * nct;
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TcBwdSmem::BAR_OFF);
+    uint64_t* empty = full + TC_NSTAGE;
+    uint64_t* tfull = empty + TC_NSTAGE;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcBwdSmem::TMEM_OFF);
+    double4* pos = reinterpret_cast<double4*>(smem + TcBwdSmem::POS_OFF);
+    const double kappa = sgn_over_c * freqs[k];
+
+    for (int o = tid * 16; o < TC_NSTAGE * TcSmem::STAGE; o += TC_THREADS * 16)
+        *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
+    for (int a = tid; a < TcBwdSmem::POS_MAX; a += TC_THREADS) {
+        double4 p = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (a < na) {
+            p.x = kappa * antv[4 * (size_t)a];
+            p.y = kappa * antv[4 * (size_t)a + 1];
+            p.z = kappa * antv[4 * (size_t)a + 2];
+        }
+        pos[a] = p;
+    }
+    if (tid == 0) {
+        for (int st = 0; st < TC_NSTAGE; ++st) {
+            mbar_init(&full[st], TC_PROD_WARPS + 1);     // producer warps + the TMA's expect_tx
+            mbar_init(&empty[st], 1);
+        }
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(&tfull[q], 1);
+            mbar_init(&tempty[q], TC_ACC_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == TC_ACC_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp >= TC_ACC_WARPS) {
+        // ---------------- producers: thread <-> source row r of the tile, antennas 8 hh .. + 7
+        setmaxnreg_dec<TC_PROD_REGS>();
+        const int pw = warp - TC_ACC_WARPS;
+        const int r = 32 * (pw & 3) + lane, hh = pw >> 2;
+        const int roff = (r >> 3) * 256 + hh * 128 + (r & 7) * 16;
+        const unsigned char* Hbase = Hq + ((((size_t)un.x * nfp + k) * nitem + ai) * (size_t)nmst_all) *
+                                              TcBwdSmem::H_BYTES;
+        long long g = 0;
+        for (int tile = 0; tile < ntile; ++tile) {
+            const long long s = (long long)un.y + (long long)tile * TC_M + r;
+            const bool valid = s < un.z;
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+            if (valid) {
+                const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
+                sx = s01.x, sy = s01.y, sz = __ldg(shat + 4 * s + 2);
+            }
+            for (int ms = 0; ms < nmst; ++ms, ++g) {
+                const int stage = (int)(g % TC_NSTAGE);
+                unsigned char* sbase = smem + stage * TcSmem::STAGE;
+                if (pw == 0) {
+                    // this warp also fetches the cotangent operand of the stage
+                    if (g >= TC_NSTAGE)
+                        mbar_wait_bounded(&empty[stage], (uint32_t)(((g / TC_NSTAGE) - 1) & 1));
+                    if (lane == 0) {
+                        mbar_expect_tx(&full[stage], TcBwdSmem::H_BYTES);
+                        bulk_g2s(sbase + TcSmem::YR_H, Hbase + (size_t)ms * TcBwdSmem::H_BYTES,
+                                 TcBwdSmem::H_BYTES, &full[stage]);
+                    }
+                }
+                float c[8], sn[8];
+                const double4* pm = pos + ms * TC_KS + hh * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const double4 p = pm[e];
+                    antenna_cis(__fma_rn(p.x, sx, __fma_rn(p.y, sy, __fma_rn(p.z, sz, 1572864.0))),
+                                c[e], sn[e]);
+                    if (!valid) c[e] = sn[e] = 0.f;
+                }
+                if (pw != 0 && g >= TC_NSTAGE)
+                    mbar_wait_bounded(&empty[stage], (uint32_t)(((g / TC_NSTAGE) - 1) & 1));
+                uint4 hi, lo;
+                split8(c, hi, lo);
+                *reinterpret_cast<uint4*>(sbase + roff + TcSmem::XR_H) = hi;
+                *reinterpret_cast<uint4*>(sbase + roff + TcSmem::XR_L) = lo;
+                split8(sn, hi, lo);
+                *reinterpret_cast<uint4*>(sbase + roff + TcSmem::XI_H) = hi;
+                *reinterpret_cast<uint4*>(sbase + roff + TcSmem::XI_L) = lo;
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+            }
+        }
+    } else {
+        // ---------------- accumulator warps: lane quarter q (source rows 32 q ..), column half h
+        setmaxnreg_inc<TC_ACC_REGS>();
+        const int q = warp & 3, h = warp >> 2;
+        float aR[64], aI[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) aR[c] = aI[c] = 0.f;
+        float gr[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * h);
+        TcIssue iq;
+        iq.tmem = tmem;
+        iq.id_pos = umma_idesc_f16(N, false);
+        iq.id_neg = umma_idesc_f16(N, true);
+        iq.smem_base = smem_u32(smem);
+        const float inv_h = 1.f / __ldg(hscale);
+        const float kf = (float)(kappa * 6.283185307179586476925286766559);
+
+        for (int chain = 0; chain <= nchain; ++chain) {
+            if (warp == 0 && chain < nchain) {
+                // ---- issue the MMAs of this chain
+                const int set = chain & 1;
+                if (chain >= 2)
+                    mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
+                const int tile = chain / nct, ms0 = (chain % nct) * TC_FLUSH;
+                const int ms1 = min(nmst, ms0 + TC_FLUSH);
+                for (int ms = ms0; ms < ms1; ++ms) {
+                    const long long g = (long long)tile * nmst + ms;
+                    const int stage = (int)(g % TC_NSTAGE);
+                    mbar_wait_bounded(&full[stage], (uint32_t)((g / TC_NSTAGE) & 1));
+                    tc_fence_after();
+                    if (lane == 0) {
+                        tc_issue_stage_bwd(iq, stage, set, ms == ms0);
+                        umma_commit(&empty[stage]);
+                        if (ms == ms1 - 1) umma_commit(&tfull[set]);
+                    }
+                    __syncwarp();
+                }
+            }
+            const int rc = warp == 0 ? chain - 1 : chain;
+            if (rc < 0 || rc >= nchain) continue;
+            {
+                const int set = rc & 1;
+                mbar_wait_bounded(&tfull[set], (uint32_t)((rc >> 1) & 1));
+                tc_fence_after();
+                const uint32_t ta = ta0 + (uint32_t)(set * TC_SET_COLS);
+#pragma unroll
+                for (int g8 = 0; g8 < 8; ++g8) {
+                    uint32_t vr[8], vi[8];
+                    tmem_ld8(ta + 8 * g8, vr);
+                    tmem_ld8(ta + TC_IM_COL + 8 * g8, vi);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        aR[8 * g8 + c] += __uint_as_float(vr[c]);
+                        aI[8 * g8 + c] += __uint_as_float(vi[c]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[set]);
+            }
+            if (rc % nct != nct - 1) continue;
+            // ---- source tile complete: p = conj(E_a) y_a for this thread's source and 64 antennas
+            const int tile = rc / nct;
+            const long long s = (long long)un.y + (long long)tile * TC_M + 32 * q + lane;
+            const bool valid = s < un.z;
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+            float wk = 0.f;
+            if (valid) {
+                const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
+                sx = s01.x, sy = s01.y, sz = __ldg(shat + 4 * s + 2);
+                if (need_r) wk = __ldg(Acm + (size_t)k * (size_t)S + s) * kf * inv_h;
+            }
+            const float fx = (float)sx, fy = (float)sy, fz = (float)sz;
+            float dacc = 0.f;
+#pragma unroll
+            for (int grp = 0; grp < 2; ++grp) {
+                float w[32];
+                const double4* pa = pos + a0 + 64 * h + 32 * grp;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const double4 p = pa[c];
+                    float cs, sn;
+                    antenna_cis(__fma_rn(p.x, sx, __fma_rn(p.y, sy, __fma_rn(p.z, sz, 1572864.0))),
+                                cs, sn);
+                    const float yr = aR[32 * grp + c], yi = aI[32 * grp + c];
+                    dacc = fmaf(cs, yr, fmaf(sn, yi, dacc));            // Re(conj(E) y)
+                    w[c] = wk * fmaf(cs, yi, -sn * yr);                 // A kappa 2 pi Im(conj(E) y)
+                    aR[32 * grp + c] = 0.f;
+                    aI[32 * grp + c] = 0.f;
+                }
+                if (need_r) {
+                    float v[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = w[c] * fx;
+                    gr[grp][0] += warp_reduce_scatter32(v, lane);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = w[c] * fy;
+                    gr[grp][1] += warp_reduce_scatter32(v, lane);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = w[c] * fz;
+                    gr[grp][2] += warp_reduce_scatter32(v, lane);
+                }
+            }
+            if (need_a && valid)
+                dAcm[((size_t)(ai * 2 + h) * nfp + k) * (size_t)S + s] = 0.5f * dacc * inv_h;
+        }
+        if (need_r) {
+            float4* dst = reinterpret_cast<float4*>(drpart) +
+                          (((size_t)blockIdx.x * nfp + k) * 4 + q) * (size_t)(nitem * TC_M) + a0 + 64 * h;
+            dst[lane] = make_float4(gr[0][0], gr[0][1], gr[0][2], 0.f);
+            dst[32 + lane] = make_float4(gr[1][0], gr[1][1], gr[1][2], 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_ACC_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+int launch_tc_fwd(const float* Acm, const float* ascale, const double* shat, const double* antv,
                   const double* freqs, const int* units, int nunits, const int* items, int nitems,
                   const int* pair_bl, int ldp, int na, int nbl, int nfreq, long long S, int conj,
                   float* vpart, cudaStream_t st) {
@@ -363,27 +829,73 @@ int launch_tc_fwd(const float* A, const float* ascale, const double* shat, const
     const long long gx = (long long)nitems * nfreq;
     if (gx > 2147483647LL || nunits > 65535) return set_error("tcfringe_fwd: grid too large");
     static DeviceOnce attr_once;
-    if (attr_once.first() &&
-        cudaFuncSetAttribute(tc_fringe_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TcSmem::TOTAL) != cudaSuccess)
-        return set_error("tcfringe_fwd: cannot reserve shared memory");
+    if (attr_once.first()) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, tc_fringe_fwd_kernel) != cudaSuccess ||
+            fa.numRegs * TC_THREADS < 256 * (TC_ACC_REGS + TC_PROD_REGS))
+            return set_error("tcfringe_fwd: register pool smaller than the setmaxnreg plan");
+        if (cudaFuncSetAttribute(tc_fringe_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TcSmem::TOTAL) != cudaSuccess)
+            return set_error("tcfringe_fwd: cannot reserve shared memory");
+    }
     dim3 grid((unsigned)gx, nunits);
     tc_fringe_fwd_kernel<<<grid, TC_THREADS, TcSmem::TOTAL, st>>>(
-        A, ascale, shat, antv, freqs, reinterpret_cast<const int4*>(units),
+        Acm, ascale, shat, antv, freqs, reinterpret_cast<const int4*>(units),
         reinterpret_cast<const int4*>(items), pair_bl, ldp, na, nbl, nfreq, nfp, S,
         (conj ? -1.0 : 1.0) / C_LIGHT, vpart);
     return check_launch("tcfringe_fwd");
+}
+
+int launch_tc_bwd(const void* Hq, const float* hscale, const float* Acm, const double* shat,
+                  const double* antv, const double* freqs, const int* units, int nunits, int nitem,
+                  int na, int nm_pad, int nfreq, long long S, int conj, int lower_only, float* dAcm,
+                  float* drpart, cudaStream_t st) {
+    if (nunits <= 0 || nitem <= 0 || nfreq <= 0) return 0;
+    if (S % SRC_PAD) return set_error("tcfringe_bwd: S must be a multiple of 128");
+    if (nm_pad % TC_KS || nm_pad < na || nm_pad > TcBwdSmem::POS_MAX || nitem * TC_M > TcBwdSmem::POS_MAX ||
+        nitem != (na + TC_M - 1) / TC_M)
+        return set_error("tcfringe_bwd: antenna count / padding not supported (na <= 512, nm_pad % 16)");
+    if (drpart != nullptr && Acm == nullptr)
+        return set_error("tcfringe_bwd: the antenna gradient needs the perceived sky");
+    const int nfp = ((nfreq + TC_KC - 1) / TC_KC) * TC_KC;
+    const long long gy = (long long)nitem * nfreq;
+    if (gy > 65535) return set_error("tcfringe_bwd: grid too large");
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, tc_fringe_bwd_kernel) != cudaSuccess ||
+            fa.numRegs * TC_THREADS < 256 * (TC_ACC_REGS + TC_PROD_REGS))
+            return set_error("tcfringe_bwd: register pool smaller than the setmaxnreg plan");
+        if (cudaFuncSetAttribute(tc_fringe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TcBwdSmem::TOTAL) != cudaSuccess)
+            return set_error("tcfringe_bwd: cannot reserve shared memory");
+    }
+    dim3 grid(nunits, (unsigned)gy);
+    tc_fringe_bwd_kernel<<<grid, TC_THREADS, TcBwdSmem::TOTAL, st>>>(
+        static_cast<const unsigned char*>(Hq), hscale, Acm, shat, antv, freqs,
+        reinterpret_cast<const int4*>(units), nitem, na, nm_pad, nfreq, nfp, S,
+        (conj ? -1.0 : 1.0) / C_LIGHT, dAcm != nullptr, drpart != nullptr, lower_only, dAcm, drpart);
+    return check_launch("tcfringe_bwd");
 }
 
 }  // namespace b200rime
 
 extern "C" {
 
-int b200rime_tcfringe_fwd_f32(const float* A, const float* ascale, const double* shat,
+int b200rime_tcfringe_bwd_f32(const void* Hq, const float* hscale, const float* Acm,
+                              const double* shat, const double* antv, const double* freqs,
+                              const int* units, int nunits, int nitem, int na, int nm_pad,
+                              int nfreq, long long S, int conj, int lower_only, float* dAcm,
+                              float* drpart, void* stream) {
+    return b200rime::launch_tc_bwd(Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, na,
+                                   nm_pad, nfreq, S, conj, lower_only, dAcm, drpart,
+                                   (cudaStream_t)stream);
+}
+int b200rime_tcfringe_fwd_f32(const float* Acm, const float* ascale, const double* shat,
                               const double* antv, const double* freqs, const int* units, int nunits,
                               const int* items, int nitems, const int* pair_bl, int ldp, int na,
                               int nbl, int nfreq, long long S, int conj, float* Vpart, void* stream) {
-    return b200rime::launch_tc_fwd(A, ascale, shat, antv, freqs, units, nunits, items, nitems,
+    return b200rime::launch_tc_fwd(Acm, ascale, shat, antv, freqs, units, nunits, items, nitems,
                                    pair_bl, ldp, na, nbl, nfreq, S, conj, Vpart,
                                    (cudaStream_t)stream);
 }

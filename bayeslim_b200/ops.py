@@ -692,6 +692,54 @@ class TcTiling:
         dev = torch.device(device)
         self.items = torch.as_tensor(np.asarray(items, dtype=np.int32).reshape(-1, 4), device=dev)
         self.pair_bl = torch.as_tensor(pair.reshape(self.ldp, self.ldp), device=dev)
+        # backward (include/b200rime.h, tcfringe_bwd): items of 128 output antennas, partner axis
+        # padded to 16
+        self.nitem_bwd = -(-self.na // M)
+        self.apad = self.nitem_bwd * M
+        self.nm_pad = -(-self.na // 16) * 16
+        self.bwd_usable = self.usable and self.na <= 512
+        self.i = torch.as_tensor(i, device=dev)
+        self.j = torch.as_tensor(j, device=dev)
+        self.cross = torch.as_tensor(np.nonzero(i != j)[0], device=dev)
+        self.auto = torch.as_tensor(np.nonzero(i == j)[0], device=dev)
+        self.jgt = torch.as_tensor(np.nonzero(j > i)[0], device=dev)
+        self.igt = torch.as_tensor(np.nonzero(i > j)[0], device=dev)
+
+    def cotangent_operand(self, G, nfp, lower_only=False):
+        """G (nbl, nt, nf) complex64 -> (Hq, hscale): the Hermitian cotangent matrix
+        H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m), 2 Re G_b for autos (lower_only: the
+        doubled lower triangle a > m), scaled by the power of two hscale into float16 range,
+        split into float16 hi / lo parts and laid out as the UMMA B operand of tcfringe_bwd:
+        [nt][Nfp][item][stage of 16 m][re_hi | re_lo | im_hi | im_lo][16 row groups][2 k groups]
+        [8 rows][8 k]."""
+        nbl, nt, nf = G.shape
+        Gq = G.permute(1, 2, 0)                                    # (nt, nf, nbl)
+        H = torch.zeros(nt, nfp, self.apad, self.nm_pad, dtype=torch.complex64, device=G.device)
+        Hv = H[:, :nf]
+        if lower_only:
+            if len(self.jgt):
+                Hv[:, :, self.j[self.jgt], self.i[self.jgt]] = 2 * Gq.index_select(2, self.jgt)
+            if len(self.igt):
+                Hv[:, :, self.i[self.igt], self.j[self.igt]] = 2 * Gq.index_select(2, self.igt).conj()
+        else:
+            Hv[:, :, self.j, self.i] = Gq
+            if len(self.cross):
+                Hv[:, :, self.i[self.cross], self.j[self.cross]] = Gq.index_select(2, self.cross).conj()
+        if len(self.auto):
+            Hv[:, :, self.i[self.auto], self.i[self.auto]] = \
+                (2 * Gq.index_select(2, self.auto).real).to(G.dtype)
+        Hr = torch.view_as_real(H)                                  # (nt, nfp, apad, nm, 2)
+        amax = Hr.abs().amax().clamp_min(1e-30)
+        hscale = torch.exp2(14.0 - torch.floor(torch.log2(amax))).to(torch.float32).reshape(1)
+        Hr = Hr * hscale
+        hi = Hr.to(torch.float16)
+        lo = (Hr - hi.to(torch.float32)).to(torch.float16)
+        del Hr, H
+        Q = torch.stack([hi[..., 0], lo[..., 0], hi[..., 1], lo[..., 1]], dim=2)   # (nt,nfp,4,a,m)
+        del hi, lo
+        Q = Q.reshape(nt, nfp, 4, self.nitem_bwd, 16, 8, self.nm_pad // 16, 2, 8)
+        Q = Q.permute(0, 1, 3, 6, 2, 4, 7, 5, 8).contiguous()
+        return Q, hscale
 
 
 def tc_scale(A):
@@ -721,13 +769,16 @@ class _AntFringeSum(torch.autograd.Function):
             # pairs outside the tiling keep their zero: every wanted pair has exactly one owner
             vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=torch.float32, device=dev)
             Vr = torch.view_as_real(V)
-            ascale = tc_scale(A) if tc is not None else None
+            if tc is not None:
+                # channel-major copy: a stage's 16 sky values become one contiguous TMA copy
+                ascale = tc_scale(A)
+                acm = A.permute(0, 1, 3, 2).reshape(nplane, nfp, A.shape[2]).contiguous()
             for (ta, tb) in batches:
                 u0, u1 = ubeg[ta], ubeg[tb]
                 ub = torch.as_tensor(np.asarray(ubeg[ta:tb + 1], dtype=np.int32) - u0, device=dev)
                 for p in range(nplane):
                     if tc is not None:
-                        _call("tcfringe_fwd", "f32", A[p], ascale[p:p + 1], geom.shat, antv,
+                        _call("tcfringe_fwd", "f32", acm[p], ascale[p:p + 1], geom.shat, antv,
                               freqs64, units[u0:], u1 - u0, tc.items, tc.nitems, tc.pair_bl,
                               tc.ldp, tc.na, nbl, nfreq, geom.S, int(conj), vpart)
                     else:
@@ -737,16 +788,21 @@ class _AntFringeSum(torch.autograd.Function):
                     _call("reduce_units", "f32", vpart, ub, tb - ta, nbl, nfreq,
                           Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, 0)
         ctx.save_for_backward(A, antv, freqs64)
-        ctx.meta = (geom, nfreq, int(conj), tiling, antvecs.dtype, antvecs.device, antvecs.shape)
+        ctx.meta = (geom, nfreq, int(conj), tiling, antvecs.dtype, antvecs.device, antvecs.shape,
+                    tc)
         return V
 
     @staticmethod
     def backward(ctx, G):
         A, antv, freqs64 = ctx.saved_tensors
-        geom, nfreq, conj, tiling, adtype, adev, ashape_ant = ctx.meta
+        geom, nfreq, conj, tiling, adtype, adev, ashape_ant, tc = ctx.meta
         need_A, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dA, dr = _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, A.shape, need_A,
-                               need_r)
+        if tc is not None and tc.bwd_usable:
+            dA, dr = _tc_backward(G, A, antv, geom, freqs64, nfreq, conj, tc, A.shape, need_A,
+                                  need_r)
+        else:
+            dA, dr = _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, A.shape, need_A,
+                                   need_r)
         gant = None
         if need_r:
             gant = torch.zeros(ashape_ant, dtype=torch.float64, device=G.device)
@@ -790,6 +846,48 @@ def _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, ashape, need_A
                 del Hp
             if need_A:
                 dA[p] = dApart.sum(0)
+    return dA, dr
+
+
+TC_H_BUDGET = 3 << 30       # bytes of dense cotangent matrix per backward sub-batch of times
+
+
+def _tc_backward(G, A, antv, geom, freqs64, nfreq, conj, tc, ashape, need_A, need_r):
+    """Tensor-core adjoints (tcfringe_bwd) for a cotangent G (nplane, Nbl, Nt, Nf) complex64: dA in
+    the tiled layout and dL/d(antenna positions) (rows, 3) float64 (needs the perceived sky A)."""
+    dev = G.device
+    nplane, nchunk, S, kc = ashape
+    nfp = nchunk * kc
+    nt = geom.nt
+    dA = torch.zeros(ashape, dtype=torch.float32, device=dev) if need_A else None
+    dr = torch.zeros(antv.shape[0], 3, dtype=torch.float64, device=dev) if need_r else None
+    if tc.nbl > 0 and nt > 0 and geom.S > 0 and (need_A or need_r):
+        units, ubeg = geom.units(tc.nbl, nchunk, sm_count(dev))
+        per_time = nfp * tc.apad * tc.nm_pad * 8
+        tstep = max(1, TC_H_BUDGET // per_time)
+        G = G.contiguous()
+        for p in range(nplane):
+            dAcm = (torch.zeros(tc.nitem_bwd * 2, nfp, S, dtype=torch.float32, device=dev)
+                    if need_A else None)
+            acm = A[p].permute(0, 2, 1).reshape(nfp, S).contiguous() if need_r else None
+            for ta in range(0, nt, tstep):
+                tb = min(nt, ta + tstep)
+                u0, u1 = ubeg[ta], ubeg[tb]
+                if u1 == u0:
+                    continue
+                Hq, hscale = tc.cotangent_operand(G[p, :, ta:tb], nfp, lower_only=not need_r)
+                un = units[u0:u1].clone()
+                un[:, 0] -= ta
+                drpart = (torch.zeros(u1 - u0, nfp, 4, tc.apad, 4, dtype=torch.float32, device=dev)
+                          if need_r else None)
+                _call("tcfringe_bwd", "f32", Hq, hscale, acm, geom.shat, antv, freqs64, un,
+                      u1 - u0, tc.nitem_bwd, tc.na, tc.nm_pad, nfreq, geom.S, conj,
+                      int(not need_r), dAcm, drpart)
+                if need_r:
+                    dr[:tc.na] += drpart.sum(dim=(0, 1, 2), dtype=torch.float64)[:tc.na, :3]
+                del Hq
+            if need_A:
+                dA[p] = dAcm.sum(0).reshape(nchunk, kc, S).permute(0, 2, 1)
     return dA, dr
 
 

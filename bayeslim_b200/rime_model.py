@@ -141,6 +141,7 @@ class RIME(utils.Module):
         self.sim_blvec_groups = {k: self.array.get_blvecs(v) for k, v in sim_bl_groups.items()}
         self._bl_meta = {}
         self._ant_tilings = {}
+        self._tc_tilings = {}
         if data_bls is None:
             self.data_bl_groups = self.sim_bl_groups
             self._sim2data = {k: None for k in sim_bl_groups}
@@ -272,12 +273,27 @@ class RIME(utils.Module):
             self._ant_tilings[key] = til
         return self._ant_tilings[key]
 
+    def _tc_tiling(self, dev):
+        """ops.TcTiling of the current baseline group (tensor-core forward kernel) when the
+        antenna-factorised route is taken, else None.  B200RIME_TC=0 keeps the FP32-pipe
+        forward kernel."""
+        if os.environ.get("B200RIME_TC", "1") == "0":
+            return None
+        til = self._ant_tiling(dev)
+        if til is None:
+            return None
+        key = (self._bl_key, dev)
+        if key not in self._tc_tilings:
+            tc = ops.TcTiling(til.i.cpu().numpy(), til.j.cpu().numpy(), til.na, dev)
+            self._tc_tilings[key] = tc if tc.usable else None
+        return self._tc_tilings[key]
+
     def _fringe(self, A, blvecs, rec, f64, nfreq, uniform, dev):
         """Fringe sum of tiled planes A over all baselines of the current group."""
         til = self._ant_tiling(dev) if A.dtype == torch.float32 else None
         if til is not None:
             return ops.fringe_sum_ant(A, self.array.antvecs.to(dev), til, rec.geom, f64, nfreq,
-                                      conj=False)
+                                      conj=False, tc=self._tc_tiling(dev))
         return ops.fringe_sum(A, blvecs, rec.geom, f64, nfreq, conj=False, uniform=uniform)
 
     def _geometry(self, sky_comp, dev):
@@ -487,9 +503,11 @@ class RIME(utils.Module):
             vis = torch.index_select(vis, 2, sim2data.to(vis.device))
 
         vd = VisData()
-        telescope = self.telescope.__class__(self.telescope.location,
-                                             tloc=getattr(self.telescope, 'tloc', None),
-                                             device=self.telescope.device)
+        tkw = dict(tloc=getattr(self.telescope, 'tloc', None), device=self.telescope.device)
+        if hasattr(self.telescope, 'eq2top_fn'):      # this package's TelescopeModel
+            tkw.update(dtype=getattr(self.telescope, 'dtype', None),
+                       eq2top_fn=self.telescope.eq2top_fn)
+        telescope = self.telescope.__class__(self.telescope.location, **tkw)
         vd.setup_meta(telescope, self.array.to_antpos())
         vd.setup_data(self.data_bls, self.sim_times, self.freqs, pol=pol, data=vis, flags=None,
                       cov=None, history=self._history())

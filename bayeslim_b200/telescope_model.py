@@ -4,12 +4,12 @@ Host-side mirror of the reference's telescope_model (bayeslim/telescope_model.py
 layout, baseline vectors, redundancy bookkeeping, fringe).
 
 Differences that matter:
-  * astropy is not a dependency.  ``TelescopeModel.eq2top`` answers from ``conv_cache``
-    (the reference's own cache, keyed exactly as rime_model.py:345 builds the key) and, on a
-    miss, from a built-in rigid sky rotation about the celestial pole (no precession /
-    nutation / aberration -- parity with astropy is unpinned); users who
-    need astropy's transformation inject its output into ``conv_cache`` or pass
-    ``eq2top_fn``.
+  * ``TelescopeModel.eq2top`` answers from ``conv_cache`` (the reference's own cache, keyed
+    exactly as rime_model.py:345 builds the key) and, on a miss, from astropy's ICRS -> AltAz
+    when astropy is importable (the reference's own call).  Without astropy (this image) it
+    warns once and uses a rigid sky rotation about the celestial pole (no precession /
+    nutation / aberration -- parity with astropy is unpinned); ``eq2top_fn``
+    overrides both.
   * ``ArrayModel.gen_fringe`` keeps the reference signature and semantics for callers
     outside the RIME (imaging), but ``rime_model.RIME`` never calls it: the fringe is
     generated inside the CUDA kernels (ops.fringe_sum).
@@ -76,7 +76,42 @@ def JD2LST(jd, longitude):
     return np.mod(gmst_hours * 15.0 + longitude, 360.0) * D2R
 
 
+_WARNED_NO_ASTROPY = False
+
+
+def _astropy_eq2top(location, time, ra, dec):
+    """The reference's own conversion (telescope_model.py:469-502): astropy ICRS -> AltAz."""
+    from astropy import units
+    from astropy.coordinates import AltAz, EarthLocation, ICRS
+    from astropy.time import Time
+    if not isinstance(location, EarthLocation):
+        alt = location[2] if len(location) > 2 else 0.0
+        location = EarthLocation.from_geodetic(location[0], location[1], alt)
+    altaz = AltAz(location=location, obstime=Time(time, format='jd'))
+    out = ICRS(ra=np.asarray(ra) * units.deg, dec=np.asarray(dec) * units.deg).transform_to(altaz)
+    return out.zen.deg, out.az.deg
+
+
 def eq2top(location, time, ra, dec):
+    """(ra, dec) [deg] -> (zen, az) [deg] at `location` (lon, lat[, alt]) and Julian date `time`.
+    With astropy installed this is the reference's ICRS -> AltAz transformation
+    (telescope_model.py:469-502).  Without it (this image) it falls back, with a warning, to
+    eq2top_rigid: a rotation about the celestial pole, arcminutes away from astropy for J2000
+    coordinates observed today -- inject conv_cache or eq2top_fn for survey-grade geometry."""
+    global _WARNED_NO_ASTROPY
+    try:
+        return _astropy_eq2top(location, time, ra, dec)
+    except ImportError:
+        if not _WARNED_NO_ASTROPY:
+            import warnings
+            warnings.warn("bayeslim_b200: astropy is not installed; eq2top falls back to a rigid "
+                          "sky rotation (no precession / nutation / aberration). Inject "
+                          "TelescopeModel.conv_cache or eq2top_fn for astropy-grade angles.")
+            _WARNED_NO_ASTROPY = True
+        return eq2top_rigid(location, time, ra, dec)
+
+
+def eq2top_rigid(location, time, ra, dec):
     """Rigid rotation of (ra, dec) [deg] to (zen, az) [deg] at `location` (lon, lat[, alt]) and
     Julian date `time`.  Not astropy's ICRS->AltAz (telescope_model.py:469-502): no precession,
     nutation, aberration or refraction."""

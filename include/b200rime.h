@@ -271,11 +271,14 @@ int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* sh
  * rime_model.py:426-429) as a batched complex GEMM V = E^H diag(A) E on the 5th-generation
  * tensor cores: operands generated in shared memory (float64 phases, MUFU sine / cosine), split
  * into float16 hi + lo pairs (three MMAs per real product, float32-grade results), FP32
- * accumulators in tensor memory.
+ * accumulators in tensor memory, read out every 64 sources into register accumulators (the
+ * tensor core's accumulate truncates; short chains keep the bias below 1e-6).
+ *   Acm      float [Nfp][S]   the perceived sky A, channel-major (row = channel over the packed
+ *            source axis; the tiled A transposed), so that a stage's sources are contiguous
  *   ascale   float [1]   power of two s with max|A| s in [2^14, 2^15) (float16 range of A E)
  *   antv     f64 [>= na][4]   antenna positions (ENU metres)
  *   items    int32 [nitems][4]   {i0, j0, N, 0}: first antennas i0 .. i0 + 127 (tc_rows()) against
- *            second antennas j0 .. j0 + N - 1, N a multiple of 32, <= tc_cols_max() = 256;
+ *            second antennas j0 .. j0 + N - 1, N a multiple of 32, <= tc_cols_max() = 128;
  *            i0 + 128 and j0 + N may exceed na (rows beyond na are skipped)
  *   pair_bl  int32 [ldp][ldp]    (baseline << 1 | c) of the pair (first i, second j), or -1;
  *            c = 1: the baseline is (j, i) and the result is conjugated on output; ldp = na
@@ -283,11 +286,34 @@ int b200rime_antfringe_bwd_f32(const float* Hp, const float* A, const double* sh
  *   Vpart    [nunits][nbl][Nfp][2]   (as fringe_sum_fwd; reduce with reduce_units) */
 int b200rime_tc_rows(void);
 int b200rime_tc_cols_max(void);
-int b200rime_tcfringe_fwd_f32(const float* A, const float* ascale, const double* shat,
+int b200rime_tcfringe_fwd_f32(const float* Acm, const float* ascale, const double* shat,
                               const double* antv, const double* freqs, const int* units,
                               int nunits, const int* items, int nitems, const int* pair_bl,
                               int ldp, int na, int nbl, int nfreq, long long S, int conj,
                               float* Vpart, b200rime_stream_t stream);
+
+/* Backward of the same sum on the tensor cores: y_a[s] = sum_m H[a][m] E_m[s] as a GEMM
+ * (M = sources, N = antennas a, K = partner antennas m), then p = conj(E_a) y_a,
+ * dL/dA = 1/2 sum_a Re p and dL/dr_a = sum_s shat_s A_s (2 pi sgn nu / c) Im p (autograd of
+ * rime_model.py:429 w.r.t. psky and of telescope_model.py:356 w.r.t. the antenna positions).
+ *   Hq      float16 [nt][Nfp][nitem][nm_pad/16][4][16][2][8][8]: the Hermitian cotangent matrix
+ *           (as for antfringe_bwd: H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m),
+ *           2 Re G_b for autos; lower_only != 0: the doubled lower triangle a > m, enough for
+ *           dL/dA), times hscale, split into float16 hi + lo, as UMMA K-major B operands:
+ *           [item of 128 antennas a][stage of 16 m][re_hi | re_lo | im_hi | im_lo]
+ *           [a / 8][m / 8][a % 8][m % 8]
+ *   hscale  float [1]   power of two that brings max |H| into [2^14, 2^15)
+ *   Acm     float [Nfp][S] channel-major perceived sky (only for drpart, else NULL)
+ *   nitem = ceil(na / 128), nm_pad = na rounded up to 16, na <= 512
+ *   dAcm    float [nitem * 2][Nfp][S]   partial dL/dA, channel-major; ZERO before the call
+ *           (padding sources and channels are not written); sum over the first axis; or NULL
+ *   drpart  float [nunits][Nfp][4][nitem * 128][4]   partial dL/dr; sum over the first three
+ *           axes; or NULL */
+int b200rime_tcfringe_bwd_f32(const void* Hq, const float* hscale, const float* Acm,
+                              const double* shat, const double* antv, const double* freqs,
+                              const int* units, int nunits, int nitem, int na, int nm_pad,
+                              int nfreq, long long S, int conj, int lower_only, float* dAcm,
+                              float* drpart, b200rime_stream_t stream);
 
 /* ---- gain application --------------------------------------
  * V_out = g_1 V g_2^H per baseline: reference calibration._apply_cal (calibration.py:2412-2487),

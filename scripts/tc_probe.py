@@ -79,11 +79,11 @@ def run(na, ns, nfreq, dyn=1.0, time_it=False, seed=0, extent=300.0, unit_max=81
         out["sample"] = [[complex(a).real, complex(a).imag, complex(b).real, complex(b).imag]
                          for a, b in zip(V[:4, 0].tolist(), ref[:4, 0].tolist())]
     if time_it:
-        if til.usable:
+        if til.usable and not (len(sys.argv) > 1 and sys.argv[1] == "time"):
             V2 = ops.fringe_sum_ant(A, antvecs, til, geom, f64, nfreq)[0, :, 0]
             out["relmax_fp32"] = ((V2.to(torch.complex128) - ref).abs().max().item() / scale)
         for name, kw in (("tc", dict(tc=tc)), ("fp32", dict())):
-            if name == "fp32" and not til.usable:
+            if name == "fp32" and (not til.usable or (len(sys.argv) > 1 and sys.argv[1] == "time")):
                 continue
             for _ in range(2):
                 ops.fringe_sum_ant(A, antvecs, til, geom, f64, nfreq, **kw)
@@ -98,6 +98,70 @@ def run(na, ns, nfreq, dyn=1.0, time_it=False, seed=0, extent=300.0, unit_max=81
     return out
 
 
+def run_bwd(na, ns, nfreq, need_r=True, seed=0, time_it=False):
+    """Tensor-core backward against complex128 autograd of the same sum."""
+    dev = torch.device("cuda")
+    ops.UNIT_MAX_SRC = 8192
+    antv, zen, az, freqs, i, j = make_case(na, ns, nfreq, seed)
+    geom = ops.Geometry([torch.as_tensor(zen)], [torch.as_tensor(az)], dev)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A_rm = (torch.randn(nfreq, ns, generator=g).abs() * 3.7e3).to(dev, torch.float32)
+    G = torch.complex(torch.randn(len(i), nfreq, generator=g, dtype=torch.float64),
+                      torch.randn(len(i), nfreq, generator=g, dtype=torch.float64)).to(dev) * 2.5e-3
+    til = ops.AntTiling(i, j, na, dev)
+    tc = ops.TcTiling(i, j, na, dev)
+    f64 = torch.as_tensor(freqs, device=dev, dtype=torch.float64)
+    out = dict(kind="bwd", na=na, ns=ns, nfreq=nfreq, need_r=need_r)
+    res = {}
+    for name, kw in (("tc", dict(tc=tc)), ("fp32", dict())):
+        if name == "fp32" and not til.usable:
+            continue
+        Ain = A_rm.clone().requires_grad_(True)
+        antvecs = torch.as_tensor(antv, device=dev).requires_grad_(need_r)
+        A = ops.pack_planes(geom, [Ain[None]])
+        V = ops.fringe_sum_ant(A, antvecs, til, geom, f64, nfreq, **kw)[0, :, 0]
+        loss = torch.sum(G.real.float() * V.real + G.imag.float() * V.imag)
+        loss.backward()
+        res[name] = (Ain.grad.double(), antvecs.grad.double() if need_r else None)
+        if time_it:
+            Gc = torch.zeros(1, len(i), 1, nfreq, dtype=torch.complex64, device=dev)
+            Gc[0, :, 0] = G.to(torch.complex64)
+            fn = ops._tc_backward if name == "tc" else ops._ant_backward
+            t_or_til = tc if name == "tc" else til
+            antv4 = til.antv4(antvecs)
+            for _ in range(2):
+                fn(Gc, A.detach(), antv4, geom, f64, nfreq, 0, t_or_til, A.shape, True, need_r)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn(Gc, A.detach(), antv4, geom, f64, nfreq, 0, t_or_til, A.shape, True, need_r)
+            torch.cuda.synchronize()
+            out["ms_" + name] = (time.perf_counter() - t0) / 3 * 1e3
+    if ns * na * nfreq <= 4e7:
+        # complex128 autograd reference
+        Aref = A_rm.double().clone().requires_grad_(True)
+        r = torch.as_tensor(antv, device=dev).requires_grad_(True)
+        shat = geom.shat[:ns, :3]
+        u = r @ shat.T
+        ii, jj = torch.as_tensor(i, device=dev), torch.as_tensor(j, device=dev)
+        loss = 0
+        for f, nu in enumerate(freqs):
+            E = torch.exp(2j * math.pi * u * (nu / 2.99792458e8))
+            M = (E.conj() * Aref[f][None]) @ E.T
+            Vf = M[ii, jj]
+            loss = loss + torch.sum(G[:, f].real * Vf.real + G[:, f].imag * Vf.imag)
+        loss.backward()
+        ref = (Aref.grad, r.grad)
+    else:
+        ref = res.get("fp32")
+        out["ref"] = "fp32 kernels"
+    for name, (dA, dr) in res.items():
+        out["dA_relmax_" + name] = ((dA - ref[0]).abs().max() / ref[0].abs().max()).item()
+        if need_r:
+            out["dr_relmax_" + name] = ((dr - ref[1]).abs().max() / ref[1].abs().max()).item()
+    return out
+
+
 if __name__ == "__main__":
     cases = [(40, 128, 2, 1.0, False), (130, 640, 3, 1.0, False), (350, 4096, 2, 2.0, False),
              (350, 98304, 64, 1.0, True)]
@@ -107,7 +171,26 @@ if __name__ == "__main__":
         # accumulation-length study: coherent sums (tiny array) and random ones
         cases = [(350, 98304, 4, 1.0, False, 0, ext, um) for ext in (300.0, 2.0)
                  for um in (8192, 2048, 512, 128)]
+    if len(sys.argv) > 1 and sys.argv[1] == "time":
+        cases = [(350, 98304, 64, 1.0, True)]
+    if len(sys.argv) > 1 and sys.argv[1] == "prof":
+        cases = [(350, 98304, 16, 1.0, False)]
+    if len(sys.argv) > 1 and sys.argv[1] == "all":
+        cases = cases + [(350, 98304, 4, 1.0, False, 0, ext, 8192) for ext in (300.0, 2.0)]
     res = []
+    if len(sys.argv) > 1 and sys.argv[1] == "bwd":
+        for c in [(40, 128, 2, True), (130, 640, 3, True), (130, 640, 3, False),
+                  (350, 4096, 2, True), (350, 4096, 2, False),
+                  (350, 98304, 64, True, 0, True), (350, 98304, 64, False, 0, True)]:
+            try:
+                r = run_bwd(*c)
+            except Exception as e:  # noqa: BLE001
+                import traceback
+                r = dict(case=list(c), error=repr(e), tb=traceback.format_exc()[-1500:])
+            print(json.dumps(r), flush=True)
+            if "error" in r:
+                break
+        sys.exit(0)
     for c in cases:
         try:
             r = run(*c)

@@ -235,6 +235,73 @@ def antfringe_fwd(sfx, A, shat, antv, freqs, units, nunits, tile_ant, tile_bl, t
                 vpart[u, e[sl] >> 1, :nfreq, 1] = V.imag.to(vpart.dtype)
 
 
+def tcfringe_fwd(sfx, Acm, ascale, shat, antv, freqs, units, nunits, items, nitems, pair_bl, ldp, na,
+                 nbl, nfreq, S, conj, vpart):
+    """Contract of b200rime_tcfringe_fwd_f32: every (first i, second j) pair of an item with a
+    baseline in pair_bl is summed once; ascale only conditions the float16 operands."""
+    M = _lib.TC_ROWS
+    s = float(ascale[0])
+    assert s > 0 and math.log2(s) == round(math.log2(s)), "ascale must be a power of two"
+    amax = float(Acm.abs().max())
+    assert amax == 0 or 2.0 ** 14 <= amax * s < 2.0 ** 15
+    assert Acm.shape[1] == S and Acm.is_contiguous()
+    Af = Acm[:nfreq].double()
+    seen = torch.zeros(nbl, dtype=torch.int32)
+    for u in range(nunits):
+        _, s0, s1, _ = [int(v) for v in units[u]]
+        E = _ant_E(antv, shat[s0:s1], freqs[:nfreq], conj)
+        vpart[u, :, nfreq:] = 0
+        for n in range(nitems):
+            i0, j0, N, _ = [int(v) for v in items[n]]
+            assert N % 32 == 0 and 0 < N <= _lib.TC_COLS_MAX and j0 % 32 == 0
+            sub = pair_bl[i0:min(i0 + M, ldp), j0:j0 + N]
+            xs, ys = torch.where(sub >= 0)
+            e = sub[xs, ys].long()
+            ax, ay = xs + i0, ys + j0
+            assert (ax < na).all() and (ay < na).all()
+            if u == 0:
+                seen[e >> 1] += 1
+            for c0 in range(0, len(e), 256):                      # bounded temporaries
+                sl = slice(c0, c0 + 256)
+                V = (E[ax[sl]].conj() * E[ay[sl]] * Af[None, :, s0:s1]).sum(-1)
+                V = torch.where((e[sl] & 1).bool()[:, None], V.conj(), V)
+                vpart[u, e[sl] >> 1, :nfreq, 0] = V.real.to(vpart.dtype)
+                vpart[u, e[sl] >> 1, :nfreq, 1] = V.imag.to(vpart.dtype)
+    assert nunits == 0 or bool((seen == 1).all()), "every baseline needs exactly one owner"
+
+
+def tcfringe_bwd(sfx, Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, na, nm_pad, nfreq, S,
+                 conj, lower_only, dAcm, drpart):
+    """Contract of b200rime_tcfringe_bwd_f32 (operand layout decoded back to the dense matrix)."""
+    M = _lib.TC_ROWS
+    nt, nfp = Hq.shape[0], Hq.shape[1]
+    assert Hq.shape[2:] == (nitem, nm_pad // 16, 4, 16, 2, 8, 8) and Hq.dtype == torch.float16
+    assert nitem == -(-na // M) and nm_pad % 16 == 0 and na <= nm_pad <= 512
+    # (nt,nfp,item,mst,4,rg,kg,r8,k8) -> (nt,nfp,4,item,rg,r8,mst,kg,k8) -> (nt,nfp,4,a,m)
+    Q = Hq.permute(0, 1, 4, 2, 5, 7, 3, 6, 8).reshape(nt, nfp, 4, nitem * M, nm_pad).double()
+    sc = float(hscale[0])
+    H = torch.complex(Q[:, :, 0] + Q[:, :, 1], Q[:, :, 2] + Q[:, :, 3]) / sc     # (nt, f, a, m)
+    sgn = -1.0 if conj else 1.0
+    antp = torch.zeros(nitem * M, 4, dtype=torch.float64)
+    antp[:na] = antv[:na].double()
+    for u in range(nunits):
+        t, s0, s1, _ = [int(v) for v in units[u]]
+        E = _ant_E(antp, shat[s0:s1], freqs[:nfreq], conj)                      # (apad, nf, ns)
+        Ht = H[t, :nfreq]
+        if lower_only:      # item ib stops after its own antennas
+            a_blk = torch.arange(nitem * M) // M
+            Ht = Ht * (torch.arange(nm_pad)[None, :] < (a_blk[:, None] + 1) * M)[None]
+        y = torch.einsum('fam,mfs->afs', Ht, E[:nm_pad])
+        p = E.conj() * y
+        if dAcm is not None:
+            half = 0.5 * p.real.reshape(nitem, 2, M // 2, nfreq, s1 - s0).sum(2)   # (item, h, f, s)
+            dAcm[:, :nfreq, s0:s1] = half.reshape(nitem * 2, nfreq, s1 - s0).to(dAcm.dtype)
+        if drpart is not None:
+            w = p.imag * (Acm[:nfreq, s0:s1].double() * freqs.double()[:nfreq, None])[None]
+            g = torch.einsum('afs,sc->fac', w, shat[s0:s1, :3].double())
+            drpart[u, :nfreq, 0, :, :3] = (sgn * 2 * math.pi / C * g).to(drpart.dtype)
+
+
 def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na, na_pad, nm_pad, nfreq, S, conj,
                   dApart, drpart):
     assert na_pad - _lib.ANT_TILE < na <= na_pad
@@ -316,6 +383,7 @@ _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
               gather_times=gather_times,
               build_airy=build_airy, build_airy_bwd=build_airy_bwd,
               antfringe_fwd=antfringe_fwd, antfringe_bwd=antfringe_bwd,
+              tcfringe_fwd=tcfringe_fwd, tcfringe_bwd=tcfringe_bwd,
               apply_cal=apply_cal, apply_cal_bwd_gains=apply_cal_bwd_gains)
 
 

@@ -413,6 +413,93 @@ def test_c3_full_size_subset_and_gradients():
     assert float(rime.sky.params.grad[..., mask].abs().max()) == 0.0
 
 
+def _oracle_grad_subset(rime, bl_sel, f_idx, G_sub, kind='interp'):
+    """fp64 oracle V and autograd gradients (sky params, beam params, antenna positions) of a
+    workloads.pixel_interp model restricted to baselines bl_sel and channels f_idx, for the
+    cotangent G_sub (1, 1, len(bl_sel), Nt, len(f_idx)) -- exact gradients of a loss whose
+    cotangent vanishes elsewhere."""
+    zenaz = [(za[0].cpu().double(), za[1].cpu().double()) for za in workloads.zenaz_of(rime)]
+    f_idx = torch.as_tensor(f_idx)
+    freqs = rime.array.freqs.detach().cpu().double()[f_idx]
+    bls = [rime.sim_bls[i] for i in bl_sel]
+    antvecs = rime.array.antvecs.detach().cpu().double().requires_grad_(True)
+    sp = rime.sky.params.detach().cpu().double()[:, :, f_idx].requires_grad_(True)
+    bp = rime.beam.params.detach().cpu().double()[:, :, :, f_idx].requires_grad_(True)
+    blvecs = orc.get_blvecs(antvecs, rime.array.ants, bls)
+    bmap = orc.pixel_response_forward(bp, powerbeam=True)
+    tg, pg = rime.beam.R.theta_grid.cpu(), rime.beam.R.phi_grid.cpu()
+
+    def beam_fn(z, a):
+        inds, wgts = orc.rect_interp_weights(tg, pg, z, a, 'linear')
+        return orc.interp_map(bmap, inds, wgts)
+
+    Vo = orc.rime_forward(sp * float(rime.sky.px_area), zenaz, beam_fn, bls, blvecs, freqs,
+                          fov=rime.beam.fov, bl_chunk=4)
+    oc.real_loss(Vo, G_sub).backward()
+    return Vo.detach(), sp.grad, bp.grad, antvecs.grad
+
+
+@pytest.mark.parametrize("route", ["tc", "fp32"])
+def test_c3_full_size_all_pairs_factorised_vs_oracle(route):
+    """BASELINE config 3 exactly as benchmarked -- HERA-350, all 61,075 cross baselines,
+    nside-128 PixelSky (98 k sources above the horizon), rect-interpolated PixelBeam, 1024
+    channels, 1 time, float32 -- through the antenna-factorised kernels (route 'tc': tensor-core
+    forward; 'fp32': FP32-pipe forward), against the fp64 oracle:
+      * V on 16 baselines (shortest, longest, outriggers, random) x 64 channels x all sources;
+      * gradients to sky, beam map and antenna positions for a cotangent that is non-zero only on
+        8 baselines x 32 channels, for which the oracle's autograd gives the exact answer."""
+    if DOUBLE:
+        pytest.skip("full size needs the GPU")
+    os.environ["B200RIME_TC"] = "1" if route == "tc" else "0"
+    try:
+        rime = workloads.pixel_interp(128, 1024, 1, DEV, torch.float32, antpos_param=True)
+        dev = torch.device(DEV, torch.cuda.current_device())
+        assert rime._ant_tiling(dev) is not None, "C3 must run on the antenna-factorised kernels"
+        assert (rime._tc_tiling(dev) is not None) == (route == "tc")
+        nbl = len(rime.sim_bls)
+        assert nbl == 61075
+        V = rime().data
+        assert V.shape == (1, 1, nbl, 1, 1024)
+        blen = rime.sim_blvecs.detach().norm(dim=1).cpu().numpy()
+        order = np.argsort(blen)
+        rng = np.random.default_rng(5)
+        bl_sel = sorted(set(order[:3].tolist() + order[-3:].tolist()
+                            + rng.choice(nbl, 10, replace=False).tolist()))
+        f_sel = slice(0, 1024, 16)
+        Vo = _oracle_of_workload(rime, 'interp', bl_sel, f_sel)
+        tag = "c3_full_allpairs/%s" % route
+        # max-norm over the visibility tensor (SURVEY 8c): the subset holds the shortest baselines,
+        # whose visibilities are the largest of the tensor
+        scale = float(V.abs().max())
+        errV = float((V[:, :, bl_sel][..., f_sel].cpu().to(torch.complex128) - Vo).abs().max()) / scale
+        ERRLOG[tag + "/V"] = errV
+        assert errV < 1e-5
+
+        # sparse cotangent -> exact oracle gradients
+        gb = sorted(set(order[:2].tolist() + order[-2:].tolist()
+                        + rng.choice(nbl, 4, replace=False).tolist()))
+        gf = list(range(7, 1024, 32))
+        gen = torch.Generator().manual_seed(11)
+        G_sub = torch.complex(torch.randn(1, 1, len(gb), 1, len(gf), generator=gen, dtype=torch.float64),
+                              torch.randn(1, 1, len(gb), 1, len(gf), generator=gen, dtype=torch.float64))
+        G = torch.zeros(V.shape, dtype=torch.complex64, device=V.device)
+        gbt, gft = torch.as_tensor(gb, device=V.device), torch.as_tensor(gf, device=V.device)
+        G[0, 0, gbt[:, None], 0, gft[None, :]] = G_sub[0, 0, :, 0].to(V.device, torch.complex64)
+        torch.sum(G.real * V.real + G.imag * V.imag).backward()
+        Vo2, dsp, dbp, dant = _oracle_grad_subset(rime, gb, gf, G_sub)
+        assert relmax(V[:, :, gb][..., gf], Vo2, tag + "/V_gradsubset") < 1e-5 * scale / float(Vo2.abs().max())
+        gs = rime.sky.params.grad
+        assert relmax(gs[:, :, gf], dsp, tag + "/dsky") < 5e-5
+        assert relmax(rime.beam.params.grad[:, :, :, gf], dbp, tag + "/dbeam") < 5e-5
+        assert relmax(rime.array.antvecs.grad, dant, tag + "/dantvecs") < 5e-5
+        # channels without cotangent receive exactly zero
+        mask = torch.ones(1024, dtype=torch.bool, device=V.device)
+        mask[gft] = False
+        assert float(gs[:, :, mask].abs().max()) == 0.0
+    finally:
+        os.environ.pop("B200RIME_TC", None)
+
+
 def test_gradients_small_c3_vs_oracle_autograd():
     """Gradients to sky, beam map and antenna positions of a C3-shaped model small enough for
     the oracle's autograd (nside 8, HERA-37, 48 freqs, 2 times), float32 and float64."""

@@ -238,6 +238,7 @@ def test_golden_cases_through_antenna_factorised_path(name, monkeypatch):
     kernels replaced by their torch restatement."""
     monkeypatch.setattr(ops, "ANT_FWD_MIN_FILL", 0.0)
     monkeypatch.setattr(ops, "ANT_BWD_MIN_FILL", 0.0)
+    monkeypatch.setenv("B200RIME_TC", "0")
     with emulated_kernels() as calls:
         vd, grads, g, gkeys = mc.run_case(name, 'cpu', torch.float32)
     assert "antfringe_fwd" in calls and "antfringe_bwd" in calls
@@ -246,4 +247,53 @@ def test_golden_cases_through_antenna_factorised_path(name, monkeypatch):
     for k, gk in gkeys.items():
         if gk == "grad_beam" and name == "rime_point_airy":
             continue        # truncated-gradient convention, covered by the float64 case
+        assert relmax(grads[k], g[gk]) < 2e-5, (k, gk)
+
+
+def test_tensor_core_item_tables():
+    """ops.TcTiling: every baseline sits in exactly one item cell (first antenna i <= second
+    antenna j, conjugate flag for baselines listed the other way round); items are 128 rows by
+    at most tc_cols_max() columns on 32-column boundaries; repeated pairs are refused."""
+    rng = np.random.default_rng(4)
+    M, NMAX = _lib.TC_ROWS, _lib.TC_COLS_MAX
+    for na in (37, 130, 350):
+        ii, jj = np.triu_indices(na, k=0)
+        flip = rng.random(len(ii)) < 0.4
+        i, j = np.where(flip, jj, ii), np.where(flip, ii, jj)
+        perm = rng.permutation(len(i))
+        i, j = i[perm], j[perm]
+        tc = ops.TcTiling(i, j, na, 'cpu')
+        assert tc.unique and tc.ldp % 32 == 0 and tc.ldp >= na
+        pair, items = tc.pair_bl.numpy(), tc.items.numpy()
+        seen = np.zeros(len(i), dtype=int)
+        for i0, j0, n, _ in items:
+            assert i0 % M == 0 and j0 % 32 == 0 and n % 32 == 0 and 0 < n <= NMAX
+            assert j0 + n <= tc.ldp
+            sub = pair[i0:i0 + M, j0:j0 + n]
+            xs, ys = np.nonzero(sub >= 0)
+            e = sub[xs, ys]
+            bl, cj = e >> 1, e & 1
+            seen[bl] += 1
+            assert (np.where(cj == 1, j[bl], i[bl]) == xs + i0).all()
+            assert (np.where(cj == 1, i[bl], j[bl]) == ys + j0).all()
+        assert (seen == 1).all()
+        assert abs(tc.fill - len(i) / sum(M * int(n) for _, _, n, _ in items)) < 1e-12
+    assert not ops.TcTiling([0, 1, 5], [1, 0, 7], 8, 'cpu').unique
+    assert not ops.TcTiling(np.arange(0, 100), np.arange(100, 200), 200, 'cpu').usable
+
+
+@pytest.mark.parametrize("name", ["rime_pixel_interp", "rime_4pol"])
+def test_golden_cases_through_tensor_core_route(name, monkeypatch):
+    """Host side of the tensor-core forward route (item tables, operand scale, unit partials)
+    against the reference's golden vectors, with the kernels replaced by their torch
+    restatement."""
+    monkeypatch.setattr(ops, "ANT_FWD_MIN_FILL", 0.0)
+    monkeypatch.setattr(ops, "ANT_BWD_MIN_FILL", 0.0)
+    monkeypatch.setattr(ops, "TC_MIN_FILL", 0.0)
+    with emulated_kernels() as calls:
+        vd, grads, g, gkeys = mc.run_case(name, 'cpu', torch.float32)
+    assert "tcfringe_fwd" in calls and "antfringe_fwd" not in calls
+    assert "tcfringe_bwd" in calls and "antfringe_bwd" not in calls
+    assert relmax(vd.data, g["vis"]) < 5e-6
+    for k, gk in gkeys.items():
         assert relmax(grads[k], g[gk]) < 2e-5, (k, gk)
