@@ -56,7 +56,7 @@ _ANT_SIGS = {
     "antfringe_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _L, _I, _P, _P],
     "antfringe_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _I, _P, _P, _P],
     "tcfringe_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _I, _P, _P],
-    "tcfringe_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _I, _I, _P, _P, _P],
+    "tcfringe_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _L, _I, _P, _P, _P],
 }
 for _name, _sig in _ANT_SIGS.items():        # float32 only
     _fn = getattr(lib, "b200rime_%s_f32" % _name)

@@ -523,8 +523,10 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
 // form p and reduce: dL/dA over the thread's own columns (one float per source, written
 // channel-major, partial per (item, column half)), dL/dr over the 32 sources of the warp with a
 // transposed shuffle reduction (lane <-> antenna), accumulated over the tiles of the unit.
-//   lower_only: H holds the doubled lower triangle (a > m; enough for dL/dA) and item ib stops
-//   after its own antennas.
+//   mrange [nitem][2]: stages of 16 partner antennas [lo, hi) that hold cotangent entries for the
+//   item.  When only dL/dA is wanted H is the doubled lower triangle (a > m) and item ib stops
+//   after its own antennas; a baseline group that covers only some antenna blocks skips the
+//   stages it leaves empty.
 //   dAcm   [nitem * 2][Nfp][S]                 partial dL/dA, channel-major (sum over axis 0)
 //   drpart [nunits][Nfp][4][nitem * 128][4]    partial dL/dr (float32; sum over the first three)
 // -------------------------------------------------------------------------------------
@@ -581,9 +583,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restrict__ hscale,
                      const float* __restrict__ Acm, const double* __restrict__ shat,
                      const double* __restrict__ antv, const double* __restrict__ freqs,
-                     const int4* __restrict__ units, int nitem, int na, int nm_pad, int nfreq,
-                     int nfp, long long S, double sgn_over_c, int need_a, int need_r,
-                     int lower_only, float* __restrict__ dAcm, float* __restrict__ drpart) {
+                     const int4* __restrict__ units, int nitem, int na, int nm_pad,
+                     const int2* __restrict__ mrange, int nfreq, int nfp, long long S,
+                     double sgn_over_c, int need_a, int need_r, float* __restrict__ dAcm,
+                     float* __restrict__ drpart) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ai = blockIdx.y / nfreq, k = blockIdx.y % nfreq;
@@ -593,9 +596,10 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     // sums, and the epilogue needs no column mask (the MMAs are not the bottleneck)
     const int N = TC_NMAX;
     const int nmst_all = nm_pad / TC_KS;
-    const int nmst = lower_only ? min(nmst_all, (ai + 1) * (TC_M / TC_KS)) : nmst_all;
+    const int2 mr = mrange[ai];
+    const int mlo = max(0, mr.x), nmst = min(nmst_all, mr.y) - mlo;
     const int ntile = (un.z - un.y + TC_M - 1) / TC_M;
-    if (ntile <= 0 || N <= 0) return;
+    if (ntile <= 0 || nmst <= 0) return;        // nothing to add: dAcm / drpart were zeroed
     const int nct = (nmst + TC_FLUSH - 1) / TC_FLUSH;                 // chains per source tile
     const int nchain = ntile * nct;
 
@@ -648,7 +652,7 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
         const int pw = warp - TC_ACC_WARPS;
         const int r = 32 * (pw & 3) + lane, hh = pw >> 2;
         const int roff = (r >> 3) * 256 + hh * 128 + (r & 7) * 16;
-        const unsigned char* Hbase = Hq + ((((size_t)un.x * nfp + k) * nitem + ai) * (size_t)nmst_all) *
+        const unsigned char* Hbase = Hq + ((((size_t)un.x * nfp + k) * nitem + ai) * (size_t)nmst_all + mlo) *
                                               TcBwdSmem::H_BYTES;
         long long g = 0;
         for (int tile = 0; tile < ntile; ++tile) {
@@ -673,7 +677,7 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
                     }
                 }
                 float c[8], sn[8];
-                const double4* pm = pos + ms * TC_KS + hh * 8;
+                const double4* pm = pos + (mlo + ms) * TC_KS + hh * 8;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const double4 p = pm[e];
@@ -848,8 +852,8 @@ int launch_tc_fwd(const float* Acm, const float* ascale, const double* shat, con
 
 int launch_tc_bwd(const void* Hq, const float* hscale, const float* Acm, const double* shat,
                   const double* antv, const double* freqs, const int* units, int nunits, int nitem,
-                  int na, int nm_pad, int nfreq, long long S, int conj, int lower_only, float* dAcm,
-                  float* drpart, cudaStream_t st) {
+                  int na, int nm_pad, const int* mrange, int nfreq, long long S, int conj,
+                  float* dAcm, float* drpart, cudaStream_t st) {
     if (nunits <= 0 || nitem <= 0 || nfreq <= 0) return 0;
     if (S % SRC_PAD) return set_error("tcfringe_bwd: S must be a multiple of 128");
     if (nm_pad % TC_KS || nm_pad < na || nm_pad > TcBwdSmem::POS_MAX || nitem * TC_M > TcBwdSmem::POS_MAX ||
@@ -873,8 +877,9 @@ int launch_tc_bwd(const void* Hq, const float* hscale, const float* Acm, const d
     dim3 grid(nunits, (unsigned)gy);
     tc_fringe_bwd_kernel<<<grid, TC_THREADS, TcBwdSmem::TOTAL, st>>>(
         static_cast<const unsigned char*>(Hq), hscale, Acm, shat, antv, freqs,
-        reinterpret_cast<const int4*>(units), nitem, na, nm_pad, nfreq, nfp, S,
-        (conj ? -1.0 : 1.0) / C_LIGHT, dAcm != nullptr, drpart != nullptr, lower_only, dAcm, drpart);
+        reinterpret_cast<const int4*>(units), nitem, na, nm_pad,
+        reinterpret_cast<const int2*>(mrange), nfreq, nfp, S, (conj ? -1.0 : 1.0) / C_LIGHT,
+        dAcm != nullptr, drpart != nullptr, dAcm, drpart);
     return check_launch("tcfringe_bwd");
 }
 
@@ -885,10 +890,10 @@ extern "C" {
 int b200rime_tcfringe_bwd_f32(const void* Hq, const float* hscale, const float* Acm,
                               const double* shat, const double* antv, const double* freqs,
                               const int* units, int nunits, int nitem, int na, int nm_pad,
-                              int nfreq, long long S, int conj, int lower_only, float* dAcm,
+                              const int* mrange, int nfreq, long long S, int conj, float* dAcm,
                               float* drpart, void* stream) {
     return b200rime::launch_tc_bwd(Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, na,
-                                   nm_pad, nfreq, S, conj, lower_only, dAcm, drpart,
+                                   nm_pad, mrange, nfreq, S, conj, dAcm, drpart,
                                    (cudaStream_t)stream);
 }
 int b200rime_tcfringe_fwd_f32(const float* Acm, const float* ascale, const double* shat,

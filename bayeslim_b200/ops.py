@@ -437,18 +437,34 @@ def _blv4(blvecs, device):
     return b
 
 
-def _time_batches(ubeg, nt, bytes_per_unit):
-    """Sub-batches (t0, t1) of whole times whose unit partials fit the workspace budget, and the
-    largest number of units in one of them."""
-    max_units = min(max(1, VPART_BUDGET // bytes_per_unit), MAX_GRID_UNITS)
-    t0, batches = 0, []
+def _unit_batches(ubeg, nt, bytes_per_unit):
+    """Launch plan whose unit partials fit the workspace budget (and the grid limit):
+    [(t0, t1, u0, u1, accumulate)] -- whole times t0..t1 with units u0..u1 where they fit; a time
+    with more units than the budget allows is split into several launches of that one time, each
+    reduced into the output with accumulate = 1 after the first.  Also returns the largest
+    number of units in one launch."""
+    max_units = min(max(1, VPART_BUDGET // max(bytes_per_unit, 1)), MAX_GRID_UNITS)
+    t0, plan = 0, []
     while t0 < nt:
+        n0 = ubeg[t0 + 1] - ubeg[t0]
+        if n0 > max_units:
+            for u in range(ubeg[t0], ubeg[t0 + 1], max_units):
+                plan.append((t0, t0 + 1, u, min(u + max_units, ubeg[t0 + 1]), int(u > ubeg[t0])))
+            t0 += 1
+            continue
         t1 = t0 + 1
         while t1 < nt and ubeg[t1 + 1] - ubeg[t0] <= max_units:
             t1 += 1
-        batches.append((t0, t1))
+        plan.append((t0, t1, ubeg[t0], ubeg[t1], 0))
         t0 = t1
-    return batches, max(ubeg[b] - ubeg[a] for a, b in batches)
+    return plan, max(u1 - u0 for _, _, u0, u1, _ in plan)
+
+
+def _batch_ubeg(ubeg, ta, tb, u0, u1, device):
+    """Unit offsets of the times ta..tb of a launch, relative to its first unit u0 (a split time
+    has the single range [0, u1 - u0))."""
+    rel = np.clip(np.asarray(ubeg[ta:tb + 1], dtype=np.int64), u0, u1) - u0
+    return torch.as_tensor(rel.astype(np.int32), device=device)
 
 
 class _FringeSum(torch.autograd.Function):
@@ -467,18 +483,17 @@ class _FringeSum(torch.autograd.Function):
         if nbl > 0 and nt > 0 and geom.S > 0:
             units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
             esize = 8 if sfx == "f32" else 16
-            batches, nu_max = _time_batches(ubeg, nt, nbl * nfp * esize)
+            batches, nu_max = _unit_batches(ubeg, nt, nbl * nfp * esize)
             vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=dtype, device=dev)
             Vr = torch.view_as_real(V)
-            for (ta, tb) in batches:
-                u0, u1 = ubeg[ta], ubeg[tb]
-                ub = torch.as_tensor(np.asarray(ubeg[ta:tb + 1], dtype=np.int32) - u0, device=dev)
+            for (ta, tb, u0, u1, accum) in batches:
+                ub = _batch_ubeg(ubeg, ta, tb, u0, u1, dev)
                 for p in range(nplane):
                     _call("fringe_sum_fwd", sfx, A[p], geom.shat, blv, freqs64,
                           units[u0:], u1 - u0, nbl, nfreq, geom.S, int(conj), int(uniform),
                           vpart)
                     _call("reduce_units", sfx, vpart, ub, tb - ta, nbl, nfreq,
-                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, 0)
+                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, accum)
         need_bl = ctx.needs_input_grad[1]
         ctx.save_for_backward(A if need_bl else None, blv, freqs64)
         ctx.meta = (geom, nfreq, int(conj), int(uniform), blvecs.dtype, blvecs.device, A.shape)
@@ -704,6 +719,26 @@ class TcTiling:
         self.auto = torch.as_tensor(np.nonzero(i == j)[0], device=dev)
         self.jgt = torch.as_tensor(np.nonzero(j > i)[0], device=dev)
         self.igt = torch.as_tensor(np.nonzero(i > j)[0], device=dev)
+        # stages of 16 partner antennas m that hold cotangent entries, per item of 128 antennas a
+        # [lo, hi): full matrix (both triangles) and doubled lower triangle (a > m).  A baseline
+        # group that covers only some antenna blocks skips the empty stages.
+        def stage_ranges(a_idx, m_idx):
+            out = np.zeros((self.nitem_bwd, 2), dtype=np.int32)
+            for ib in range(self.nitem_bwd):
+                sel = (a_idx // M) == ib
+                if sel.any():
+                    out[ib] = (m_idx[sel].min() // 16, m_idx[sel].max() // 16 + 1)
+            return out
+        both_a, both_m = np.concatenate([j, i]), np.concatenate([i, j])
+        self.mrange_full = torch.as_tensor(stage_ranges(both_a, both_m), device=dev)
+        self.mrange_lower = torch.as_tensor(stage_ranges(y, x), device=dev)
+        self.bwd_stages_full = int((self.mrange_full[:, 1] - self.mrange_full[:, 0]).sum())
+        self.bwd_stages_lower = int((self.mrange_lower[:, 1] - self.mrange_lower[:, 0]).sum())
+
+    def antv4(self, antvecs):
+        out = torch.zeros(self.apad, 4, dtype=torch.float64, device=self.items.device)
+        out[:self.na, :3] = antvecs.detach().to(out.device, torch.float64)[:self.na]
+        return out
 
     def cotangent_operand(self, G, nfp, lower_only=False):
         """G (nbl, nt, nf) complex64 -> (Hq, hscale): the Hermitian cotangent matrix
@@ -760,12 +795,13 @@ class _AntFringeSum(torch.autograd.Function):
         nplane, nchunk = A.shape[0], A.shape[1]
         kc = _lib.KC["f32"]
         nfp = nchunk * kc
-        nbl, nt = tiling.nbl, geom.nt
-        antv = tiling.antv4(antvecs)
+        plan = tiling if tiling is not None else tc
+        nbl, nt = plan.nbl, geom.nt
+        antv = plan.antv4(antvecs)
         V = torch.zeros(nplane, nbl, nt, nfreq, dtype=torch.complex64, device=dev)
         if nbl > 0 and nt > 0 and geom.S > 0:
             units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
-            batches, nu_max = _time_batches(ubeg, nt, nbl * nfp * 8)
+            batches, nu_max = _unit_batches(ubeg, nt, nbl * nfp * 8)
             # pairs outside the tiling keep their zero: every wanted pair has exactly one owner
             vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=torch.float32, device=dev)
             Vr = torch.view_as_real(V)
@@ -773,9 +809,8 @@ class _AntFringeSum(torch.autograd.Function):
                 # channel-major copy: a stage's 16 sky values become one contiguous TMA copy
                 ascale = tc_scale(A)
                 acm = A.permute(0, 1, 3, 2).reshape(nplane, nfp, A.shape[2]).contiguous()
-            for (ta, tb) in batches:
-                u0, u1 = ubeg[ta], ubeg[tb]
-                ub = torch.as_tensor(np.asarray(ubeg[ta:tb + 1], dtype=np.int32) - u0, device=dev)
+            for (ta, tb, u0, u1, accum) in batches:
+                ub = _batch_ubeg(ubeg, ta, tb, u0, u1, dev)
                 for p in range(nplane):
                     if tc is not None:
                         _call("tcfringe_fwd", "f32", acm[p], ascale[p:p + 1], geom.shat, antv,
@@ -786,7 +821,7 @@ class _AntFringeSum(torch.autograd.Function):
                               u1 - u0, tiling.tile_ant, tiling.tile_bl, tiling.tile_order,
                               tiling.ntile, nbl, nfreq, geom.S, int(conj), vpart)
                     _call("reduce_units", "f32", vpart, ub, tb - ta, nbl, nfreq,
-                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, 0)
+                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, accum)
         ctx.save_for_backward(A, antv, freqs64)
         ctx.meta = (geom, nfreq, int(conj), tiling, antvecs.dtype, antvecs.device, antvecs.shape,
                     tc)
@@ -797,7 +832,7 @@ class _AntFringeSum(torch.autograd.Function):
         A, antv, freqs64 = ctx.saved_tensors
         geom, nfreq, conj, tiling, adtype, adev, ashape_ant, tc = ctx.meta
         need_A, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if tc is not None and tc.bwd_usable:
+        if tc is not None and (tc.bwd_usable or tiling is None):
             dA, dr = _tc_backward(G, A, antv, geom, freqs64, nfreq, conj, tc, A.shape, need_A,
                                   need_r)
         else:
@@ -806,7 +841,8 @@ class _AntFringeSum(torch.autograd.Function):
         gant = None
         if need_r:
             gant = torch.zeros(ashape_ant, dtype=torch.float64, device=G.device)
-            gant[:tiling.na] = dr[:tiling.na]
+            na = (tiling if tiling is not None else tc).na
+            gant[:na] = dr[:na]
             gant = gant.to(device=adev, dtype=adtype)
         return dA, gant, None, None, None, None, None, None
 
@@ -881,8 +917,9 @@ def _tc_backward(G, A, antv, geom, freqs64, nfreq, conj, tc, ashape, need_A, nee
                 drpart = (torch.zeros(u1 - u0, nfp, 4, tc.apad, 4, dtype=torch.float32, device=dev)
                           if need_r else None)
                 _call("tcfringe_bwd", "f32", Hq, hscale, acm, geom.shat, antv, freqs64, un,
-                      u1 - u0, tc.nitem_bwd, tc.na, tc.nm_pad, nfreq, geom.S, conj,
-                      int(not need_r), dAcm, drpart)
+                      u1 - u0, tc.nitem_bwd, tc.na, tc.nm_pad,
+                      tc.mrange_full if need_r else tc.mrange_lower, nfreq, geom.S, conj,
+                      dAcm, drpart)
                 if need_r:
                     dr[:tc.na] += drpart.sum(dim=(0, 1, 2), dtype=torch.float64)[:tc.na, :3]
                 del Hq
@@ -894,8 +931,8 @@ def _tc_backward(G, A, antv, geom, freqs64, nfreq, conj, tc, ashape, need_A, nee
 def fringe_sum_ant(A, antvecs, tiling, geom, freqs64, nfreq, conj=False, tc=None):
     """Same sum as fringe_sum for the baselines (tiling.i, tiling.j) of antenna positions
     antvecs (Na, 3), through the antenna-factorised float32 kernels; gradients flow to A and
-    straight to antvecs.  tc (TcTiling of the same baseline list): the forward sum runs on the
-    tensor cores (tcgen05) instead of the FP32 pipes."""
+    straight to antvecs.  tc (TcTiling of the same baseline list): the sum and its adjoints run
+    on the tensor cores (tcgen05) instead of the FP32 pipes; tiling may then be None."""
     return _AntFringeSum.apply(A, antvecs, geom, freqs64, nfreq, conj, tiling, tc)
 
 

@@ -259,12 +259,7 @@ class RIME(utils.Module):
         if key not in self._ant_tilings:
             til = None
             try:
-                rows = getattr(self.array, '_ant_idx', None)
-                if rows is None:
-                    rows = {int(a): k for k, a in enumerate(self.array.ants)}
-                bls = self.sim_bls
-                i = [rows[int(b[0])] for b in bls]
-                j = [rows[int(b[1])] for b in bls]
+                i, j = self._antenna_rows()
                 til = ops.AntTiling(i, j, len(self.array.antvecs), dev)
                 if not til.usable:
                     til = None
@@ -273,27 +268,43 @@ class RIME(utils.Module):
             self._ant_tilings[key] = til
         return self._ant_tilings[key]
 
+    def _antenna_rows(self):
+        """Antenna row (into array.antvecs) of the first / second antenna of every baseline."""
+        rows = getattr(self.array, '_ant_idx', None)
+        if rows is None:
+            rows = {int(a): k for k, a in enumerate(self.array.ants)}
+        bls = self.sim_bls
+        return [rows[int(b[0])] for b in bls], [rows[int(b[1])] for b in bls]
+
     def _tc_tiling(self, dev):
-        """ops.TcTiling of the current baseline group (tensor-core forward kernel) when the
-        antenna-factorised route is taken, else None.  B200RIME_TC=0 keeps the FP32-pipe
-        forward kernel."""
-        if os.environ.get("B200RIME_TC", "1") == "0":
-            return None
-        til = self._ant_tiling(dev)
-        if til is None:
+        """ops.TcTiling of the current baseline group when the tensor-core kernels pay off (the
+        group fills its 128 x 128 antenna-pair items well enough), else None.  B200RIME_TC=0
+        keeps the FP32-pipe kernels."""
+        if os.environ.get("B200RIME_TC", "1") == "0" or os.environ.get("B200RIME_ANT", "1") == "0":
             return None
         key = (self._bl_key, dev)
         if key not in self._tc_tilings:
-            tc = ops.TcTiling(til.i.cpu().numpy(), til.j.cpu().numpy(), til.na, dev)
-            self._tc_tilings[key] = tc if tc.usable else None
+            tc = None
+            try:
+                i, j = self._antenna_rows()
+                tc = ops.TcTiling(i, j, len(self.array.antvecs), dev)
+                if not (tc.usable and tc.bwd_usable):
+                    tc = None
+            except (KeyError, TypeError, AttributeError, IndexError):
+                tc = None
+            self._tc_tilings[key] = tc
         return self._tc_tilings[key]
 
     def _fringe(self, A, blvecs, rec, f64, nfreq, uniform, dev):
-        """Fringe sum of tiled planes A over all baselines of the current group."""
-        til = self._ant_tiling(dev) if A.dtype == torch.float32 else None
-        if til is not None:
-            return ops.fringe_sum_ant(A, self.array.antvecs.to(dev), til, rec.geom, f64, nfreq,
-                                      conj=False, tc=self._tc_tiling(dev))
+        """Fringe sum of tiled planes A over all baselines of the current group: tensor-core
+        kernels when the group is dense in antenna pairs, else the FP32 antenna-factorised
+        kernels, else the baseline-owned kernels (always for float64)."""
+        if A.dtype == torch.float32:
+            tc = self._tc_tiling(dev)
+            til = self._ant_tiling(dev)
+            if tc is not None or til is not None:
+                return ops.fringe_sum_ant(A, self.array.antvecs.to(dev), til, rec.geom, f64, nfreq,
+                                          conj=False, tc=tc)
         return ops.fringe_sum(A, blvecs, rec.geom, f64, nfreq, conj=False, uniform=uniform)
 
     def _geometry(self, sky_comp, dev):

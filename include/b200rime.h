@@ -298,13 +298,15 @@ int b200rime_tcfringe_fwd_f32(const float* Acm, const float* ascale, const doubl
  * rime_model.py:429 w.r.t. psky and of telescope_model.py:356 w.r.t. the antenna positions).
  *   Hq      float16 [nt][Nfp][nitem][nm_pad/16][4][16][2][8][8]: the Hermitian cotangent matrix
  *           (as for antfringe_bwd: H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m),
- *           2 Re G_b for autos; lower_only != 0: the doubled lower triangle a > m, enough for
- *           dL/dA), times hscale, split into float16 hi + lo, as UMMA K-major B operands:
+ *           2 Re G_b for autos; when only dL/dA is wanted the doubled lower triangle a > m is
+ *           enough), times hscale, split into float16 hi + lo, as UMMA K-major B operands:
  *           [item of 128 antennas a][stage of 16 m][re_hi | re_lo | im_hi | im_lo]
  *           [a / 8][m / 8][a % 8][m % 8]
  *   hscale  float [1]   power of two that brings max |H| into [2^14, 2^15)
  *   Acm     float [Nfp][S] channel-major perceived sky (only for drpart, else NULL)
  *   nitem = ceil(na / 128), nm_pad = na rounded up to 16, na <= 512
+ *   mrange  int32 [nitem][2]   stages of 16 partner antennas [lo, hi) that hold entries of H for
+ *           the item (all stages: {0, nm_pad / 16}; lower triangle: item ib ends at 8 (ib + 1))
  *   dAcm    float [nitem * 2][Nfp][S]   partial dL/dA, channel-major; ZERO before the call
  *           (padding sources and channels are not written); sum over the first axis; or NULL
  *   drpart  float [nunits][Nfp][4][nitem * 128][4]   partial dL/dr; sum over the first three
@@ -312,7 +314,7 @@ int b200rime_tcfringe_fwd_f32(const float* Acm, const float* ascale, const doubl
 int b200rime_tcfringe_bwd_f32(const void* Hq, const float* hscale, const float* Acm,
                               const double* shat, const double* antv, const double* freqs,
                               const int* units, int nunits, int nitem, int na, int nm_pad,
-                              int nfreq, long long S, int conj, int lower_only, float* dAcm,
+                              const int* mrange, int nfreq, long long S, int conj, float* dAcm,
                               float* drpart, b200rime_stream_t stream);
 
 /* ---- gain application --------------------------------------

@@ -1,13 +1,18 @@
 #!/bin/bash
+# round-2 evidence: smoke, bench lines (C3 default, forward-only, C2, C1, C4, C5 at N=1),
+# reference arms, then the ncu launch list of the default bench command
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?"; tail -n 15 gpurun_out/pytest_gpu.log
-python scripts/prof_case.py 8192 > gpurun_out/prof_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fringe_sum -s 3 -c 3 \
-    -o gpurun_out/prof_fringe python scripts/prof_case.py 8192 > gpurun_out/ncu_full.log 2>&1
-echo "ncu full exit $?"; tail -n 5 gpurun_out/ncu_full.log
-python scripts/prof_case.py 8192 > gpurun_out/prof_plain2.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file gpurun_out/launches.csv python scripts/prof_case.py 8192 > gpurun_out/ncu_list.log 2>&1
-echo "ncu list exit $?"; tail -n 3 gpurun_out/ncu_list.log
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/nvsmi.txt
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+run() { # name, args...
+  n=$1; shift
+  timeout 1500 python bench.py "$@" > gpurun_out/bench_$n.json 2> gpurun_out/bench_$n.err
+  echo "bench $n rc=$? $(head -c 300 gpurun_out/bench_$n.json)"
+}
+run c3 --steps 3 --warmup 3
+run c3_fwd --steps 3 --warmup 3 --pass fwd --no-cpu-baseline
+run c2 --workload c2 --steps 3 --warmup 3
+run c1 --workload c1 --steps 5 --warmup 3
+B200RIME_TC=0 timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_c3_fp32.json 2> gpurun_out/bench_c3_fp32.err; echo "bench c3_fp32 rc=$?"
+run ref_c3 --impl reference --steps 5 --warmup 1

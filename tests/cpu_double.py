@@ -270,8 +270,8 @@ def tcfringe_fwd(sfx, Acm, ascale, shat, antv, freqs, units, nunits, items, nite
     assert nunits == 0 or bool((seen == 1).all()), "every baseline needs exactly one owner"
 
 
-def tcfringe_bwd(sfx, Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, na, nm_pad, nfreq, S,
-                 conj, lower_only, dAcm, drpart):
+def tcfringe_bwd(sfx, Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, na, nm_pad, mrange,
+                 nfreq, S, conj, dAcm, drpart):
     """Contract of b200rime_tcfringe_bwd_f32 (operand layout decoded back to the dense matrix)."""
     M = _lib.TC_ROWS
     nt, nfp = Hq.shape[0], Hq.shape[1]
@@ -288,9 +288,11 @@ def tcfringe_bwd(sfx, Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, 
         t, s0, s1, _ = [int(v) for v in units[u]]
         E = _ant_E(antp, shat[s0:s1], freqs[:nfreq], conj)                      # (apad, nf, ns)
         Ht = H[t, :nfreq]
-        if lower_only:      # item ib stops after its own antennas
-            a_blk = torch.arange(nitem * M) // M
-            Ht = Ht * (torch.arange(nm_pad)[None, :] < (a_blk[:, None] + 1) * M)[None]
+        # only the stages [lo, hi) of every item are read
+        a_blk = torch.arange(nitem * M) // M
+        mst = torch.arange(nm_pad) // 16
+        lo, hi = mrange[a_blk, 0].long(), mrange[a_blk, 1].long()
+        Ht = Ht * ((mst[None, :] >= lo[:, None]) & (mst[None, :] < hi[:, None]))[None]
         y = torch.einsum('fam,mfs->afs', Ht, E[:nm_pad])
         p = E.conj() * y
         if dAcm is not None:

@@ -297,3 +297,19 @@ def test_golden_cases_through_tensor_core_route(name, monkeypatch):
     assert relmax(vd.data, g["vis"]) < 5e-6
     for k, gk in gkeys.items():
         assert relmax(grads[k], g[gk]) < 2e-5, (k, gk)
+
+
+def test_unit_workspace_budget_splits_a_single_time(monkeypatch):
+    """ops._unit_batches: a time whose unit partials exceed the workspace budget is processed in
+    several launches accumulated into the output (same visibilities as one launch)."""
+    plan, nmax = ops._unit_batches([0, 5, 7, 20], 3, ops.VPART_BUDGET // 6)
+    assert nmax <= 6 and [p[:2] for p in plan] == [(0, 1), (1, 2), (2, 3), (2, 3), (2, 3)]
+    assert [p[4] for p in plan] == [0, 0, 0, 1, 1] and plan[-1][2:4] == (19, 20)
+    assert ops._batch_ubeg([0, 5, 7, 20], 2, 3, 13, 19, 'cpu').tolist() == [0, 6]
+    monkeypatch.setattr(ops, "UNIT_MAX_SRC", 64)
+    monkeypatch.setattr(ops, "UNIT_MIN_SRC", 64)
+    with emulated_kernels():
+        vd0, _, g, _ = mc.run_case("rime_pixel_interp", 'cpu', torch.float64)
+        monkeypatch.setattr(ops, "VPART_BUDGET", 1)        # one unit per launch
+        vd1, _, _, _ = mc.run_case("rime_pixel_interp", 'cpu', torch.float64)
+    assert relmax(vd1.data, vd0.data) < 1e-13 and relmax(vd1.data, g["vis"]) < 1e-10

@@ -8,8 +8,10 @@ layouts, skies and beams are generated from fixed seeds.
   C2  HERA-37, 10k point sources, 256 freqs, 60 times, grads to sky
   C3  HERA-350, HEALPix nside-128 PixelSky, rect-grid interpolated PixelBeam, 1024 freqs,
       grads to sky, beam (and optionally antenna positions)
-  C4  HERA-350, 4-pol Jones beams, PixelSky with Stokes I, Q, U (pixel_interp_pol; parity-test
-      case at reduced nside, not a bench line)
+  C4  HERA-350, 4-pol Jones beams, nside-256 PixelSky with Stokes I, Q, U, 1024 freqs
+      (pixel_interp_pol), time-sharded
+  C5  HERA-350, nside-256 PixelSky, 1024 freqs, full-night time axis in single-time minibatches x
+      two block-aligned baseline groups (pixel_interp(bl_groups=True, time_groups=True))
 """
 import itertools
 import math
@@ -97,10 +99,22 @@ def rect_airy_map(freqs, dtheta=1.0, dphi=1.0, D=14.0, dtype=torch.float32, devi
     return theta, phi, airy.to(dtype)
 
 
+def block_aligned_groups(ants, bls, block=128):
+    """Baseline groups aligned to the 128-antenna row blocks of the tensor-core items: group g
+    holds the pairs whose lower antenna row falls into... block 0 (group 0) or any later block
+    (group 1).  Each group then maps onto whole items (no antenna term is generated for a pair
+    the group does not own) and onto disjoint blocks of the cotangent matrix in the backward."""
+    row = {a: k for k, a in enumerate(ants)}
+    g0 = [b for b in bls if min(row[b[0]], row[b[1]]) < block]
+    g1 = [b for b in bls if min(row[b[0]], row[b[1]]) >= block]
+    return [g for g in (g0, g1) if g]
+
+
 def pixel_interp(nside, n_freq, n_time, device, dtype=torch.float32, n_bl=None, seed=0,
                  sky_param=True, beam_param=True, antpos_param=False, layout='hera350',
-                 dgrid=1.0):
-    """C3 family."""
+                 dgrid=1.0, bl_groups=False, time_groups=False):
+    """C3 family (bl_groups / time_groups: the C5 minibatch grid of block-aligned baseline
+    groups x single times)."""
     gen = torch.Generator(device='cpu').manual_seed(seed)
     freqs = torch.linspace(100e6, 200e6, n_freq, dtype=torch.float64, device=device)
     ants, vecs = hera350() if layout == 'hera350' else hera37()
@@ -126,6 +140,10 @@ def pixel_interp(nside, n_freq, n_time, device, dtype=torch.float32, n_bl=None, 
                                    powerbeam=True, fov=180, parameter=beam_param)
     tel = ba.telescope_model.TelescopeModel(LOCATION, device=device)
     times = np.linspace(2458148.15, 2458148.25, n_time)
+    if bl_groups:
+        sim_bls = block_aligned_groups(ants, sim_bls)
+    if time_groups:
+        times = [np.asarray([t]) for t in times]
     rime = ba.RIME(sky, tel, beam, array, sim_bls, times, freqs, device=device)
     return rime
 
@@ -187,11 +205,14 @@ def pixel_interp_pol(nside, n_freq, n_time, device, dtype=torch.float32, n_bl=No
 
 
 def count_evals(rime):
-    """source x baseline x freq x time evaluations of the current batch, sources counted after
-    the FOV cut.  Requires one forward to have populated the geometry cache."""
+    """source x baseline x freq x time evaluations of the CURRENT batch (time group x baseline
+    group), sources counted after the FOV cut.  Requires one forward of the batch
+    to have populated the geometry cache."""
+    times = tuple(float(t) for t in rime.sim_times)
     total = 0
-    for rec in rime._geom_cache.values():
-        total += sum(rec.geom.ns)
+    for key, rec in rime._geom_cache.items():
+        if key[2] == times:
+            total += sum(rec.geom.ns)
     return total * len(rime.sim_bls) * len(rime.array.freqs)
 
 
