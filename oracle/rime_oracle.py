@@ -511,8 +511,39 @@ def prod_and_sum(beam, cut_sky, bls, blvecs, zen, az, freqs, powerbeam=True,
     return torch.cat(out, dim=2)
 
 
+def pointing_offset(zen, az, theta_x=0.0, theta_y=0.0):
+    """(zen, az) [deg] at which the beam response is evaluated for a beam with a small-angle
+    pointing offset: beam_model.py:244-256 + pointing_offset :1631-1678 (unit vector
+    (sin t cos p, sin t sin p, cos t), rotation about x-hat by theta_x then about y-hat by
+    theta_y, each only when > 0 (`rotation`, :1514-1545), back to angles with new_phi in
+    [0, 2 pi)).  Non-differentiable (numpy), as in the reference."""
+    if not (theta_x > 0 or theta_y > 0):
+        return zen, az
+    t = np.asarray(torch.as_tensor(zen).detach().cpu().double()) * D2R
+    p = np.asarray(torch.as_tensor(az).detach().cpu().double()) * D2R
+    r = np.array([np.sin(t) * np.cos(p), np.sin(t) * np.sin(p), np.cos(t)])
+    if theta_x > 0:
+        c, s = math.cos(theta_x), math.sin(theta_x)
+        r = np.array([[1.0, 0, 0], [0, c, -s], [0, s, c]]) @ r
+    if theta_y > 0:
+        c, s = math.cos(theta_y), math.sin(theta_y)
+        r = np.array([[c, 0, s], [0, 1.0, 0], [-s, 0, c]]) @ r
+    nt = np.arccos(r[2])
+    xzero, yzero = np.isclose(r[0], 0), np.isclose(r[1], 0)
+    xneg, ypos = r[0] < 0, r[1] > 0
+    nphi = np.zeros_like(nt)
+    nphi[~xzero] = np.arctan(r[1][~xzero] / r[0][~xzero])
+    nphi[xneg & ypos] += np.pi
+    nphi[xneg & ~ypos] -= np.pi
+    nphi[xzero & yzero] = 0.0
+    nphi[xzero & ypos] = np.pi / 2
+    nphi[xzero & ~ypos] = -np.pi / 2
+    nphi = nphi % (2 * np.pi)
+    return torch.as_tensor(nt / D2R), torch.as_tensor(nphi / D2R)
+
+
 def rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=180.0, powerbeam=True,
-                 ant2beam=None, sim2data=None, bl_chunk=None):
+                 ant2beam=None, sim2data=None, bl_chunk=None, offset=(0.0, 0.0)):
     """The reference time loop (rime_model.py:326-368) for one sky component.
 
     sky      : (Nvec, Nvec, Nf, Npix) coherency / (1,1,Nf,Npix) Stokes-I tensor
@@ -526,7 +557,7 @@ def rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=180.0, powerbeam=T
         az = torch.as_tensor(az)
         cut = fov_cut(zen, fov)
         zc, ac = zen[cut], az[cut]
-        beam = beam_fn(zc, ac)
+        beam = beam_fn(*pointing_offset(zc, ac, *offset))     # the fringe keeps (zc, ac)
         cut_sky = sky.index_select(-1, cut)
         v = prod_and_sum(beam, cut_sky, bls, blvecs, zc, ac, freqs, powerbeam=powerbeam,
                          ant2beam=ant2beam, bl_chunk=bl_chunk)

@@ -215,6 +215,54 @@ def gold_rime_pixel_interp():
          grad_beam=beam.params.grad, grad_antvecs=array.antvecs.grad, fov=180.0)
 
 
+def gold_rime_pointing():
+    """Pointing offset (beam_model.py:244-256, 1631-1678): the pixel-interp case with the beam
+    tilted by (theta_x, theta_y) = (0.03, 0.05) rad, fov 150 deg so that the interpolation
+    stays inside the beam grid, and the Airy beam with the same offset; values and gradients."""
+    rng = np.random.default_rng(21)
+    freqs = torch.linspace(100e6, 200e6, 7)
+    times = np.linspace(2458148.15, 2458148.25, 2)
+    ants, vecs, array = hera_array(2, freqs, set_param=True)
+    bls = [(0, 1), (0, 2), (0, 3), (1, 5), (2, 6), (0, 6), (3, 4)]
+    ra, dec, px_area, sparams = healpix_sky(4, freqs, rng)
+    angs = torch.as_tensor(np.stack([ra, dec]))
+    offset = (0.03, 0.05)
+    out = {}
+    # interpolated pixel beam
+    sky = ba.sky_model.PixelSky(sparams.clone(), angs, px_area,
+                                R=ba.sky_model.PixelSkyResponse(freqs), parameter=True)
+    theta, phi, b_theta, b_phi, airy = rect_airy_beam(freqs, 5.0, 10.0)
+    R = ba.beam_model.PixelResponse(freqs, 'rect', interp_mode='linear', theta=b_theta, phi=b_phi,
+                                    theta_grid=theta, phi_grid=phi, freq_mode='channel',
+                                    powerbeam=True, realbeam=True, log=False)
+    bp = torch.as_tensor(airy[None, None, None, :, :]).clone()
+    beam = ba.beam_model.PixelBeam(bp.clone(), freqs, R=R, pol='e', powerbeam=True, fov=150,
+                                   parameter=True, offset=offset)
+    tel = ba.telescope_model.TelescopeModel(LOC)
+    rime = ba.rime_model.RIME(sky, tel, beam, array, bls, times, freqs)
+    zen_az = inject_geometry(rime, sky.name, ra, dec, rime.sim_times)
+    vd = rime()
+    G = cotangent(vd.data.shape, 121)
+    backward_with(vd.data, G)
+    out.update(vis_interp=vd.data, grad_sky_interp=sky.params.grad, grad_beam_interp=beam.params.grad,
+               grad_antvecs_interp=array.antvecs.grad.clone())
+    # Airy beam with the same offset
+    array.antvecs.grad = None
+    sky2 = ba.sky_model.PixelSky(sparams.clone(), angs, px_area,
+                                 R=ba.sky_model.PixelSkyResponse(freqs), parameter=True)
+    beam2 = ba.beam_model.PixelBeam(torch.ones(1, 1, 1, 1, 1) * 14.0, freqs,
+                                    R=ba.beam_model.AiryResponse(powerbeam=True), pol='e',
+                                    powerbeam=True, fov=150, parameter=False, offset=offset)
+    rime2 = ba.rime_model.RIME(sky2, tel, beam2, array, bls, times, freqs)
+    inject_geometry(rime2, sky2.name, ra, dec, rime2.sim_times)
+    vd2 = rime2()
+    backward_with(vd2.data, G)
+    out.update(vis_airy=vd2.data, grad_sky_airy=sky2.params.grad)
+    save("rime_pointing", antvecs=vecs, ants=ants, bls=bls, freqs=freqs, times=times, ra=ra,
+         dec=dec, zen_az=zen_az, sky_params=sparams, px_area=px_area, beam_params=bp,
+         theta_grid=theta, phi_grid=phi, G=G, fov=150.0, offset=np.asarray(offset), **out)
+
+
 def gold_rime_batched():
     """test_RIME analogue (tests/test_rime.py:29-51): minibatched == single shot, plus values.
     Also exercises a narrower FOV (fov=120) and quadratic interpolation."""
@@ -497,6 +545,7 @@ if __name__ == "__main__":
     gold_rect_interp()
     gold_rime_point_airy()
     gold_rime_pixel_interp()
+    gold_rime_pointing()
     gold_rime_batched()
     gold_rime_2pol()
     gold_rime_4pol()

@@ -74,6 +74,30 @@ def build_pixel_interp(g, device, dtype=torch.float64, params=("sky", "beam", "a
     return rime, dict(sky=sky.params, beam=beam.params, antvecs=array.antvecs)
 
 
+def build_pointing_interp(g, device, dtype=torch.float64):
+    rime, leaves = build_pixel_interp(g, device, dtype)
+    rime.beam.set_pointing_offset(*[float(x) for x in g["offset"]])
+    return rime, leaves
+
+
+def build_pointing_airy(g, device, dtype=torch.float64):
+    freqs = _t(g["freqs"], torch.float64, device)
+    ants, array = _array(g, freqs, device, dtype)
+    sky = ba.sky_model.PixelSky(_t(g["sky_params"], dtype, device),
+                                _t(np.stack([g["ra"], g["dec"]]), torch.float64, device),
+                                float(g["px_area"]),
+                                R=ba.sky_model.PixelSkyResponse(freqs.to(dtype), device=device),
+                                parameter=True)
+    beam = ba.beam_model.PixelBeam(torch.ones(1, 1, 1, 1, 1, dtype=dtype, device=device) * 14.0,
+                                   freqs, R=ba.beam_model.AiryResponse(powerbeam=True), pol='e',
+                                   powerbeam=True, fov=float(g["fov"]), parameter=False,
+                                   offset=tuple(float(x) for x in g["offset"]))
+    tel = ba.telescope_model.TelescopeModel(LOC, device=device)
+    rime = ba.RIME(sky, tel, beam, array, bl_list(g["bls"]), g["times"], freqs, device=device)
+    _inject(rime, sky.name, len(g["ra"]), g["times"], g["zen_az"], device)
+    return rime, dict(sky=sky.params)
+
+
 def build_2pol(g, device, dtype=torch.float64):
     freqs = _t(g["freqs"], torch.float64, device)
     ants, array = _array(g, freqs, device, dtype)

@@ -50,6 +50,31 @@ def oracle_point_airy(g, dtype=torch.float64):
     return V, dict(sky=sky_params, beam=beam_params, antvecs=antvecs)
 
 
+def oracle_pointing(g, which, dtype=torch.float64):
+    """Pointing-offset fixture: 'interp' (rect-interpolated pixel beam) or 'airy'."""
+    antvecs = tt(g["antvecs"], dtype, grad=True)
+    sky_params = tt(g["sky_params"], dtype, grad=True)
+    beam_params = tt(g["beam_params"], dtype, grad=True)
+    freqs = tt(g["freqs"], dtype)
+    ants = [int(a) for a in g["ants"]]
+    bls = bl_list(g["bls"])
+    blvecs = orc.get_blvecs(antvecs, ants, bls)
+    sky = sky_params * float(g["px_area"])
+    zenaz = [(tt(za[0], dtype), tt(za[1], dtype)) for za in g["zen_az"]]
+    if which == 'interp':
+        beam_cache = orc.pixel_response_forward(beam_params, powerbeam=True)
+
+        def beam_fn(z, a):
+            inds, wgts = orc.rect_interp_weights(g["theta_grid"], g["phi_grid"], z, a, 'linear')
+            return orc.interp_map(beam_cache, inds, wgts.to(dtype))
+    else:
+        D = torch.ones(1, 1, 1, 1, 1, dtype=dtype) * 14.0
+        beam_fn = lambda z, a: orc.airy_response(D, z, a, freqs, powerbeam=True)
+    V = orc.rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=float(g["fov"]),
+                         offset=tuple(float(x) for x in g["offset"]))
+    return V, dict(sky=sky_params, beam=beam_params, antvecs=antvecs)
+
+
 def oracle_pixel_interp(g, dtype=torch.float64, interp_mode='linear', grad=True):
     antvecs = tt(g["antvecs"], dtype, grad=grad)
     sky_params = tt(g["sky_params"], dtype, grad=grad)

@@ -500,6 +500,85 @@ def test_c3_full_size_all_pairs_factorised_vs_oracle(route):
         os.environ.pop("B200RIME_TC", None)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("which", ["interp", "airy"])
+def test_golden_pointing_offset(which, dtype):
+    """Beam pointing offset (reference beam_model.py:244-256, 1631-1678) against golden vectors
+    of the unmodified reference: fused interpolation route and generic (Airy) route."""
+    g = oc.load("rime_pointing")
+    build = mc.build_pointing_interp if which == "interp" else mc.build_pointing_airy
+    rime, leaves = build(g, DEV, dtype)
+    V = rime().data
+    G = torch.as_tensor(g["G"]).to(device=DEV, dtype=V.dtype)
+    torch.sum(G.real * V.real + G.imag * V.imag).backward()
+    tol = TOL[dtype]
+    tag = "golden/rime_pointing_%s/%s" % (which, str(dtype)[6:])
+    assert relmax(V, g["vis_" + which], tag + "/V") < tol
+    assert relmax(leaves["sky"].grad, g["grad_sky_" + which], tag + "/dsky") < 5 * tol
+    if which == "interp":
+        assert relmax(leaves["beam"].grad, g["grad_beam_interp"], tag + "/dbeam") < 5 * tol
+        assert relmax(leaves["antvecs"].grad, g["grad_antvecs_interp"], tag + "/dant") < 5 * tol
+
+
+def test_c4_nside64_all_pols_and_gradients_vs_oracle():
+    """BASELINE config 4 family at nside 64: HERA-350, all 61,075 cross baselines, 4-pol real
+    Jones beams interpolated from rect-grid maps, PixelSky with Stokes I, Q, U (24.5 k sources
+    above the horizon), 256 channels, float32, through the tensor-core kernels (one launch per
+    coherency plane), against the fp64 oracle: all four polarisation products of V on a baseline
+    / channel subset, and the gradients to the sky parameters, the Jones maps and the antenna
+    positions for a sparse cotangent whose oracle autograd is exact."""
+    if DOUBLE:
+        pytest.skip("full size needs the GPU")
+    rime = workloads.pixel_interp_pol(64, 256, 1, DEV, torch.float32, antpos_param=True)
+    dev = torch.device(DEV, torch.cuda.current_device())
+    assert rime._tc_tiling(dev) is not None
+    nbl = len(rime.sim_bls)
+    V = rime().data
+    assert tuple(V.shape) == (2, 2, nbl, 1, 256)
+    blen = rime.sim_blvecs.detach().norm(dim=1).cpu().numpy()
+    order = np.argsort(blen)
+    rng = np.random.default_rng(7)
+    gb = sorted(set(order[:2].tolist() + order[-1:].tolist() + rng.choice(nbl, 3, replace=False).tolist()))
+    gf = list(range(5, 256, 32))
+    gen = torch.Generator().manual_seed(13)
+    shp = (2, 2, len(gb), 1, len(gf))
+    G_sub = torch.complex(torch.randn(shp, generator=gen, dtype=torch.float64),
+                          torch.randn(shp, generator=gen, dtype=torch.float64))
+    G = torch.zeros(V.shape, dtype=torch.complex64, device=V.device)
+    gbt, gft = torch.as_tensor(gb, device=V.device), torch.as_tensor(gf, device=V.device)
+    G[:, :, gbt[:, None], 0, gft[None, :]] = G_sub[:, :, :, 0].to(V.device, torch.complex64)
+    torch.sum(G.real * V.real + G.imag * V.imag).backward()
+    # oracle with autograd on the subset
+    zenaz = [(za[0].cpu().double(), za[1].cpu().double()) for za in workloads.zenaz_of(rime)]
+    fi = torch.as_tensor(gf)
+    freqs = rime.array.freqs.detach().cpu().double()[fi]
+    antvecs = rime.array.antvecs.detach().cpu().double().requires_grad_(True)
+    pix = rime.sky.sky
+    sp = pix.params.detach().cpu().double()[:, :, fi].requires_grad_(True)
+    bp = rime.beam.params.detach().cpu().double()[:, :, :, fi].requires_grad_(True)
+    bls = [rime.sim_bls[i] for i in gb]
+    blvecs = orc.get_blvecs(antvecs, rime.array.ants, bls)
+    sky = orc.stokes_to_coherency(sp * float(pix.px_area))
+    bmap = orc.pixel_response_forward(bp, powerbeam=False, realbeam=True)
+    tg, pg = rime.beam.R.theta_grid.cpu().double(), rime.beam.R.phi_grid.cpu().double()
+
+    def beam_fn(z, a):
+        inds, wgts = orc.rect_interp_weights(tg, pg, z, a, 'linear')
+        return orc.interp_map(bmap, inds, wgts)
+
+    Vo = orc.rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=180.0, powerbeam=False,
+                          bl_chunk=2)
+    oc.real_loss(Vo, G_sub).backward()
+    scale = float(V.abs().max())
+    sub = V[:, :, gbt[:, None], 0, gft[None, :]].detach().cpu().to(torch.complex128)
+    errV = float((sub - Vo[:, :, :, 0].detach()).abs().max()) / scale
+    ERRLOG["c4_nside64/tc/V"] = errV
+    assert errV < 1e-5
+    assert relmax(pix.params.grad[:, :, gf], sp.grad, "c4_nside64/tc/dsky") < 5e-5
+    assert relmax(rime.beam.params.grad[:, :, :, gf], bp.grad, "c4_nside64/tc/dbeam") < 5e-5
+    assert relmax(rime.array.antvecs.grad, antvecs.grad, "c4_nside64/tc/dantvecs") < 5e-5
+
+
 def test_gradients_small_c3_vs_oracle_autograd():
     """Gradients to sky, beam map and antenna positions of a C3-shaped model small enough for
     the oracle's autograd (nside 8, HERA-37, 48 freqs, 2 times), float32 and float64."""
