@@ -178,6 +178,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "all":
         cases = cases + [(350, 98304, 4, 1.0, False, 0, ext, 8192) for ext in (300.0, 2.0)]
     res = []
+    if len(sys.argv) > 1 and sys.argv[1] == "profbwd":
+        print(json.dumps(run_bwd(350, 98304, 16, True)), flush=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "bwd":
         for c in [(40, 128, 2, True), (130, 640, 3, True), (130, 640, 3, False),
                   (350, 4096, 2, True), (350, 4096, 2, False),
