@@ -663,3 +663,33 @@ def apply_cal(vis, gains, g1_idx, g2_idx, cal_2pol=False, cov=None, undo=False):
     else:
         vout = torch.einsum("ab...,bc...,dc...->ad...", g1, vis, g2.conj())
     return vout, cov_out
+
+
+def jones_gains(params, param_type, freqs=None, refant_idx=None):
+    """JonesModel's parameter -> gain map for channel-mode parameters (calibration.py:587-597
+    fix_refant_phs with mode 'rephase' :2541-2574, then JonesResponse.params2complex :816-865 over
+    params2complex :215-251).  Returns (rephased params, complex gains)."""
+    p = params
+    if refant_idx is not None:
+        ref = p[:, :, refant_idx:refant_idx + 1]
+        if param_type == 'com':
+            p = p / torch.exp(1j * torch.angle(ref).detach())
+        elif param_type in ('dly', 'phs'):
+            p = p - ref
+        elif param_type == 'amp_phs':
+            p = torch.stack([p[..., 0], p[..., 1] - ref[..., 1]], dim=-1)
+    if param_type == 'com':
+        g = p
+    elif param_type == 'real':
+        g = p + 0j
+    elif param_type == 'amp':
+        g = torch.exp(p) + 0j
+    elif param_type == 'phs':
+        g = torch.exp(1j * p)
+    elif param_type == 'amp_phs':
+        g = torch.exp(p[..., 0] + 1j * p[..., 1])
+    elif param_type == 'dly':
+        g = torch.exp(2j * math.pi * p * (torch.as_tensor(freqs, dtype=p.dtype) / 1e9))
+    else:
+        raise ValueError(param_type)
+    return p, g

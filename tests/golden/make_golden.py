@@ -539,7 +539,59 @@ def gold_apply_cal():
     save("apply_cal", **out)
 
 
+def gold_jones_model():
+    """calibration.JonesModel.forward (calibration.py:599-664): model
+    visibilities through the Jones term for 1pol complex gains with a reference antenna, a
+    time-minibatched VisData (gain times indexed with atol), 2pol amplitude+phase gains, delay
+    gains, 4pol complex gains; outputs and autograd gradients to the gain parameters and the
+    model visibilities for a fixed cotangent."""
+    rng = np.random.default_rng(33)
+    ants = [0, 1, 2, 3, 4, 5]
+    bls = [(a, b) for a in ants for b in ants if a < b]
+    freqs = torch.linspace(120e6, 180e6, 6)
+    times = np.linspace(2458148.15, 2458148.25, 4)
+    nbl, nt, nf, na = len(bls), len(times), len(freqs), len(ants)
+    tel = ba.telescope_model.TelescopeModel(LOC)
+    c = lambda *shape: torch.as_tensor(rng.normal(size=shape) + 1j * rng.normal(size=shape))
+
+    def visdata(npol, tsel):
+        vd = ba.dataset.VisData()
+        vd.setup_meta(telescope=tel)
+        data = c(npol, npol, nbl, len(tsel), nf).requires_grad_(True)
+        vd.setup_data(bls, times[tsel], freqs, pol='ee' if npol == 1 else None, data=data)
+        return vd
+
+    out = dict(ants=ants, bls=bls, freqs=freqs, times=times)
+    cases = (("1pol_com_refant", 1, '1pol', 'com', 2, [0, 1, 2, 3]),
+             ("1pol_com_tbatch", 1, '1pol', 'com', None, [1, 3]),
+             ("2pol_ampphs", 2, '2pol', 'amp_phs', 0, [0, 1, 2, 3]),
+             ("1pol_dly", 1, '1pol', 'dly', 1, [0, 1, 2, 3]),
+             ("4pol_com", 2, '4pol', 'com', None, [0, 2, 3]))
+    for tag, npol, polmode, ptype, refant, tsel in cases:
+        if ptype == 'com':
+            params = c(npol, npol, na, nt, nf) * 0.3 + torch.eye(npol)[:, :, None, None, None]
+        elif ptype == 'amp_phs':
+            params = torch.as_tensor(rng.normal(size=(npol, npol, na, nt, nf, 2))) * 0.2
+        else:
+            params = torch.as_tensor(rng.normal(size=(npol, npol, na, nt, nf))) * 3.0   # ns
+        R = ba.calibration.JonesResponse(param_type=ptype, freqs=freqs, times=torch.as_tensor(times))
+        J = ba.calibration.JonesModel(params.clone(), ants, refant=refant, R=R, polmode=polmode)
+        vd = visdata(npol, tsel)
+        vout = J(vd)
+        G = cotangent(vout.data.shape, 500 + len(tag))
+        backward_with(vout.data, G)
+        out.update({tag + "_params_in": params, tag + "_params": J.params.detach().clone(),
+                    tag + "_vis": vd.data, tag + "_tsel": np.asarray(tsel), tag + "_out": vout.data,
+                    tag + "_G": G, tag + "_dparams": J.params.grad, tag + "_dvis": vd.data.grad})
+        out[tag + "_refant"] = -1 if refant is None else refant
+    save("jones_model", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["gold_" + name]()
+        sys.exit(0)
     gold_fringe()
     gold_airy()
     gold_rect_interp()
@@ -553,3 +605,4 @@ if __name__ == "__main__":
     gold_rime_databls()
     gold_vismapper()
     gold_apply_cal()
+    gold_jones_model()
