@@ -13,7 +13,7 @@ package without it raises.
 """
 from . import _lib                      # noqa: F401  (fails loudly if the library is missing)
 from . import utils, paramdict, dataset, healpix, telescope_model, sky_model, beam_model
-from . import ops, rime_model, imaging, calibration, parallel
+from . import ops, rime_model, imaging, calibration, parallel, optim
 from .utils import D2R, _float, _cfloat
 from .paramdict import ParamDict
 from .dataset import VisData, MapData

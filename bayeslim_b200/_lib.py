@@ -25,10 +25,12 @@ lib.b200rime_device_info.argtypes = [_I] + [ctypes.POINTER(_I)] * 4
 lib.b200rime_kc.argtypes = [_I]
 lib.b200rime_microbench.argtypes = [_I, _I, ctypes.POINTER(_D), ctypes.POINTER(_D)]
 lib.b200rime_airy_bwd_blocks.argtypes = [_I, _I]
+lib.b200rime_chisq_blocks.argtypes = [_I, _I]
 
 _SIGS = {
     "fringe_sum_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _I, _P, _P],
     "reduce_units": [_P, _P, _I, _I, _I, _P, _L, _L, _L, _D, _D, _I, _P],
+    "reduce_units_chisq": [_P, _P, _I, _I, _I, _P, _P, _P, _L, _L, _L, _I, _P, _P],
     "fringe_sum_bwd_sky": [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _I, _P, _P],
     "fringe_sum_bwd_bl": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _I, _I, _P, _P],
     "pack": [_P, _L, _I, _I, _I, _L, _L, _P, _P],

@@ -192,6 +192,58 @@ reduce_units_kernel(const T* __restrict__ vpart, const int* __restrict__ ubeg, i
 }
 
 // -------------------------------------------------------------------------------------
+// Likelihood epilogue: the unit reduction fused with the Gaussian
+// chi-square of optim.py:1012-1024 (res = V - D, chisq = sum conj(res) res icov, apply_icov
+// :1836 with cov_axis None).  V is never written: its slot receives the cotangent
+// G = dchisq/dV = 2 icov (V - D) (PyTorch's convention for a real loss), which is what the
+// backward kernels consume; chisq goes out as one float64 partial per block, summed in block
+// order by the caller (bitwise reproducible).  grid = (ceil(nbl * nfreq / 256), nt).
+// -------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+reduce_units_chisq_kernel(const T* __restrict__ vpart, const int* __restrict__ ubeg, int nbl,
+                          int nfreq, int nfp, T* __restrict__ V, const T* __restrict__ D,
+                          const T* __restrict__ W, long long sb, long long st, long long sf,
+                          int accumulate, double* __restrict__ chi_part) {
+    __shared__ double red[8];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    double chi = 0.0;
+    if (idx < (long long)nbl * nfreq) {
+        const int b = (int)(idx / nfreq);
+        const int f = (int)(idx - (long long)b * nfreq);
+        double sr = 0.0, si = 0.0;
+        const int u0 = ubeg[t], u1 = ubeg[t + 1];
+        for (int u = u0; u < u1; ++u) {
+            const T* p = vpart + (((size_t)u * nbl + b) * nfp + f) * 2;
+            sr += (double)p[0];
+            si += (double)p[1];
+        }
+        const long long e = (long long)b * sb + (long long)t * st + (long long)f * sf;
+        T* o = V + e * 2;
+        if (accumulate) {
+            sr += (double)o[0];
+            si += (double)o[1];
+        }
+        const double rr = sr - (double)D[e * 2], ri = si - (double)D[e * 2 + 1];
+        const double w = W != nullptr ? (double)W[e] : 1.0;
+        chi = w * (rr * rr + ri * ri);
+        o[0] = (T)(2.0 * w * rr);
+        o[1] = (T)(2.0 * w * ri);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) chi += __shfl_xor_sync(0xffffffffu, chi, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = chi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) tot += red[w8];
+        chi_part[(size_t)t * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+// -------------------------------------------------------------------------------------
 // K2: backward to the perceived sky.  grid = (S/128, nchunk), block = 128 (thread <-> source)
 // -------------------------------------------------------------------------------------
 template <typename T, bool UNIFORM>
@@ -526,6 +578,21 @@ int launch_reduce(const T* vpart, const int* ubeg, int nt, int nbl, int nfreq, T
 }
 
 template <typename T>
+int launch_reduce_chisq(const T* vpart, const int* ubeg, int nt, int nbl, int nfreq, T* V, const T* D,
+                        const T* W, long long sb, long long stt, long long sf, int accumulate,
+                        double* chi_part, cudaStream_t st) {
+    if (nt <= 0 || nbl <= 0 || nfreq <= 0) return 0;
+    if (D == nullptr || chi_part == nullptr) return set_error("reduce_units_chisq: data and partials are required");
+    constexpr int KC = Cfg<T>::KC;
+    const int nfp = ((nfreq + KC - 1) / KC) * KC;
+    const long long n = (long long)nbl * nfreq;
+    dim3 grid((unsigned)((n + 255) / 256), nt);
+    reduce_units_chisq_kernel<T><<<grid, 256, 0, st>>>(vpart, ubeg, nbl, nfreq, nfp, V, D, W, sb, stt,
+                                                        sf, accumulate, chi_part);
+    return check_launch("reduce_units_chisq");
+}
+
+template <typename T>
 int launch_bwd_sky(const T* Gp, const double* shat, const double* blv, const double* freqs,
                    const int* tile_time, int nbl, int nt, int nfreq, long long S, int conj,
                    int uniform, T* dA, cudaStream_t st) {
@@ -609,6 +676,23 @@ int b200rime_reduce_units_f32(const float* Vpart, const int* ubeg, int nt, int n
                               double aim, int accumulate, void* stream) {
     return launch_reduce<float>(Vpart, ubeg, nt, nbl, nfreq, V, sb, st, sf, are, aim, accumulate,
                                 (cudaStream_t)stream);
+}
+int b200rime_chisq_blocks(int nbl, int nfreq) {
+    return (int)(((long long)nbl * nfreq + 255) / 256);
+}
+int b200rime_reduce_units_chisq_f32(const float* Vpart, const int* ubeg, int nt, int nbl, int nfreq,
+                                    float* V, const float* D, const float* W, long long sb,
+                                    long long st, long long sf, int accumulate, double* chi_part,
+                                    void* stream) {
+    return launch_reduce_chisq<float>(Vpart, ubeg, nt, nbl, nfreq, V, D, W, sb, st, sf, accumulate,
+                                      chi_part, (cudaStream_t)stream);
+}
+int b200rime_reduce_units_chisq_f64(const double* Vpart, const int* ubeg, int nt, int nbl,
+                                    int nfreq, double* V, const double* D, const double* W,
+                                    long long sb, long long st, long long sf, int accumulate,
+                                    double* chi_part, void* stream) {
+    return launch_reduce_chisq<double>(Vpart, ubeg, nt, nbl, nfreq, V, D, W, sb, st, sf, accumulate,
+                                       chi_part, (cudaStream_t)stream);
 }
 int b200rime_reduce_units_f64(const double* Vpart, const int* ubeg, int nt, int nbl, int nfreq,
                               double* V, long long sb, long long st, long long sf, double are,

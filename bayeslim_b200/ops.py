@@ -460,6 +460,39 @@ def _unit_batches(ubeg, nt, bytes_per_unit):
     return plan, max(u1 - u0 for _, _, u0, u1, _ in plan)
 
 
+def _final_flags(plan):
+    """True for the launches after which their times are complete (a time split over several
+    launches is complete after the last of them)."""
+    return [not (k + 1 < len(plan) and plan[k + 1][4] == 1) for k in range(len(plan))]
+
+
+class _ChisqEpilogue:
+    """State of the fused likelihood epilogue (reduce_units_chisq): data D and weights W in the
+    layout of V (nplane, nbl, nt, nfreq), and the float64 block partials collected per launch."""
+
+    def __init__(self, data, icov, rdtype):
+        self.D = torch.view_as_real(data.contiguous())
+        self.W = icov.to(rdtype).contiguous() if icov is not None else None
+        self.parts = []
+
+    def reduce(self, sfx, vpart, ub, ntimes, nbl, nfreq, Vr, p, ta, nt, accum, final):
+        if not final:
+            _call("reduce_units", sfx, vpart, ub, ntimes, nbl, nfreq, Vr[p, :, ta:], nt * nfreq,
+                  nfreq, 1, 1.0, 0.0, accum)
+            return
+        nb = _lib.lib.b200rime_chisq_blocks(nbl, nfreq)
+        part = torch.empty(ntimes, nb, dtype=torch.float64, device=vpart.device)
+        _call("reduce_units_chisq", sfx, vpart, ub, ntimes, nbl, nfreq, Vr[p, :, ta:],
+              self.D[p, :, ta:], self.W[p, :, ta:] if self.W is not None else None, nt * nfreq,
+              nfreq, 1, accum, part)
+        self.parts.append(part)
+
+    def total(self, device):
+        if not self.parts:
+            return torch.zeros((), dtype=torch.float64, device=device)
+        return torch.stack([q.sum() for q in self.parts]).sum()
+
+
 def _batch_ubeg(ubeg, ta, tb, u0, u1, device):
     """Unit offsets of the times ta..tb of a launch, relative to its first unit u0 (a split time
     has the single range [0, u1 - u0))."""
@@ -467,33 +500,45 @@ def _batch_ubeg(ubeg, ta, tb, u0, u1, device):
     return torch.as_tensor(rel.astype(np.int32), device=device)
 
 
+def _run_fwd_baseline(A, blv, geom, freqs64, nfreq, conj, uniform, epilogue=None):
+    """Launches of the baseline-owned forward: V (nplane, nbl, nt, nfreq) complex, or -- with a
+    _ChisqEpilogue -- the cotangent 2 W (V - D) in its place."""
+    dtype, sfx = A.dtype, _sfx(A.dtype)
+    dev = A.device
+    nplane, nchunk = A.shape[0], A.shape[1]
+    nfp = nchunk * _lib.KC[sfx]
+    nbl, nt = blv.shape[0], geom.nt
+    V = torch.zeros(nplane, nbl, nt, nfreq, dtype=_cplx(dtype), device=dev)
+    if nbl > 0 and nt > 0 and geom.S > 0:
+        units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
+        esize = 8 if sfx == "f32" else 16
+        batches, nu_max = _unit_batches(ubeg, nt, nbl * nfp * esize)
+        final = _final_flags(batches)
+        vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=dtype, device=dev)
+        Vr = torch.view_as_real(V)
+        for (ta, tb, u0, u1, accum), fin in zip(batches, final):
+            ub = _batch_ubeg(ubeg, ta, tb, u0, u1, dev)
+            for p in range(nplane):
+                _call("fringe_sum_fwd", sfx, A[p], geom.shat, blv, freqs64,
+                      units[u0:], u1 - u0, nbl, nfreq, geom.S, int(conj), int(uniform),
+                      vpart)
+                if epilogue is not None:
+                    epilogue.reduce(sfx, vpart, ub, tb - ta, nbl, nfreq, Vr, p, ta, nt, accum, fin)
+                else:
+                    _call("reduce_units", sfx, vpart, ub, tb - ta, nbl, nfreq,
+                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, accum)
+    elif epilogue is not None and V.numel():
+        raise RuntimeError("fused chi-square needs at least one source inside the field of view")
+    return V
+
+
 class _FringeSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, blvecs, geom, freqs64, nfreq, conj, uniform):
         _need_cuda(A, freqs64)
-        dtype, sfx = A.dtype, _sfx(A.dtype)
         A = A.contiguous()
-        dev = A.device
-        nplane, nchunk = A.shape[0], A.shape[1]
-        kc = _lib.KC[sfx]
-        nfp = nchunk * kc
-        nbl, nt = blvecs.shape[0], geom.nt
-        blv = _blv4(blvecs, dev)
-        V = torch.zeros(nplane, nbl, nt, nfreq, dtype=_cplx(dtype), device=dev)
-        if nbl > 0 and nt > 0 and geom.S > 0:
-            units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
-            esize = 8 if sfx == "f32" else 16
-            batches, nu_max = _unit_batches(ubeg, nt, nbl * nfp * esize)
-            vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=dtype, device=dev)
-            Vr = torch.view_as_real(V)
-            for (ta, tb, u0, u1, accum) in batches:
-                ub = _batch_ubeg(ubeg, ta, tb, u0, u1, dev)
-                for p in range(nplane):
-                    _call("fringe_sum_fwd", sfx, A[p], geom.shat, blv, freqs64,
-                          units[u0:], u1 - u0, nbl, nfreq, geom.S, int(conj), int(uniform),
-                          vpart)
-                    _call("reduce_units", sfx, vpart, ub, tb - ta, nbl, nfreq,
-                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, accum)
+        blv = _blv4(blvecs, A.device)
+        V = _run_fwd_baseline(A, blv, geom, freqs64, nfreq, conj, uniform)
         need_bl = ctx.needs_input_grad[1]
         ctx.save_for_backward(A if need_bl else None, blv, freqs64)
         ctx.meta = (geom, nfreq, int(conj), int(uniform), blvecs.dtype, blvecs.device, A.shape)
@@ -784,6 +829,52 @@ def tc_scale(A):
     return torch.exp2(14.0 - torch.floor(torch.log2(amax))).to(torch.float32).contiguous()
 
 
+def _run_fwd_ant(A, antv, geom, freqs64, nfreq, conj, tiling, tc, epilogue=None):
+    """Launches of the antenna-factorised forward (tensor-core items when tc is given)."""
+    dev = A.device
+    nplane, nchunk = A.shape[0], A.shape[1]
+    nfp = nchunk * _lib.KC["f32"]
+    plan = tiling if tiling is not None else tc
+    nbl, nt = plan.nbl, geom.nt
+    V = torch.zeros(nplane, nbl, nt, nfreq, dtype=torch.complex64, device=dev)
+    if nbl > 0 and nt > 0 and geom.S > 0:
+        units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
+        batches, nu_max = _unit_batches(ubeg, nt, nbl * nfp * 8)
+        final = _final_flags(batches)
+        # pairs outside the tiling keep their zero: every wanted pair has exactly one owner
+        vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=torch.float32, device=dev)
+        Vr = torch.view_as_real(V)
+        if tc is not None:
+            # channel-major copy: a stage's 16 sky values become one contiguous TMA copy
+            ascale = tc_scale(A)
+            acm = A.permute(0, 1, 3, 2).reshape(nplane, nfp, A.shape[2]).contiguous()
+        for (ta, tb, u0, u1, accum), fin in zip(batches, final):
+            ub = _batch_ubeg(ubeg, ta, tb, u0, u1, dev)
+            for p in range(nplane):
+                if tc is not None:
+                    _call("tcfringe_fwd", "f32", acm[p], ascale[p:p + 1], geom.shat, antv,
+                          freqs64, units[u0:], u1 - u0, tc.items, tc.nitems, tc.pair_bl,
+                          tc.ldp, tc.na, nbl, nfreq, geom.S, int(conj), vpart)
+                else:
+                    _call("antfringe_fwd", "f32", A[p], geom.shat, antv, freqs64, units[u0:],
+                          u1 - u0, tiling.tile_ant, tiling.tile_bl, tiling.tile_order,
+                          tiling.ntile, nbl, nfreq, geom.S, int(conj), vpart)
+                if epilogue is not None:
+                    epilogue.reduce("f32", vpart, ub, tb - ta, nbl, nfreq, Vr, p, ta, nt, accum, fin)
+                else:
+                    _call("reduce_units", "f32", vpart, ub, tb - ta, nbl, nfreq,
+                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, accum)
+    elif epilogue is not None and V.numel():
+        raise RuntimeError("fused chi-square needs at least one source inside the field of view")
+    return V
+
+
+def _ant_route_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, tc, need_A, need_r):
+    if tc is not None and (tc.bwd_usable or tiling is None):
+        return _tc_backward(G, A, antv, geom, freqs64, nfreq, conj, tc, A.shape, need_A, need_r)
+    return _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, A.shape, need_A, need_r)
+
+
 class _AntFringeSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, antvecs, geom, freqs64, nfreq, conj, tiling, tc=None):
@@ -791,37 +882,8 @@ class _AntFringeSum(torch.autograd.Function):
         if A.dtype != torch.float32:
             raise TypeError("fringe_sum_ant is float32 only")
         A = A.contiguous()
-        dev = A.device
-        nplane, nchunk = A.shape[0], A.shape[1]
-        kc = _lib.KC["f32"]
-        nfp = nchunk * kc
-        plan = tiling if tiling is not None else tc
-        nbl, nt = plan.nbl, geom.nt
-        antv = plan.antv4(antvecs)
-        V = torch.zeros(nplane, nbl, nt, nfreq, dtype=torch.complex64, device=dev)
-        if nbl > 0 and nt > 0 and geom.S > 0:
-            units, ubeg = geom.units(nbl, nchunk, sm_count(dev))
-            batches, nu_max = _unit_batches(ubeg, nt, nbl * nfp * 8)
-            # pairs outside the tiling keep their zero: every wanted pair has exactly one owner
-            vpart = torch.empty(nu_max, nbl, nfp, 2, dtype=torch.float32, device=dev)
-            Vr = torch.view_as_real(V)
-            if tc is not None:
-                # channel-major copy: a stage's 16 sky values become one contiguous TMA copy
-                ascale = tc_scale(A)
-                acm = A.permute(0, 1, 3, 2).reshape(nplane, nfp, A.shape[2]).contiguous()
-            for (ta, tb, u0, u1, accum) in batches:
-                ub = _batch_ubeg(ubeg, ta, tb, u0, u1, dev)
-                for p in range(nplane):
-                    if tc is not None:
-                        _call("tcfringe_fwd", "f32", acm[p], ascale[p:p + 1], geom.shat, antv,
-                              freqs64, units[u0:], u1 - u0, tc.items, tc.nitems, tc.pair_bl,
-                              tc.ldp, tc.na, nbl, nfreq, geom.S, int(conj), vpart)
-                    else:
-                        _call("antfringe_fwd", "f32", A[p], geom.shat, antv, freqs64, units[u0:],
-                              u1 - u0, tiling.tile_ant, tiling.tile_bl, tiling.tile_order,
-                              tiling.ntile, nbl, nfreq, geom.S, int(conj), vpart)
-                    _call("reduce_units", "f32", vpart, ub, tb - ta, nbl, nfreq,
-                          Vr[p, :, ta:], nt * nfreq, nfreq, 1, 1.0, 0.0, accum)
+        antv = (tiling if tiling is not None else tc).antv4(antvecs)
+        V = _run_fwd_ant(A, antv, geom, freqs64, nfreq, conj, tiling, tc)
         ctx.save_for_backward(A, antv, freqs64)
         ctx.meta = (geom, nfreq, int(conj), tiling, antvecs.dtype, antvecs.device, antvecs.shape,
                     tc)
@@ -832,12 +894,8 @@ class _AntFringeSum(torch.autograd.Function):
         A, antv, freqs64 = ctx.saved_tensors
         geom, nfreq, conj, tiling, adtype, adev, ashape_ant, tc = ctx.meta
         need_A, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if tc is not None and (tc.bwd_usable or tiling is None):
-            dA, dr = _tc_backward(G, A, antv, geom, freqs64, nfreq, conj, tc, A.shape, need_A,
-                                  need_r)
-        else:
-            dA, dr = _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, A.shape, need_A,
-                                   need_r)
+        dA, dr = _ant_route_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, tc, need_A,
+                                     need_r)
         gant = None
         if need_r:
             gant = torch.zeros(ashape_ant, dtype=torch.float64, device=G.device)
@@ -845,6 +903,65 @@ class _AntFringeSum(torch.autograd.Function):
             gant[:na] = dr[:na]
             gant = gant.to(device=adev, dtype=adtype)
         return dA, gant, None, None, None, None, None, None
+
+
+class _FringeChisq(torch.autograd.Function):
+    """chisq = sum icov |V - data|^2 with V the fringe sum of A, fused: the unit reduction writes
+    the cotangent 2 icov (V - data) instead of V (reduce_units_chisq), the backward kernels start
+    from it.  vecs: baseline vectors (baseline-owned kernels) or antenna positions (tiling / tc)."""
+
+    @staticmethod
+    def forward(ctx, A, vecs, geom, freqs64, nfreq, conj, uniform, tiling, tc, data, icov):
+        _need_cuda(A, freqs64, data, icov)
+        A = A.contiguous()
+        ant = tiling is not None or tc is not None
+        if ant and A.dtype != torch.float32:
+            raise TypeError("the antenna-factorised kernels are float32 only")
+        epi = _ChisqEpilogue(data.to(_cplx(A.dtype)), icov, A.dtype)
+        if ant:
+            v4 = (tiling if tiling is not None else tc).antv4(vecs)
+            G = _run_fwd_ant(A, v4, geom, freqs64, nfreq, conj, tiling, tc, epilogue=epi)
+        else:
+            v4 = _blv4(vecs, A.device)
+            G = _run_fwd_baseline(A, v4, geom, freqs64, nfreq, conj, uniform, epilogue=epi)
+        if tuple(G.shape) != tuple(data.shape):
+            raise ValueError("data %s does not match the visibilities %s" % (tuple(data.shape),
+                                                                              tuple(G.shape)))
+        ctx.save_for_backward(A, v4, freqs64, G)
+        ctx.meta = (geom, nfreq, int(conj), int(uniform), tiling, tc, vecs.dtype, vecs.device,
+                    vecs.shape)
+        ctx.mark_non_differentiable(G)
+        return epi.total(A.device), G
+
+    @staticmethod
+    def backward(ctx, gchi, _gG):
+        A, v4, freqs64, G = ctx.saved_tensors
+        geom, nfreq, conj, uniform, tiling, tc, vdtype, vdev, vshape = ctx.meta
+        need_A, need_v = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if tiling is not None or tc is not None:
+            dA, dv = _ant_route_backward(G, A, v4, geom, freqs64, nfreq, conj, tiling, tc, need_A,
+                                         need_v)
+        else:
+            dA, dv = _fringe_backward(G, A, v4, geom, freqs64, nfreq, conj, uniform, A.shape,
+                                      need_A, need_v)
+        if need_A:
+            dA = dA * gchi.to(dA.dtype)
+        gv = None
+        if need_v:
+            gv = torch.zeros(vshape, dtype=torch.float64, device=G.device)
+            n = min(vshape[0], dv.shape[0])
+            gv[:n] = dv[:n, :3] * gchi.to(torch.float64)
+            gv = gv.to(device=vdev, dtype=vdtype)
+        return dA, gv, None, None, None, None, None, None, None, None, None
+
+
+def fringe_chisq(A, vecs, geom, freqs64, nfreq, data, icov=None, conj=False, uniform=True,
+                 tiling=None, tc=None):
+    """(chisq, G): chisq = sum icov |V - data|^2 (float64 scalar, differentiable with respect to A
+    and vecs) and the cotangent G = 2 icov (V - data), for V = fringe_sum(A, ...) -- the fused
+    form of optim.LogProb.forward_chisq (optim.py:1012-1024) on the visibilities of the RIME.
+    The residual is V - data = G / (2 icov)."""
+    return _FringeChisq.apply(A, vecs, geom, freqs64, nfreq, conj, uniform, tiling, tc, data, icov)
 
 
 def _ant_backward(G, A, antv, geom, freqs64, nfreq, conj, tiling, ashape, need_A, need_r):

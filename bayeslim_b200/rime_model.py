@@ -565,6 +565,68 @@ class RIME(utils.Module):
             out = out.index_copy(2, sel, V)
         return out
 
+    # ------------------------------------------------------------------ fused likelihood
+    def _single_plane_set(self, sky_comp):
+        """(A, (P, Q), rec, blvecs, f64, nfreq, uniform, dev) when the perceived sky of this
+        component is one set of real tiled planes summed over all baselines of the group (fused
+        builders, or polarised interpolated beams with a single beam model), else None."""
+        sky = sky_comp.data
+        dev = self._compute_device(sky)
+        sky = sky.to(dev)
+        rdtype = ops._real(sky.dtype)
+        rec = self._geometry(sky_comp, dev)
+        blvecs, uniform = self._baseline_meta(dev, rdtype)
+        f64 = self._freqs64(self.array, dev)
+        mode = self._fused_mode(sky)
+        if mode is not None:
+            A = self._build_airy(sky, rec, dev) if mode == 'airy' else self._build_interp(sky, rec, dev)
+            return A, (A.shape[0], 1), rec, blvecs, f64, len(f64), uniform, dev
+        if self._interp_pol_mode(sky):
+            psky, modelpairs, _ = self._tiled_pol_planes(sky, rec, dev)
+            if len(modelpairs) == 1 and not psky.is_complex():
+                P, Q = psky.shape[0], psky.shape[1]
+                A = psky[:, :, 0].reshape((P * Q,) + tuple(psky.shape[3:])).to(rdtype).contiguous()
+                return A, (P, Q), rec, blvecs, f64, len(f64), uniform, dev
+        return None
+
+    def forward_chisq(self, data, icov=None, prior_cache=None):
+        """chisq = sum icov |V - data|^2 of the current batch against data (Npol, Npol|1, Nbl,
+        Ntimes, Nfreqs) -- what optim.LogProb.forward_chisq computes from forward()
+        (optim.py:1012-1024, apply_icov :1836 with cov_axis None), fused into the unit reduction
+        of the fringe-sum kernels so the visibilities never reach HBM and the backward pass starts
+        from the cotangent the epilogue wrote.  Falls back to forward() + torch for the cases the
+        epilogue does not cover (several sky components, several beam models, complex perceived
+        sky, data_bls inflation).  Returns (chisq, residual-free handle): the float64 scalar and
+        the cotangent tensor G = 2 icov (V - data) (None on the fallback route)."""
+        self._set_group()
+        comps = self.sky.forward(prior_cache=prior_cache)
+        comps = comps if isinstance(comps, list) else [comps]
+        plan = None
+        if len(comps) == 1 and self._sim2data[self._bl_key] is None:
+            if hasattr(self.beam.R, 'clear_beam_cache'):
+                self.beam.R.clear_beam_cache()
+            self.beam.skycut_device = getattr(self.sky, 'device', None)
+            plan = self._single_plane_set(comps[0])
+        if plan is None:
+            vd = self.forward(prior_cache=prior_cache)
+            res = vd.data - data.to(vd.data.device)
+            w = 1.0 if icov is None else icov.to(res.device)
+            return (res.real ** 2 + res.imag ** 2).mul(w).sum().double(), None
+        A, (P, Q), rec, blvecs, f64, nfreq, uniform, dev = plan
+        self.beam.eval_prior(prior_cache)
+        nbl, nt = len(self.sim_bls), self.Ntimes
+        D = data.to(dev).reshape(P * Q, nbl, nt, nfreq)
+        W = icov.to(dev).reshape(P * Q, nbl, nt, nfreq) if icov is not None else None
+        tc = til = None
+        if A.dtype == torch.float32:
+            tc, til = self._tc_tiling(dev), self._ant_tiling(dev)
+        if tc is not None or til is not None:
+            chi, G = ops.fringe_chisq(A, self.array.antvecs.to(dev), rec.geom, f64, nfreq, D, W,
+                                      tiling=til, tc=tc)
+        else:
+            chi, G = ops.fringe_chisq(A, blvecs, rec.geom, f64, nfreq, D, W, uniform=uniform)
+        return chi, G.reshape(P, Q, nbl, nt, nfreq)
+
     def _history(self):
         return "bayeslim_b200.RIME | sky={} beam={}({}) array={} Nbls={} Ntimes={} Nfreqs={}".format(
             self.sky.__class__.__name__, self.beam.__class__.__name__,

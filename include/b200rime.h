@@ -83,6 +83,25 @@ int b200rime_reduce_units_f64(const double* Vpart, const int* ubeg, int nt, int 
                               double alpha_re, double alpha_im, int accumulate,
                               b200rime_stream_t stream);
 
+/* ---- likelihood epilogue ----------------------------------------------------------
+ * reduce_units fused with the Gaussian chi-square of optim.LogProb.forward_chisq
+ * (optim.py:1012-1024: res = prediction - data, chisq = sum conj(res) res icov; apply_icov
+ * optim.py:1836 with cov_axis None).  With V = (V if accumulate) + sum_u Vpart[u]:
+ *   chi_part[t * chisq_blocks(nbl, nfreq) + block] = sum over the block's 256 (b, f) elements of
+ *                                                    W |V - D|^2        (float64, fixed order)
+ *   V[b*sb + t*st + f*sf] <- 2 W (V - D)    the cotangent dchisq/dV the backward kernels consume
+ * so the visibilities themselves never reach HBM when only the likelihood is wanted.  D (complex)
+ * and W (real, NULL = 1) use V's strides. */
+int b200rime_chisq_blocks(int nbl, int nfreq);
+int b200rime_reduce_units_chisq_f32(const float* Vpart, const int* ubeg, int nt, int nbl, int nfreq,
+                                    float* V, const float* D, const float* W, long long sb,
+                                    long long st, long long sf, int accumulate, double* chi_part,
+                                    b200rime_stream_t stream);
+int b200rime_reduce_units_chisq_f64(const double* Vpart, const int* ubeg, int nt, int nbl,
+                                    int nfreq, double* V, const double* D, const double* W,
+                                    long long sb, long long st, long long sf, int accumulate,
+                                    double* chi_part, b200rime_stream_t stream);
+
 /* ---- fringe sum backward to the perceived sky ----------------------------------
  * dA[f][s] = sum_b Re( conj(F[b][f][s]) * Gp[t(s)][f][b] )   (autograd of rime_model.py:429
  * w.r.t. psky, for a real plane).  tile_time: int32 [S/128] time index of each 128-source

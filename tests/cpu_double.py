@@ -68,6 +68,23 @@ def reduce_units(sfx, vpart, ubeg, nt, nbl, nfreq, V, sb, st, sf, are, aim, accu
         V[:, t, :, 1] = i.to(V.dtype)
 
 
+def reduce_units_chisq(sfx, vpart, ubeg, nt, nbl, nfreq, V, D, W, sb, st, sf, accumulate, chi_part):
+    assert sf == 1 and st == nfreq
+    nb = chi_part.shape[1]
+    for t in range(nt):
+        u0, u1 = int(ubeg[t]), int(ubeg[t + 1])
+        v = vpart[u0:u1, :, :nfreq].double().sum(0)
+        if accumulate:
+            v = v + V[:, t].double()
+        r = v - D[:, t].double()
+        w = W[:, t].double() if W is not None else torch.ones(nbl, nfreq, dtype=torch.float64)
+        chi = (w * (r[..., 0] ** 2 + r[..., 1] ** 2)).reshape(-1)
+        pad = torch.zeros(nb * 256, dtype=torch.float64)
+        pad[:chi.numel()] = chi
+        chi_part[t] = pad.reshape(nb, 256).sum(1)
+        V[:, t] = (2 * w[..., None] * r).to(V.dtype)
+
+
 def fringe_sum_bwd_sky(sfx, Gp, shat, blv, freqs, tile_time, nbl, nt, nfreq, S, conj, uniform, dA):
     kc = _kc(sfx)
     pad = _lib.SRC_PAD
@@ -379,6 +396,7 @@ def apply_cal_bwd_gains(sfx, vis, gains, gout, g1, g2, p1, b1, p2, b2, npol, ful
 
 
 _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
+              reduce_units_chisq=reduce_units_chisq,
               fringe_sum_bwd_sky=fringe_sum_bwd_sky, fringe_sum_bwd_bl=fringe_sum_bwd_bl,
               pack=pack, unpack=unpack, build_interp=build_interp, build_interp_t=build_interp_t,
               build_interp_bwd=build_interp_bwd, interp_transpose=interp_transpose,
