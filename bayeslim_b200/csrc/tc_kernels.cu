@@ -46,6 +46,9 @@
 
 namespace b200rime {
 
+#ifndef B200_TC_PROBE
+#define B200_TC_PROBE 0            // timing probes (wrong results): 1 no sine / cosine, 2 no MMAs, 8 no proxy fence
+#endif
 #ifndef B200_TC_FLUSH
 #define B200_TC_FLUSH 4            // stages (of 16 sources) per TMEM accumulation chain
 #endif
@@ -55,21 +58,14 @@ constexpr int TC_KS = 16;            // sources per stage = one kind::f16 UMMA K
 constexpr int TC_NSTAGE = 6;         // operand stages
 constexpr int TC_NSRC = 8;           // source-data slots (staged TC_NSRC stages ahead)
 constexpr int TC_FLUSH = B200_TC_FLUSH;
-constexpr int TC_ACC_WARPS = 8;      // warps 0..7: TMEM -> register accumulators; warp 0 issues
-constexpr int TC_PROD_WARPS = 8;     // warps 8..15: operand generation
-constexpr int TC_THREADS = (TC_ACC_WARPS + TC_PROD_WARPS) * 32;   // 512 = four whole warpgroups
-// registers after setmaxnreg: 256 * 168 + 256 * 88 = 512 * 128 = the CTA's pool (the launcher
-// checks the kernel's register count: asking for more than the pool makes setmaxnreg.inc spin)
-#ifndef B200_TC_ACCREGS
-#define B200_TC_ACCREGS 168
-#endif
-#ifndef B200_TC_PV
-#define B200_TC_PV 1               // producer code variant (0: one pass over X and Y, 1: X pass then Y pass)
-#endif
-constexpr int TC_ACC_REGS = B200_TC_ACCREGS, TC_PROD_REGS = 256 - B200_TC_ACCREGS, TC_LAUNCH_REGS = 128;
+constexpr int TC_WORK_WARPS = 16;    // warps 0..15: operand generation AND register accumulators
+constexpr int TC_WORKERS = TC_WORK_WARPS * 32;
+constexpr int TC_CTRL_WARP = 0;      // its lane 0 also stages the sources (TMA) and issues the MMAs
+constexpr int TC_THREADS = TC_WORKERS;            // 512 threads x 128 registers = the register file
 constexpr int TC_KC = B200_KC_F32;
 constexpr int TC_TMEM_COLS = 512;    // two accumulator sets of (re, im) x 128 columns
 constexpr int TC_SET_COLS = 256, TC_IM_COL = 128;
+constexpr int TC_CG = 32;            // accumulator columns per worker warp (4 column groups)
 
 struct TcSmem {
     // one operand array = 128 rows x 16 float16 in the canonical no-swizzle K-major layout:
@@ -104,6 +100,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int n, bool neg_a) {
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
                                          uint32_t accumulate) {
+#if B200_TC_PROBE & 2
+    return;
+#endif
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -125,7 +124,9 @@ __device__ __forceinline__ void tc_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
+#if !(B200_TC_PROBE & 8)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
 }
 // 8 consecutive columns of the warp's 32 TMEM lanes -> 8 registers per thread (issue only)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -164,83 +165,65 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
 // the phase fraction as a 32-bit fixed-point number.  It is turned into a float in
 // [-2^22, 2^22) with an exponent trick and scaled to radians for MUFU sine / cosine.
 __device__ __forceinline__ void antenna_cis(double t, float& c, float& s) {
+#if B200_TC_PROBE & 1
+    c = __uint_as_float(__double2loint(t)) * 1e-30f + 0.5f;
+    s = 0.25f;
+    return;
+#endif
     const uint32_t lo = (uint32_t)__double2loint(t);
     const float fb = __uint_as_float((lo >> 9) ^ 0x4B400000u) - 12582912.0f;
     const float ang = fb * 7.4901405e-07f;          // 2 pi / 2^23
     c = __cosf(ang);
     s = __sinf(ang);
 }
+__device__ __forceinline__ double phase_fma(const double (&p)[3], const double4& sv) {
+    return __fma_rn(p[0], sv.x, __fma_rn(p[1], sv.y, __fma_rn(p[2], sv.z, 1572864.0)));
+}
 
-// hi / lo float16 split of 8 values -> two 16-byte rows
-__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
+// hi / lo float16 split of 4 values -> two 8-byte half rows.  lo = v - float(hi) is one
+// mixed-precision FMA (FHFMA: float16 x float16 + float32), exact before its final rounding.
+__device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo) {
+    uint32_t h[2], l[2];
+    const unsigned short m1 = 0xBC00;               // -1.0 in float16
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
         const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-        const float2 back = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(v[2 * q] - back.x, v[2 * q + 1] - back.y);
-        h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hh);
+        float l0, l1;
+        asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l0) : "h"((unsigned short)(hu & 0xffffu)), "h"(m1), "f"(v[2 * q]));
+        asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l1) : "h"((unsigned short)(hu >> 16)), "h"(m1), "f"(v[2 * q + 1]));
+        const __half2 ll = __floats2half2_rn(l0, l1);
+        h[q] = hu;
         l[q] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
+    hi = make_uint2(h[0], h[1]);
+    lo = make_uint2(l[0], l[1]);
+}
+// (cos, sin) of 4 sources -> the four arrays (re_hi, re_lo, im_hi, im_lo) of one operand
+__device__ __forceinline__ void store_split(unsigned char* dst, const float (&c)[4], const float (&s)[4]) {
+    uint2 hi, lo;
+    split4(c, hi, lo);
+    *reinterpret_cast<uint2*>(dst) = hi;
+    *reinterpret_cast<uint2*>(dst + TcSmem::ARR) = lo;
+    split4(s, hi, lo);
+    *reinterpret_cast<uint2*>(dst + 2 * TcSmem::ARR) = hi;
+    *reinterpret_cast<uint2*>(dst + 3 * TcSmem::ARR) = lo;
 }
 
-// -------------------------------------------------------------------------------------
-// forward.  grid = (nitems * nfreq, nunits), block = 512.
-//   Acm      float [Nfp][S]     perceived sky, channel-major (row k = channel k over the packed
-//                                source axis): the 16 values of a stage are one 64-byte bulk copy
-//   items    int32 [nitems][4]  {i0, j0, N, 0}: X rows = antennas i0 .. i0 + 127, Y rows =
-//                                antennas j0 .. j0 + N - 1 (N a multiple of 32, <= 128)
-//   pair_bl  int32 [ldp][ldp]   (baseline << 1 | conj) of V_ij = sum conj(E_i) A E_j, or -1
-//   ascale   float [1]          power of two that brings max |A| into [2^14, 2^15)
-// -------------------------------------------------------------------------------------
-// one producer thread, one stage: antenna terms of operand row `row` (X role: position xp, Y role:
-// position yp times the sky values a) for the 8 sources sh[0..8)
-template <bool DIAG>
-__device__ __forceinline__ void tc_produce_rows(unsigned char* row, const double4* sh,
-                                                const float (&a)[8], const double (&xp)[3],
-                                                const double (&yp)[3], bool xlive, bool ylive) {
-    float c[8], s[8];
-    uint4 hi, lo;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const double4 sv = sh[e];
-        antenna_cis(__fma_rn(xp[0], sv.x, __fma_rn(xp[1], sv.y, __fma_rn(xp[2], sv.z, 1572864.0))),
-                    c[e], s[e]);
-    }
-    if (xlive) {
-        split8(c, hi, lo);
-        *reinterpret_cast<uint4*>(row + TcSmem::XR_H) = hi;
-        *reinterpret_cast<uint4*>(row + TcSmem::XR_L) = lo;
-        split8(s, hi, lo);
-        *reinterpret_cast<uint4*>(row + TcSmem::XI_H) = hi;
-        *reinterpret_cast<uint4*>(row + TcSmem::XI_L) = lo;
-    }
-    if (!DIAG) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const double4 sv = sh[e];
-            antenna_cis(__fma_rn(yp[0], sv.x, __fma_rn(yp[1], sv.y, __fma_rn(yp[2], sv.z, 1572864.0))),
-                        c[e], s[e]);
-        }
-    }
-    if (ylive) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            c[e] *= a[e];
-            s[e] *= a[e];
-        }
-        split8(c, hi, lo);
-        *reinterpret_cast<uint4*>(row + TcSmem::YR_H) = hi;
-        *reinterpret_cast<uint4*>(row + TcSmem::YR_L) = lo;
-        split8(s, hi, lo);
-        *reinterpret_cast<uint4*>(row + TcSmem::YI_H) = hi;
-        *reinterpret_cast<uint4*>(row + TcSmem::YI_L) = lo;
-    }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
-struct TcIssue {                 // state of the issuing lane
+struct TcIssue {                 // state of the issuing warp (warp-uniform values)
     uint32_t tmem, id_pos, id_neg, smem_base;
 };
 
@@ -268,6 +251,44 @@ __device__ __forceinline__ void tc_issue_stage(const TcIssue& q, int stage, int 
     umma_f16(d_im, xil, yrh, q.id_neg, 1u);
 }
 
+// one worker warp adds accumulator set `set` (its 32 TMEM lanes x its 32 columns, re and im) to
+// its register accumulators and hands the set back to the issuing lane
+__device__ __forceinline__ void tc_read_chain(uint64_t* tfull, uint64_t* tempty, int rc,
+                                              uint32_t ta0, float (&aR)[TC_CG], float (&aI)[TC_CG],
+                                              int lane) {
+    const int set = rc & 1;
+    mbar_wait_bounded(&tfull[set], (uint32_t)((rc >> 1) & 1));
+    tc_fence_after();
+    const uint32_t ta = ta0 + (uint32_t)(set * TC_SET_COLS);
+#pragma unroll
+    for (int g = 0; g < TC_CG / 8; ++g) {
+        uint32_t vr[8], vi[8];
+        tmem_ld8(ta + 8 * g, vr);
+        tmem_ld8(ta + TC_IM_COL + 8 * g, vi);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            aR[8 * g + c] += __uint_as_float(vr[c]);
+            aI[8 * g + c] += __uint_as_float(vi[c]);
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[set]);
+}
+
+// -------------------------------------------------------------------------------------
+// forward.  grid = (nitems * nfreq, nunits), block = 544.
+//   Acm      float [Nfp][S]     perceived sky, channel-major (row k = channel k over the packed
+//                                source axis): the 16 values of a stage are one 64-byte bulk copy
+//   items    int32 [nitems][4]  {i0, j0, N, 0}: X rows = antennas i0 .. i0 + 127, Y rows =
+//                                antennas j0 .. j0 + N - 1 (N a multiple of 32, <= 128)
+//   pair_bl  int32 [ldp][ldp]   (baseline << 1 | conj) of V_ij = sum conj(E_i) A E_j, or -1
+//   ascale   float [1]          power of two that brings max |A| into [2^14, 2^15)
+// Worker thread p: operand row (p & 255) >> 1, sources 4 kq .. 4 kq + 3 of the stage with
+// kq = 2 (p >> 8) + (p & 1) (pairs of lanes fill one 16-byte core-matrix row); accumulators: TMEM
+// lane quarter warp & 3, columns 32 (warp >> 2) .. + 31.
+// -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ ascale,
                      const double* __restrict__ shat, const double* __restrict__ antv,
@@ -292,30 +313,23 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcSmem::TMEM_OFF);
 
-    // producer warp w (0..7) owns operand rows 32 (w & 3) .. + 31 and sources 8 (w >> 2) .. + 7 of
-    // every stage; it takes part when one of its rows is a real antenna in either role
-    const int nx = min(TC_M, na - i0), ny = min(N, na - j0);      // live X / Y rows
-    int nactive = 0;
-#pragma unroll
-    for (int w = 0; w < TC_PROD_WARPS; ++w) nactive += (32 * (w & 3) < max(nx, ny)) ? 1 : 0;
-
-    // rows nobody writes must still hold finite numbers (their products land in rows / columns
-    // of the accumulator that are never stored)
+    // rows nobody writes (antennas beyond the array) must still hold finite numbers: their
+    // products land in rows / columns of the accumulator that are never stored
     for (int o = tid * 16; o < TC_NSTAGE * TcSmem::STAGE; o += TC_THREADS * 16)
         *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int st = 0; st < TC_NSTAGE; ++st) {
-            mbar_init(&full[st], nactive);
+            mbar_init(&full[st], TC_WORK_WARPS);
             mbar_init(&empty[st], 1);
         }
         for (int st = 0; st < TC_NSRC; ++st) mbar_init(&sfull[st], 1);
         for (int q = 0; q < 2; ++q) {
             mbar_init(&tfull[q], 1);
-            mbar_init(&tempty[q], TC_ACC_WARPS);
+            mbar_init(&tempty[q], TC_WORK_WARPS);
         }
         mbar_fence_init();
     }
-    if (warp == TC_ACC_WARPS) {
+    if (warp == TC_CTRL_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
                      "r"(TC_TMEM_COLS)
@@ -329,162 +343,113 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
     const uint32_t tmem = *tmem_slot;
     const float* Ak = Acm + (size_t)k * (size_t)S;
 
-    if (warp >= TC_ACC_WARPS) {
-        // ---------------- producers
-        setmaxnreg_dec<TC_PROD_REGS>();
-        const int pw = warp - TC_ACC_WARPS;
-        const int r = 32 * (pw & 3) + lane, hh = pw >> 2;
-        if (32 * (pw & 3) < max(nx, ny)) {
-            const bool xlive = r < nx, ylive = r < ny, diag = (i0 == j0);
-            const double kappa = sgn_over_c * freqs[k];
-            // antenna positions in cycles per unit direction cosine: phase = r' . shat
-            double xp[3] = {0.0, 0.0, 0.0}, yp[3] = {0.0, 0.0, 0.0};
-            if (xlive) {
-                const double* a = antv + 4 * (size_t)(i0 + r);
-                xp[0] = kappa * a[0], xp[1] = kappa * a[1], xp[2] = kappa * a[2];
-            }
-            if (ylive) {
-                const double* a = antv + 4 * (size_t)(j0 + r);
-                yp[0] = kappa * a[0], yp[1] = kappa * a[1], yp[2] = kappa * a[2];
-            }
-            const float sc = __ldg(ascale);
-            const int roff = (r >> 3) * 256 + hh * 128 + (r & 7) * 16;
-            for (int it = 0; it < nst; ++it) {
-                const int stage = it % TC_NSTAGE, slot = it % TC_NSRC;
-                mbar_wait_bounded(&sfull[slot], (uint32_t)((it / TC_NSRC) & 1));
-                const unsigned char* src = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
-                const double4* sh = reinterpret_cast<const double4*>(src) + hh * 8;
-                const float4* av = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT) + hh * 2;
-                const float4 a0 = av[0], a1 = av[1];
-                const float a[8] = {a0.x * sc, a0.y * sc, a0.z * sc, a0.w * sc,
-                                    a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc};
-#if B200_TC_PV == 1
-                if (it >= TC_NSTAGE)
-                    mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
-                unsigned char* row = smem + stage * TcSmem::STAGE + roff;
-                if (diag) tc_produce_rows<true>(row, sh, a, xp, yp, xlive, ylive);
-                else tc_produce_rows<false>(row, sh, a, xp, yp, xlive, ylive);
-#else
-                float cx[8], sx[8], cy[8], sy[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const double4 sv = sh[e];
-                    antenna_cis(__fma_rn(xp[0], sv.x, __fma_rn(xp[1], sv.y,
-                                __fma_rn(xp[2], sv.z, 1572864.0))), cx[e], sx[e]);
-                    if (diag) {
-                        cy[e] = cx[e];
-                        sy[e] = sx[e];
-                    } else {
-                        antenna_cis(__fma_rn(yp[0], sv.x, __fma_rn(yp[1], sv.y,
-                                    __fma_rn(yp[2], sv.z, 1572864.0))), cy[e], sy[e]);
-                    }
-                    cy[e] *= a[e];
-                    sy[e] *= a[e];
-                }
-                if (it >= TC_NSTAGE)
-                    mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
-                unsigned char* row = smem + stage * TcSmem::STAGE + roff;
-                uint4 hi, lo;
-                if (xlive) {
-                    split8(cx, hi, lo);
-                    *reinterpret_cast<uint4*>(row + TcSmem::XR_H) = hi;
-                    *reinterpret_cast<uint4*>(row + TcSmem::XR_L) = lo;
-                    split8(sx, hi, lo);
-                    *reinterpret_cast<uint4*>(row + TcSmem::XI_H) = hi;
-                    *reinterpret_cast<uint4*>(row + TcSmem::XI_L) = lo;
-                }
-                if (ylive) {
-                    split8(cy, hi, lo);
-                    *reinterpret_cast<uint4*>(row + TcSmem::YR_H) = hi;
-                    *reinterpret_cast<uint4*>(row + TcSmem::YR_L) = lo;
-                    split8(sy, hi, lo);
-                    *reinterpret_cast<uint4*>(row + TcSmem::YI_H) = hi;
-                    *reinterpret_cast<uint4*>(row + TcSmem::YI_L) = lo;
-                }
-#endif
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);
-            }
+    // ---------------- control duties (lane 0 of warp 0, one stage behind its own production):
+    // source staging by TMA and MMA issue
+    TcIssue iq;
+    iq.tmem = tmem;
+    iq.id_pos = umma_idesc_f16(N, false);
+    iq.id_neg = umma_idesc_f16(N, true);
+    iq.smem_base = smem_u32(smem);
+    auto stage_sources = [&](int st) {
+        const int slot = st % TC_NSRC;
+        unsigned char* dst = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
+        const long long s0 = (long long)un.y + (long long)st * TC_KS;
+        mbar_expect_tx(&sfull[slot], TcSmem::SRC_SLOT);
+        bulk_g2s(dst, shat + 4 * s0, TcSmem::SRC_SHAT, &sfull[slot]);
+        bulk_g2s(dst + TcSmem::SRC_SHAT, Ak + s0, TcSmem::SRC_A, &sfull[slot]);
+    };
+    auto control = [&](int it) {          // whole warp 0: issue the MMAs of stage it
+        const int stage = it % TC_NSTAGE, chain = it / TC_FLUSH, set = chain & 1;
+        const bool first = (it % TC_FLUSH) == 0;
+        if (first && chain >= 2)       // the set's previous chain has been read out
+            mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
+        mbar_wait_bounded(&full[stage], (uint32_t)((it / TC_NSTAGE) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+            tc_issue_stage(iq, stage, set, first);
+            umma_commit(&empty[stage]);       // stage free once these MMAs have read it
+            if ((it % TC_FLUSH) == TC_FLUSH - 1 || it == nst - 1) umma_commit(&tfull[set]);
+            // every worker has consumed the source slot of this stage: refill it
+            if (it + TC_NSRC < nst) stage_sources(it + TC_NSRC);
         }
-    } else {
-        // ---------------- accumulator warps: lane quarter q (TMEM lanes 32 q ..), column half h
-        setmaxnreg_inc<TC_ACC_REGS>();
-        const int q = warp & 3, h = warp >> 2;
-        float aR[64], aI[64];
+        __syncwarp();
+    };
+    const bool ctrl = __shfl_sync(0xffffffffu, warp, 0) == TC_CTRL_WARP;      // warp-uniform
+    if (ctrl && elect_one())
+        for (int st = 0; st < min(nst, TC_NSRC); ++st) stage_sources(st);
+    __syncwarp();
+    {
+        // ---------------- workers
+        const int kg = tid >> 8, row = (tid & 255) >> 1, kh = tid & 1, kq = 2 * kg + kh;
+        const int nx = min(TC_M, na - i0), ny = min(N, na - j0);      // live X / Y rows
+        const bool xlive = row < nx, ylive = row < ny, diag = (i0 == j0);
+        const double kappa = sgn_over_c * freqs[k];
+        // antenna positions in cycles per unit direction cosine: phase = r' . shat
+        double xp[3] = {0.0, 0.0, 0.0}, yp[3] = {0.0, 0.0, 0.0};
+        if (xlive) {
+            const double* a = antv + 4 * (size_t)(i0 + row);
+            xp[0] = kappa * a[0], xp[1] = kappa * a[1], xp[2] = kappa * a[2];
+        }
+        if (ylive) {
+            const double* a = antv + 4 * (size_t)(j0 + row);
+            yp[0] = kappa * a[0], yp[1] = kappa * a[1], yp[2] = kappa * a[2];
+        }
+        const float sc = __ldg(ascale);
+        const int roff = (row >> 3) * 256 + kg * 128 + (row & 7) * 16 + kh * 8;
+        const int q = warp & 3, cg = warp >> 2;
+        const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_CG * cg);
+        float aR[TC_CG], aI[TC_CG];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) aR[c] = aI[c] = 0.f;
-        const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * h);
-        TcIssue iq;
-        iq.tmem = tmem;
-        iq.id_pos = umma_idesc_f16(N, false);
-        iq.id_neg = umma_idesc_f16(N, true);
-        iq.smem_base = smem_u32(smem);
-        // source data of stage st -> slot st % TC_NSRC (issued by lane 0 of warp 0)
-        auto stage_sources = [&](int st) {
-            const int slot = st % TC_NSRC;
-            unsigned char* dst = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
-            const long long s0 = (long long)un.y + (long long)st * TC_KS;
-            mbar_expect_tx(&sfull[slot], TcSmem::SRC_SLOT);
-            bulk_g2s(dst, shat + 4 * s0, TcSmem::SRC_SHAT, &sfull[slot]);
-            bulk_g2s(dst + TcSmem::SRC_SHAT, Ak + s0, TcSmem::SRC_A, &sfull[slot]);
-        };
-        if (warp == 0 && lane == 0)
-            for (int st = 0; st < min(nst, TC_NSRC); ++st) stage_sources(st);
+        for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
+        int next_read = 0;
 
-        for (int chain = 0; chain <= nchain; ++chain) {
-            if (warp == 0 && chain < nchain) {
-                // ---- issue the MMAs of this chain (stages chain * TC_FLUSH ..)
-                const int set = chain & 1;
-                if (chain >= 2)                // the set's previous chain has been read out
-                    mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
-                const int it1 = min(nst, (chain + 1) * TC_FLUSH);
-                for (int it = chain * TC_FLUSH; it < it1; ++it) {
-                    const int stage = it % TC_NSTAGE;
-                    mbar_wait_bounded(&full[stage], (uint32_t)((it / TC_NSTAGE) & 1));
-                    tc_fence_after();
-                    if (lane == 0) {
-                        tc_issue_stage(iq, stage, set, it == chain * TC_FLUSH);
-                        umma_commit(&empty[stage]);   // stage free once these MMAs have read it
-                        if (it == it1 - 1) umma_commit(&tfull[set]);
-                        // every producer has consumed the source slot of this stage: refill it
-                        if (it + TC_NSRC < nst) stage_sources(it + TC_NSRC);
-                    }
-                    __syncwarp();
-                }
-            }
-            // ---- read out the previous chain (warp 0: while the tensor core works on this one)
-            const int rc = warp == 0 ? chain - 1 : chain;
-            if (rc < 0 || rc >= nchain) continue;
-            const int set = rc & 1;
-            mbar_wait_bounded(&tfull[set], (uint32_t)((rc >> 1) & 1));
-            tc_fence_after();
-            const uint32_t ta = ta0 + (uint32_t)(set * TC_SET_COLS);
+        for (int it = 0; it < nst; ++it) {
+            if ((it % TC_FLUSH) == 0)
+                while (next_read <= it / TC_FLUSH - 2)
+                    tc_read_chain(tfull, tempty, next_read++, ta0, aR, aI, lane);
+            const int stage = it % TC_NSTAGE, slot = it % TC_NSRC;
+            mbar_wait_bounded(&sfull[slot], (uint32_t)((it / TC_NSRC) & 1));
+            const unsigned char* src = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
+            const double4* sh = reinterpret_cast<const double4*>(src) + 4 * kq;
+            const float4 av = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT)[kq];
+            float c[4], s[4];
+            if (xlive || (diag && ylive)) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                uint32_t vr[8], vi[8];
-                tmem_ld8(ta + 8 * g, vr);
-                tmem_ld8(ta + TC_IM_COL + 8 * g, vi);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    aR[8 * g + c] += __uint_as_float(vr[c]);
-                    aI[8 * g + c] += __uint_as_float(vi[c]);
-                }
+                for (int e = 0; e < 4; ++e) antenna_cis(phase_fma(xp, sh[e]), c[e], s[e]);
             }
-            tc_fence_before();
+            if (it >= TC_NSTAGE)
+                mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
+            unsigned char* dst = smem + stage * TcSmem::STAGE + roff;
+            if (xlive) store_split(dst + TcSmem::XR_H, c, s);
+            if (ylive) {
+                if (!diag) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) antenna_cis(phase_fma(yp, sh[e]), c[e], s[e]);
+                }
+                const float a[4] = {av.x * sc, av.y * sc, av.z * sc, av.w * sc};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    c[e] *= a[e];
+                    s[e] *= a[e];
+                }
+                store_split(dst + TcSmem::YR_H, c, s);
+            }
+            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[set]);
+            if (lane == 0) mbar_arrive(&full[stage]);
+            if (ctrl && it > 0) control(it - 1);
         }
+        if (ctrl) control(nst - 1);
+        while (next_read < nchain) tc_read_chain(tfull, tempty, next_read++, ta0, aR, aI, lane);
+
         // ---- scatter through the pair table
         const int ai = i0 + 32 * q + lane;
-        if (ai < na) {
-            const float inv = 1.f / __ldg(ascale);
+        if (ai < na && TC_CG * cg < N) {
+            const float inv = 1.f / sc;
             float2* vp = reinterpret_cast<float2*>(vpart) + (size_t)blockIdx.y * (size_t)nbl * nfp + k;
-            const int* pb = pair_bl + (size_t)ai * ldp + j0 + 64 * h;
+            const int* pb = pair_bl + (size_t)ai * ldp + j0 + TC_CG * cg;
 #pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) {
-                if (64 * h + 4 * c4 >= N) break;
+            for (int c4 = 0; c4 < TC_CG / 4; ++c4) {
                 const int4 e4 = __ldg(reinterpret_cast<const int4*>(pb) + c4);
                 const int e[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
@@ -499,7 +464,7 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_ACC_WARPS) {
+    if (warp == TC_CTRL_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                      "r"(TC_TMEM_COLS)
                      : "memory");
@@ -507,34 +472,36 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
 }
 
 // -------------------------------------------------------------------------------------
-// backward.  grid = (nunits, nitem * nfreq), block = 512 (units fastest: CTAs that run together
+// backward.  grid = (nunits, nitem * nfreq), block = 544 (units fastest: CTAs that run together
 // share the cotangent operand of their (antenna block, channel) through L2).
 //
 // With the Hermitian cotangent matrix H[a][m] (ant_kernels.cu) the adjoints are
 //   y_a[s] = sum_m H[a][m] E_m[s],  p = conj(E_a[s]) y_a[s],
 //   dL/dA[s] = 1/2 sum_a Re p,      dL/dr_a = sum_s shat_s A_s (2 pi sgn nu / c) Im p.
-// y is a GEMM with M = sources (tiles of 128), N = antennas a (items of at most 128), K = partner
-// antennas m: the A operand E_m[s] is generated in shared memory (thread <-> source row, 8 of the
+// y is a GEMM with M = sources (tiles of 128), N = antennas a (items of 128), K = partner antennas
+// m: the A operand E_m[s] is generated in shared memory (worker thread <-> source row, 4 of the
 // 16 antennas of a stage), the B operand H is fetched by TMA from a copy the host has scaled,
 // split into float16 hi / lo parts and laid out in the UMMA canonical order
 //   Hq[t][k][item][stage of 16 m][re_hi | re_lo | im_hi | im_lo][128 rows a x 16 m, canonical].
 // Chains of TC_FLUSH stages are added to register accumulators as in the forward kernel; after
-// the last stage of a source tile the accumulator warps regenerate E_a for their 64 antennas,
-// form p and reduce: dL/dA over the thread's own columns (one float per source, written
-// channel-major, partial per (item, column half)), dL/dr over the 32 sources of the warp with a
-// transposed shuffle reduction (lane <-> antenna), accumulated over the tiles of the unit.
+// the last chain of a source tile every worker regenerates E_a for its source and its 32 antennas,
+// forms p and reduces: dL/dA over its columns, then across the four column groups in a fixed
+// order through shared memory (one float per source and channel, written channel-major); dL/dr
+// over the 32 sources of the warp with a transposed shuffle reduction (lane <-> antenna),
+// accumulated over the tiles of the unit.
 //   mrange [nitem][2]: stages of 16 partner antennas [lo, hi) that hold cotangent entries for the
 //   item.  When only dL/dA is wanted H is the doubled lower triangle (a > m) and item ib stops
 //   after its own antennas; a baseline group that covers only some antenna blocks skips the
 //   stages it leaves empty.
-//   dAcm   [nitem * 2][Nfp][S]                 partial dL/dA, channel-major (sum over axis 0)
+//   dAcm   [nitem][Nfp][S]                     partial dL/dA, channel-major (sum over axis 0)
 //   drpart [nunits][Nfp][4][nitem * 128][4]    partial dL/dr (float32; sum over the first three)
 // -------------------------------------------------------------------------------------
 struct TcBwdSmem {
     static constexpr int POS_MAX = 512;                        // antennas the position table holds
     static constexpr int POS_OFF = TC_NSTAGE * TcSmem::STAGE;  // [POS_MAX][4] float64, kappa-scaled
+    static constexpr int RED_OFF = POS_OFF + POS_MAX * 32;     // [2][4 column groups][128] float
     // full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2]
-    static constexpr int BAR_OFF = POS_OFF + POS_MAX * 32;
+    static constexpr int BAR_OFF = RED_OFF + 2 * 4 * TC_M * 4;
     static constexpr int TMEM_OFF = BAR_OFF + (2 * TC_NSTAGE + 4) * 8;
     static constexpr int TOTAL = TMEM_OFF + 16;
     static constexpr int H_BYTES = 4 * TcSmem::ARR;            // one stage of the cotangent operand
@@ -593,7 +560,7 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     const int4 un = units[blockIdx.x];
     const int a0 = ai * TC_M;
     // all 128 columns are computed: the operand rows of antennas >= na are zero, so are their
-    // sums, and the epilogue needs no column mask (the MMAs are not the bottleneck)
+    // sums, and the epilogue needs no column mask
     const int N = TC_NMAX;
     const int nmst_all = nm_pad / TC_KS;
     const int2 mr = mrange[ai];
@@ -602,6 +569,7 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     if (ntile <= 0 || nmst <= 0) return;        // nothing to add: dAcm / drpart were zeroed
     const int nct = (nmst + TC_FLUSH - 1) / TC_FLUSH;                 // chains per source tile
     const int nchain = ntile * nct;
+    const int nst = ntile * nmst;                                     // stages of this CTA
 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TcBwdSmem::BAR_OFF);
     uint64_t* empty = full + TC_NSTAGE;
@@ -609,6 +577,7 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcBwdSmem::TMEM_OFF);
     double4* pos = reinterpret_cast<double4*>(smem + TcBwdSmem::POS_OFF);
+    float* red = reinterpret_cast<float*>(smem + TcBwdSmem::RED_OFF);
     const double kappa = sgn_over_c * freqs[k];
 
     for (int o = tid * 16; o < TC_NSTAGE * TcSmem::STAGE; o += TC_THREADS * 16)
@@ -624,16 +593,16 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     }
     if (tid == 0) {
         for (int st = 0; st < TC_NSTAGE; ++st) {
-            mbar_init(&full[st], TC_PROD_WARPS + 1);     // producer warps + the TMA's expect_tx
+            mbar_init(&full[st], TC_WORK_WARPS + 1);     // worker warps + the TMA's expect_tx
             mbar_init(&empty[st], 1);
         }
         for (int q = 0; q < 2; ++q) {
             mbar_init(&tfull[q], 1);
-            mbar_init(&tempty[q], TC_ACC_WARPS);
+            mbar_init(&tempty[q], TC_WORK_WARPS);
         }
         mbar_fence_init();
     }
-    if (warp == TC_ACC_WARPS) {
+    if (warp == TC_CTRL_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
                      "r"(TC_TMEM_COLS)
@@ -646,176 +615,150 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= TC_ACC_WARPS) {
-        // ---------------- producers: thread <-> source row r of the tile, antennas 8 hh .. + 7
-        setmaxnreg_dec<TC_PROD_REGS>();
-        const int pw = warp - TC_ACC_WARPS;
-        const int r = 32 * (pw & 3) + lane, hh = pw >> 2;
-        const int roff = (r >> 3) * 256 + hh * 128 + (r & 7) * 16;
+    // ---------------- control duties (lane 0 of warp 0, one stage behind its own production)
+    TcIssue iq;
+    iq.tmem = tmem;
+    iq.id_pos = umma_idesc_f16(N, false);
+    iq.id_neg = umma_idesc_f16(N, true);
+    iq.smem_base = smem_u32(smem);
+    auto control = [&](int g) {           // whole warp 0: issue the MMAs of stage g = tile * nmst + ms
+        const int tile = g / nmst, ms = g - tile * nmst;
+        const int stage = g % TC_NSTAGE;
+        const int chain = tile * nct + ms / TC_FLUSH, set = chain & 1;
+        const bool first = (ms % TC_FLUSH) == 0;
+        if (first && chain >= 2)
+            mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
+        mbar_wait_bounded(&full[stage], (uint32_t)((g / TC_NSTAGE) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+            tc_issue_stage_bwd(iq, stage, set, first);
+            umma_commit(&empty[stage]);
+            if ((ms % TC_FLUSH) == TC_FLUSH - 1 || ms == nmst - 1) umma_commit(&tfull[set]);
+        }
+        __syncwarp();
+    };
+    const bool ctrl = __shfl_sync(0xffffffffu, warp, 0) == TC_CTRL_WARP;      // warp-uniform
+    {
+        // ---------------- workers: operand row = source (tid & 255) >> 1 of the tile, partner
+        // antennas 4 kq .. 4 kq + 3 of the stage; accumulators: sources 32 q .., antennas 32 cg ..
+        const int kg = tid >> 8, row = (tid & 255) >> 1, kh = tid & 1, kq = 2 * kg + kh;
+        const int roff = (row >> 3) * 256 + kg * 128 + (row & 7) * 16 + kh * 8;
+        const int q = warp & 3, cg = warp >> 2;
+        const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_CG * cg);
         const unsigned char* Hbase = Hq + ((((size_t)un.x * nfp + k) * nitem + ai) * (size_t)nmst_all + mlo) *
                                               TcBwdSmem::H_BYTES;
-        long long g = 0;
-        for (int tile = 0; tile < ntile; ++tile) {
-            const long long s = (long long)un.y + (long long)tile * TC_M + r;
-            const bool valid = s < un.z;
-            double sx = 0.0, sy = 0.0, sz = 0.0;
-            if (valid) {
-                const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
-                sx = s01.x, sy = s01.y, sz = __ldg(shat + 4 * s + 2);
-            }
-            for (int ms = 0; ms < nmst; ++ms, ++g) {
-                const int stage = (int)(g % TC_NSTAGE);
-                unsigned char* sbase = smem + stage * TcSmem::STAGE;
-                if (pw == 0) {
-                    // this warp also fetches the cotangent operand of the stage
-                    if (g >= TC_NSTAGE)
-                        mbar_wait_bounded(&empty[stage], (uint32_t)(((g / TC_NSTAGE) - 1) & 1));
-                    if (lane == 0) {
-                        mbar_expect_tx(&full[stage], TcBwdSmem::H_BYTES);
-                        bulk_g2s(sbase + TcSmem::YR_H, Hbase + (size_t)ms * TcBwdSmem::H_BYTES,
-                                 TcBwdSmem::H_BYTES, &full[stage]);
-                    }
-                }
-                float c[8], sn[8];
-                const double4* pm = pos + (mlo + ms) * TC_KS + hh * 8;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const double4 p = pm[e];
-                    antenna_cis(__fma_rn(p.x, sx, __fma_rn(p.y, sy, __fma_rn(p.z, sz, 1572864.0))),
-                                c[e], sn[e]);
-                    if (!valid) c[e] = sn[e] = 0.f;
-                }
-                if (pw != 0 && g >= TC_NSTAGE)
-                    mbar_wait_bounded(&empty[stage], (uint32_t)(((g / TC_NSTAGE) - 1) & 1));
-                uint4 hi, lo;
-                split8(c, hi, lo);
-                *reinterpret_cast<uint4*>(sbase + roff + TcSmem::XR_H) = hi;
-                *reinterpret_cast<uint4*>(sbase + roff + TcSmem::XR_L) = lo;
-                split8(sn, hi, lo);
-                *reinterpret_cast<uint4*>(sbase + roff + TcSmem::XI_H) = hi;
-                *reinterpret_cast<uint4*>(sbase + roff + TcSmem::XI_L) = lo;
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);
-            }
-        }
-    } else {
-        // ---------------- accumulator warps: lane quarter q (source rows 32 q ..), column half h
-        setmaxnreg_inc<TC_ACC_REGS>();
-        const int q = warp & 3, h = warp >> 2;
-        float aR[64], aI[64];
-#pragma unroll
-        for (int c = 0; c < 64; ++c) aR[c] = aI[c] = 0.f;
-        float gr[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-        const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * h);
-        TcIssue iq;
-        iq.tmem = tmem;
-        iq.id_pos = umma_idesc_f16(N, false);
-        iq.id_neg = umma_idesc_f16(N, true);
-        iq.smem_base = smem_u32(smem);
         const float inv_h = 1.f / __ldg(hscale);
         const float kf = (float)(kappa * 6.283185307179586476925286766559);
+        float aR[TC_CG], aI[TC_CG];
+#pragma unroll
+        for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
+        float gr[3] = {0.f, 0.f, 0.f};
+        int next_read = 0;
 
-        for (int chain = 0; chain <= nchain; ++chain) {
-            if (warp == 0 && chain < nchain) {
-                // ---- issue the MMAs of this chain
-                const int set = chain & 1;
-                if (chain >= 2)
-                    mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
-                const int tile = chain / nct, ms0 = (chain % nct) * TC_FLUSH;
-                const int ms1 = min(nmst, ms0 + TC_FLUSH);
-                for (int ms = ms0; ms < ms1; ++ms) {
-                    const long long g = (long long)tile * nmst + ms;
-                    const int stage = (int)(g % TC_NSTAGE);
-                    mbar_wait_bounded(&full[stage], (uint32_t)((g / TC_NSTAGE) & 1));
-                    tc_fence_after();
-                    if (lane == 0) {
-                        tc_issue_stage_bwd(iq, stage, set, ms == ms0);
-                        umma_commit(&empty[stage]);
-                        if (ms == ms1 - 1) umma_commit(&tfull[set]);
-                    }
-                    __syncwarp();
-                }
-            }
-            const int rc = warp == 0 ? chain - 1 : chain;
-            if (rc < 0 || rc >= nchain) continue;
-            {
-                const int set = rc & 1;
-                mbar_wait_bounded(&tfull[set], (uint32_t)((rc >> 1) & 1));
-                tc_fence_after();
-                const uint32_t ta = ta0 + (uint32_t)(set * TC_SET_COLS);
-#pragma unroll
-                for (int g8 = 0; g8 < 8; ++g8) {
-                    uint32_t vr[8], vi[8];
-                    tmem_ld8(ta + 8 * g8, vr);
-                    tmem_ld8(ta + TC_IM_COL + 8 * g8, vi);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        aR[8 * g8 + c] += __uint_as_float(vr[c]);
-                        aI[8 * g8 + c] += __uint_as_float(vi[c]);
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[set]);
-            }
-            if (rc % nct != nct - 1) continue;
-            // ---- source tile complete: p = conj(E_a) y_a for this thread's source and 64 antennas
+        // chain rc -> registers; after the last chain of a source tile: the tile's epilogue
+        auto read_chain = [&](int rc) {
+            tc_read_chain(tfull, tempty, rc, ta0, aR, aI, lane);
+            if (rc % nct != nct - 1) return;
             const int tile = rc / nct;
             const long long s = (long long)un.y + (long long)tile * TC_M + 32 * q + lane;
             const bool valid = s < un.z;
-            double sx = 0.0, sy = 0.0, sz = 0.0;
+            double sv[3] = {0.0, 0.0, 0.0};
             float wk = 0.f;
             if (valid) {
                 const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
-                sx = s01.x, sy = s01.y, sz = __ldg(shat + 4 * s + 2);
+                sv[0] = s01.x, sv[1] = s01.y, sv[2] = __ldg(shat + 4 * s + 2);
                 if (need_r) wk = __ldg(Acm + (size_t)k * (size_t)S + s) * kf * inv_h;
             }
-            const float fx = (float)sx, fy = (float)sy, fz = (float)sz;
             float dacc = 0.f;
+            const double4* pa = pos + a0 + TC_CG * cg;
 #pragma unroll
-            for (int grp = 0; grp < 2; ++grp) {
-                float w[32];
-                const double4* pa = pos + a0 + 64 * h + 32 * grp;
+            for (int c = 0; c < TC_CG; ++c) {
+                const double4 p = pa[c];
+                float cs, sn;
+                antenna_cis(__fma_rn(p.x, sv[0], __fma_rn(p.y, sv[1], __fma_rn(p.z, sv[2], 1572864.0))),
+                            cs, sn);
+                const float yr = aR[c], yi = aI[c];
+                dacc = fmaf(cs, yr, fmaf(sn, yi, dacc));            // Re(conj(E) y)
+                aR[c] = wk * fmaf(cs, yi, -sn * yr);                // A kappa 2 pi Im(conj(E) y)
+            }
+            if (need_r) {
+                const float fx = (float)sv[0], fy = (float)sv[1], fz = (float)sv[2];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const double4 p = pa[c];
-                    float cs, sn;
-                    antenna_cis(__fma_rn(p.x, sx, __fma_rn(p.y, sy, __fma_rn(p.z, sz, 1572864.0))),
-                                cs, sn);
-                    const float yr = aR[32 * grp + c], yi = aI[32 * grp + c];
-                    dacc = fmaf(cs, yr, fmaf(sn, yi, dacc));            // Re(conj(E) y)
-                    w[c] = wk * fmaf(cs, yi, -sn * yr);                 // A kappa 2 pi Im(conj(E) y)
-                    aR[32 * grp + c] = 0.f;
-                    aI[32 * grp + c] = 0.f;
-                }
-                if (need_r) {
-                    float v[32];
+                for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fx;
+                gr[0] += warp_reduce_scatter32(aI, lane);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = w[c] * fx;
-                    gr[grp][0] += warp_reduce_scatter32(v, lane);
+                for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fy;
+                gr[1] += warp_reduce_scatter32(aI, lane);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = w[c] * fy;
-                    gr[grp][1] += warp_reduce_scatter32(v, lane);
+                for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fz;
+                gr[2] += warp_reduce_scatter32(aI, lane);
+            }
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = w[c] * fz;
-                    gr[grp][2] += warp_reduce_scatter32(v, lane);
+            for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
+            if (need_a) {
+                // sum over the four column groups in a fixed order (deterministic)
+                float* rb = red + (tile & 1) * 4 * TC_M;
+                rb[cg * TC_M + 32 * q + lane] = dacc;
+                named_bar_sync(1, TC_WORKERS);
+                if (cg == 0 && valid) {
+                    const float* r4 = rb + 32 * q + lane;
+                    const float tot = ((r4[0] + r4[TC_M]) + r4[2 * TC_M]) + r4[3 * TC_M];
+                    dAcm[((size_t)ai * nfp + k) * (size_t)S + s] = 0.5f * tot * inv_h;
                 }
             }
-            if (need_a && valid)
-                dAcm[((size_t)(ai * 2 + h) * nfp + k) * (size_t)S + s] = 0.5f * dacc * inv_h;
+        };
+
+        int g = 0;
+        for (int tile = 0; tile < ntile; ++tile) {
+            const long long s = (long long)un.y + (long long)tile * TC_M + row;
+            const bool valid = s < un.z;
+            double sv[3] = {0.0, 0.0, 0.0};
+            if (valid) {
+                const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
+                sv[0] = s01.x, sv[1] = s01.y, sv[2] = __ldg(shat + 4 * s + 2);
+            }
+            for (int ms = 0; ms < nmst; ++ms, ++g) {
+                if ((ms % TC_FLUSH) == 0) {
+                    const int chain = tile * nct + ms / TC_FLUSH;
+                    while (next_read <= chain - 2) read_chain(next_read++);
+                }
+                const int stage = g % TC_NSTAGE;
+                unsigned char* sbase = smem + stage * TcSmem::STAGE;
+                float c[4], sn[4];
+                const double4* pm = pos + (mlo + ms) * TC_KS + 4 * kq;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double4 p = pm[e];
+                    antenna_cis(__fma_rn(p.x, sv[0], __fma_rn(p.y, sv[1], __fma_rn(p.z, sv[2], 1572864.0))),
+                                c[e], sn[e]);
+                    if (!valid) c[e] = sn[e] = 0.f;
+                }
+                if (g >= TC_NSTAGE)
+                    mbar_wait_bounded(&empty[stage], (uint32_t)(((g / TC_NSTAGE) - 1) & 1));
+                if (tid == 0) {
+                    // this thread also fetches the cotangent operand of the stage
+                    mbar_expect_tx(&full[stage], TcBwdSmem::H_BYTES);
+                    bulk_g2s(sbase + TcSmem::YR_H, Hbase + (size_t)ms * TcBwdSmem::H_BYTES,
+                             TcBwdSmem::H_BYTES, &full[stage]);
+                }
+                store_split(sbase + roff + TcSmem::XR_H, c, sn);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+                if (ctrl && g > 0) control(g - 1);
+            }
         }
+        if (ctrl) control(nst - 1);
+        while (next_read < nchain) read_chain(next_read++);
         if (need_r) {
             float4* dst = reinterpret_cast<float4*>(drpart) +
-                          (((size_t)blockIdx.x * nfp + k) * 4 + q) * (size_t)(nitem * TC_M) + a0 + 64 * h;
-            dst[lane] = make_float4(gr[0][0], gr[0][1], gr[0][2], 0.f);
-            dst[32 + lane] = make_float4(gr[1][0], gr[1][1], gr[1][2], 0.f);
+                          (((size_t)blockIdx.x * nfp + k) * 4 + q) * (size_t)(nitem * TC_M) + a0 + TC_CG * cg;
+            dst[lane] = make_float4(gr[0], gr[1], gr[2], 0.f);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_ACC_WARPS) {
+    if (warp == TC_CTRL_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                      "r"(TC_TMEM_COLS)
                      : "memory");
@@ -834,10 +777,6 @@ int launch_tc_fwd(const float* Acm, const float* ascale, const double* shat, con
     if (gx > 2147483647LL || nunits > 65535) return set_error("tcfringe_fwd: grid too large");
     static DeviceOnce attr_once;
     if (attr_once.first()) {
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, tc_fringe_fwd_kernel) != cudaSuccess ||
-            fa.numRegs * TC_THREADS < 256 * (TC_ACC_REGS + TC_PROD_REGS))
-            return set_error("tcfringe_fwd: register pool smaller than the setmaxnreg plan");
         if (cudaFuncSetAttribute(tc_fringe_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  TcSmem::TOTAL) != cudaSuccess)
             return set_error("tcfringe_fwd: cannot reserve shared memory");
@@ -866,10 +805,6 @@ int launch_tc_bwd(const void* Hq, const float* hscale, const float* Acm, const d
     if (gy > 65535) return set_error("tcfringe_bwd: grid too large");
     static DeviceOnce attr_once;
     if (attr_once.first()) {
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, tc_fringe_bwd_kernel) != cudaSuccess ||
-            fa.numRegs * TC_THREADS < 256 * (TC_ACC_REGS + TC_PROD_REGS))
-            return set_error("tcfringe_bwd: register pool smaller than the setmaxnreg plan");
         if (cudaFuncSetAttribute(tc_fringe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  TcBwdSmem::TOTAL) != cudaSuccess)
             return set_error("tcfringe_bwd: cannot reserve shared memory");

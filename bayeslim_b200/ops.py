@@ -1020,7 +1020,7 @@ def _tc_backward(G, A, antv, geom, freqs64, nfreq, conj, tc, ashape, need_A, nee
         tstep = max(1, TC_H_BUDGET // per_time)
         G = G.contiguous()
         for p in range(nplane):
-            dAcm = (torch.zeros(tc.nitem_bwd * 2, nfp, S, dtype=torch.float32, device=dev)
+            dAcm = (torch.zeros(tc.nitem_bwd, nfp, S, dtype=torch.float32, device=dev)
                     if need_A else None)
             acm = A[p].permute(0, 2, 1).reshape(nfp, S).contiguous() if need_r else None
             for ta in range(0, nt, tstep):

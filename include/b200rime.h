@@ -326,7 +326,7 @@ int b200rime_tcfringe_fwd_f32(const float* Acm, const float* ascale, const doubl
  *   nitem = ceil(na / 128), nm_pad = na rounded up to 16, na <= 512
  *   mrange  int32 [nitem][2]   stages of 16 partner antennas [lo, hi) that hold entries of H for
  *           the item (all stages: {0, nm_pad / 16}; lower triangle: item ib ends at 8 (ib + 1))
- *   dAcm    float [nitem * 2][Nfp][S]   partial dL/dA, channel-major; ZERO before the call
+ *   dAcm    float [nitem][Nfp][S]       partial dL/dA, channel-major; ZERO before the call
  *           (padding sources and channels are not written); sum over the first axis; or NULL
  *   drpart  float [nunits][Nfp][4][nitem * 128][4]   partial dL/dr; sum over the first three
  *           axes; or NULL */

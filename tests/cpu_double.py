@@ -313,8 +313,8 @@ def tcfringe_bwd(sfx, Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, 
         y = torch.einsum('fam,mfs->afs', Ht, E[:nm_pad])
         p = E.conj() * y
         if dAcm is not None:
-            half = 0.5 * p.real.reshape(nitem, 2, M // 2, nfreq, s1 - s0).sum(2)   # (item, h, f, s)
-            dAcm[:, :nfreq, s0:s1] = half.reshape(nitem * 2, nfreq, s1 - s0).to(dAcm.dtype)
+            part = 0.5 * p.real.reshape(nitem, M, nfreq, s1 - s0).sum(1)            # (item, f, s)
+            dAcm[:, :nfreq, s0:s1] = part.to(dAcm.dtype)
         if drpart is not None:
             w = p.imag * (Acm[:nfreq, s0:s1].double() * freqs.double()[:nfreq, None])[None]
             g = torch.einsum('afs,sc->fac', w, shat[s0:s1, :3].double())
