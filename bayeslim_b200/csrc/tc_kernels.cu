@@ -58,9 +58,10 @@ constexpr int TC_KS = 16;            // sources per stage = one kind::f16 UMMA K
 constexpr int TC_NSTAGE = 6;         // operand stages
 constexpr int TC_NSRC = 8;           // source-data slots (staged TC_NSRC stages ahead)
 constexpr int TC_FLUSH = B200_TC_FLUSH;
-constexpr int TC_WORK_WARPS = 16;    // warps 0..15: operand generation AND register accumulators
+constexpr int TC_WORK_WARPS = 16;    // every warp holds a (lane quarter x 32 columns) slice of the accumulators
 constexpr int TC_WORKERS = TC_WORK_WARPS * 32;
-constexpr int TC_CTRL_WARP = 0;      // its lane 0 also stages the sources (TMA) and issues the MMAs
+constexpr int TC_CTRL_WARP = 0;      // stages the sources (TMA) and issues the MMAs (warps 1..3: read-out only)
+constexpr int TC_GROUPS = 3;         // warps 4..15 = three groups of four; group g generates stages it = g (mod 3)
 constexpr int TC_THREADS = TC_WORKERS;            // 512 threads x 128 registers = the register file
 constexpr int TC_KC = B200_KC_F32;
 constexpr int TC_TMEM_COLS = 512;    // two accumulator sets of (re, im) x 128 columns
@@ -210,6 +211,36 @@ __device__ __forceinline__ void store_split(unsigned char* dst, const float (&c)
     *reinterpret_cast<uint2*>(dst + 3 * TcSmem::ARR) = lo;
 }
 
+// hi / lo split of 8 values -> two 16-byte core-matrix rows
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    const float a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
+    uint2 h0, l0, h1, l1;
+    split4(a, h0, l0);
+    split4(b, h1, l1);
+    hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+// (cos, sin) of 8 sources -> the four arrays (re_hi, re_lo, im_hi, im_lo) of one operand row
+__device__ __forceinline__ void store_split8(unsigned char* dst, const float (&c)[8], const float (&s)[8]) {
+    uint4 hi, lo;
+    split8(c, hi, lo);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + TcSmem::ARR) = lo;
+    split8(s, hi, lo);
+    *reinterpret_cast<uint4*>(dst + 2 * TcSmem::ARR) = hi;
+    *reinterpret_cast<uint4*>(dst + 3 * TcSmem::ARR) = lo;
+}
+// phase of 8 sources (float64 unit vectors at sh, 32 bytes apart) for the antenna position p
+__device__ __forceinline__ void cis8(const double (&p)[3], const unsigned char* sh, float (&c)[8],
+                                     float (&s)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const double2 xy = *reinterpret_cast<const double2*>(sh + 32 * e);
+        const double z = *reinterpret_cast<const double*>(sh + 32 * e + 16);
+        antenna_cis(__fma_rn(p[0], xy.x, __fma_rn(p[1], xy.y, __fma_rn(p[2], z, 1572864.0))), c[e], s[e]);
+    }
+}
+
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -319,7 +350,7 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
         *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int st = 0; st < TC_NSTAGE; ++st) {
-            mbar_init(&full[st], TC_WORK_WARPS);
+            mbar_init(&full[st], 4);                  // the four warps of the generating group
             mbar_init(&empty[st], 1);
         }
         for (int st = 0; st < TC_NSRC; ++st) mbar_init(&sfull[st], 1);
@@ -343,103 +374,109 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
     const uint32_t tmem = *tmem_slot;
     const float* Ak = Acm + (size_t)k * (size_t)S;
 
-    // ---------------- control duties (lane 0 of warp 0, one stage behind its own production):
-    // source staging by TMA and MMA issue
-    TcIssue iq;
-    iq.tmem = tmem;
-    iq.id_pos = umma_idesc_f16(N, false);
-    iq.id_neg = umma_idesc_f16(N, true);
-    iq.smem_base = smem_u32(smem);
-    auto stage_sources = [&](int st) {
-        const int slot = st % TC_NSRC;
-        unsigned char* dst = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
-        const long long s0 = (long long)un.y + (long long)st * TC_KS;
-        mbar_expect_tx(&sfull[slot], TcSmem::SRC_SLOT);
-        bulk_g2s(dst, shat + 4 * s0, TcSmem::SRC_SHAT, &sfull[slot]);
-        bulk_g2s(dst + TcSmem::SRC_SHAT, Ak + s0, TcSmem::SRC_A, &sfull[slot]);
-    };
-    auto control = [&](int it) {          // whole warp 0: issue the MMAs of stage it
-        const int stage = it % TC_NSTAGE, chain = it / TC_FLUSH, set = chain & 1;
-        const bool first = (it % TC_FLUSH) == 0;
-        if (first && chain >= 2)       // the set's previous chain has been read out
-            mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
-        mbar_wait_bounded(&full[stage], (uint32_t)((it / TC_NSTAGE) & 1));
-        tc_fence_after();
-        if (elect_one()) {
-            tc_issue_stage(iq, stage, set, first);
-            umma_commit(&empty[stage]);       // stage free once these MMAs have read it
-            if ((it % TC_FLUSH) == TC_FLUSH - 1 || it == nst - 1) umma_commit(&tfull[set]);
-            // every worker has consumed the source slot of this stage: refill it
-            if (it + TC_NSRC < nst) stage_sources(it + TC_NSRC);
-        }
-        __syncwarp();
-    };
-    const bool ctrl = __shfl_sync(0xffffffffu, warp, 0) == TC_CTRL_WARP;      // warp-uniform
-    if (ctrl && elect_one())
-        for (int st = 0; st < min(nst, TC_NSRC); ++st) stage_sources(st);
-    __syncwarp();
-    {
-        // ---------------- workers
-        const int kg = tid >> 8, row = (tid & 255) >> 1, kh = tid & 1, kq = 2 * kg + kh;
-        const int nx = min(TC_M, na - i0), ny = min(N, na - j0);      // live X / Y rows
-        const bool xlive = row < nx, ylive = row < ny, diag = (i0 == j0);
-        const double kappa = sgn_over_c * freqs[k];
-        // antenna positions in cycles per unit direction cosine: phase = r' . shat
-        double xp[3] = {0.0, 0.0, 0.0}, yp[3] = {0.0, 0.0, 0.0};
-        if (xlive) {
-            const double* a = antv + 4 * (size_t)(i0 + row);
-            xp[0] = kappa * a[0], xp[1] = kappa * a[1], xp[2] = kappa * a[2];
-        }
-        if (ylive) {
-            const double* a = antv + 4 * (size_t)(j0 + row);
-            yp[0] = kappa * a[0], yp[1] = kappa * a[1], yp[2] = kappa * a[2];
-        }
-        const float sc = __ldg(ascale);
-        const int roff = (row >> 3) * 256 + kg * 128 + (row & 7) * 16 + kh * 8;
-        const int q = warp & 3, cg = warp >> 2;
-        const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_CG * cg);
-        float aR[TC_CG], aI[TC_CG];
+    // warp roles: q = TMEM lane quarter (and operand rows 32 q ..), cg = accumulator column group;
+    // warp 0 = control, warps 1..3 read-out only, warps 4..15 = generating groups cg - 1
+    const int q = warp & 3, cg = warp >> 2;
+    const int role = __shfl_sync(0xffffffffu, warp, 0);              // warp-uniform warp index
+    const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_CG * cg);
+    const float sc = __ldg(ascale);
+    float aR[TC_CG], aI[TC_CG];
 #pragma unroll
-        for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
-        int next_read = 0;
-
-        for (int it = 0; it < nst; ++it) {
-            if ((it % TC_FLUSH) == 0)
+    for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
+    int next_read = 0;
+    {
+        if (role == TC_CTRL_WARP) {
+            // ---------------- control warp: source staging by TMA, MMA issue (uniform datapath)
+            TcIssue iq;
+            iq.tmem = tmem;
+            iq.id_pos = umma_idesc_f16(N, false);
+            iq.id_neg = umma_idesc_f16(N, true);
+            iq.smem_base = smem_u32(smem);
+            auto stage_sources = [&](int st) {
+                const int slot = st % TC_NSRC;
+                unsigned char* dst = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
+                const long long s0 = (long long)un.y + (long long)st * TC_KS;
+                mbar_expect_tx(&sfull[slot], TcSmem::SRC_SLOT);
+                bulk_g2s(dst, shat + 4 * s0, TcSmem::SRC_SHAT, &sfull[slot]);
+                bulk_g2s(dst + TcSmem::SRC_SHAT, Ak + s0, TcSmem::SRC_A, &sfull[slot]);
+            };
+            if (elect_one())
+                for (int st = 0; st < min(nst, TC_NSRC); ++st) stage_sources(st);
+            __syncwarp();
+            for (int it = 0; it < nst; ++it) {
+                const int stage = it % TC_NSTAGE, chain = it / TC_FLUSH, set = chain & 1;
+                const bool first = (it % TC_FLUSH) == 0;
+                if (first) {
+                    // this warp's own share of the read-out, then: the set's previous chain has
+                    // been read out by everybody
+                    while (next_read <= chain - 2)
+                        tc_read_chain(tfull, tempty, next_read++, ta0, aR, aI, lane);
+                    if (chain >= 2)
+                        mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
+                }
+                mbar_wait_bounded(&full[stage], (uint32_t)((it / TC_NSTAGE) & 1));
+                tc_fence_after();
+                if (elect_one()) {
+                    tc_issue_stage(iq, stage, set, first);
+                    umma_commit(&empty[stage]);       // stage free once these MMAs have read it
+                    if ((it % TC_FLUSH) == TC_FLUSH - 1 || it == nst - 1) umma_commit(&tfull[set]);
+                    // the owning group has consumed the source slot of this stage: refill it
+                    if (it + TC_NSRC < nst) stage_sources(it + TC_NSRC);
+                }
+                __syncwarp();
+            }
+        } else if (cg >= 1) {
+            // ---------------- generating groups: thread <-> operand row 32 q + lane in both roles,
+            // all 16 sources of the stages it = cg - 1 (mod 3)
+            const int row = 32 * q + lane;
+            const int nx = min(TC_M, na - i0), ny = min(N, na - j0);      // live X / Y rows
+            const bool xlive = row < nx, ylive = row < ny, diag = (i0 == j0);
+            const double kappa = sgn_over_c * freqs[k];
+            // antenna positions in cycles per unit direction cosine: phase = r' . shat
+            double xp[3] = {0.0, 0.0, 0.0}, yp[3] = {0.0, 0.0, 0.0};
+            if (xlive) {
+                const double* a = antv + 4 * (size_t)(i0 + row);
+                xp[0] = kappa * a[0], xp[1] = kappa * a[1], xp[2] = kappa * a[2];
+            }
+            if (ylive) {
+                const double* a = antv + 4 * (size_t)(j0 + row);
+                yp[0] = kappa * a[0], yp[1] = kappa * a[1], yp[2] = kappa * a[2];
+            }
+            const int roff = (row >> 3) * 256 + (row & 7) * 16;
+            for (int it = cg - 1; it < nst; it += TC_GROUPS) {
                 while (next_read <= it / TC_FLUSH - 2)
                     tc_read_chain(tfull, tempty, next_read++, ta0, aR, aI, lane);
-            const int stage = it % TC_NSTAGE, slot = it % TC_NSRC;
-            mbar_wait_bounded(&sfull[slot], (uint32_t)((it / TC_NSRC) & 1));
-            const unsigned char* src = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
-            const double4* sh = reinterpret_cast<const double4*>(src) + 4 * kq;
-            const float4 av = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT)[kq];
-            float c[4], s[4];
-            if (xlive || (diag && ylive)) {
+                const int stage = it % TC_NSTAGE, slot = it % TC_NSRC;
+                mbar_wait_bounded(&sfull[slot], (uint32_t)((it / TC_NSRC) & 1));
+                if (it >= TC_NSTAGE)
+                    mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
+                const unsigned char* src = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
+                unsigned char* dst = smem + stage * TcSmem::STAGE + roff;
+#pragma unroll 1
+                for (int kg = 0; kg < ((B200_TC_PROBE & 4) ? 0 : 2); ++kg) {
+                    float c[8], s[8];
+                    const unsigned char* sh = src + kg * 8 * 32;
+                    if (xlive || (diag && ylive)) cis8(xp, sh, c, s);
+                    if (xlive) store_split8(dst + kg * 128 + TcSmem::XR_H, c, s);
+                    if (ylive) {
+                        if (!diag) cis8(yp, sh, c, s);
+                        const float4 a0 = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT)[2 * kg];
+                        const float4 a1 = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT)[2 * kg + 1];
+                        const float a[8] = {a0.x * sc, a0.y * sc, a0.z * sc, a0.w * sc,
+                                            a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) antenna_cis(phase_fma(xp, sh[e]), c[e], s[e]);
-            }
-            if (it >= TC_NSTAGE)
-                mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
-            unsigned char* dst = smem + stage * TcSmem::STAGE + roff;
-            if (xlive) store_split(dst + TcSmem::XR_H, c, s);
-            if (ylive) {
-                if (!diag) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) antenna_cis(phase_fma(yp, sh[e]), c[e], s[e]);
+                        for (int e = 0; e < 8; ++e) {
+                            c[e] *= a[e];
+                            s[e] *= a[e];
+                        }
+                        store_split8(dst + kg * 128 + TcSmem::YR_H, c, s);
+                    }
                 }
-                const float a[4] = {av.x * sc, av.y * sc, av.z * sc, av.w * sc};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    c[e] *= a[e];
-                    s[e] *= a[e];
-                }
-                store_split(dst + TcSmem::YR_H, c, s);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[stage]);
-            if (ctrl && it > 0) control(it - 1);
         }
-        if (ctrl) control(nst - 1);
         while (next_read < nchain) tc_read_chain(tfull, tempty, next_read++, ta0, aR, aI, lane);
 
         // ---- scatter through the pair table
@@ -500,9 +537,9 @@ struct TcBwdSmem {
     static constexpr int POS_MAX = 512;                        // antennas the position table holds
     static constexpr int POS_OFF = TC_NSTAGE * TcSmem::STAGE;  // [POS_MAX][4] float64, kappa-scaled
     static constexpr int RED_OFF = POS_OFF + POS_MAX * 32;     // [2][4 column groups][128] float
-    // full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2]
+    // full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], rbar[2], rdone[2]
     static constexpr int BAR_OFF = RED_OFF + 2 * 4 * TC_M * 4;
-    static constexpr int TMEM_OFF = BAR_OFF + (2 * TC_NSTAGE + 4) * 8;
+    static constexpr int TMEM_OFF = BAR_OFF + (2 * TC_NSTAGE + 8) * 8;
     static constexpr int TOTAL = TMEM_OFF + 16;
     static constexpr int H_BYTES = 4 * TcSmem::ARR;            // one stage of the cotangent operand
 };
@@ -575,6 +612,8 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     uint64_t* empty = full + TC_NSTAGE;
     uint64_t* tfull = empty + TC_NSTAGE;
     uint64_t* tempty = tfull + 2;
+    uint64_t* rbar = tempty + 2;             // column-group partials of a source tile are in `red`
+    uint64_t* rdone = rbar + 2;              // ... and have been summed: the buffer is free again
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcBwdSmem::TMEM_OFF);
     double4* pos = reinterpret_cast<double4*>(smem + TcBwdSmem::POS_OFF);
     float* red = reinterpret_cast<float*>(smem + TcBwdSmem::RED_OFF);
@@ -593,12 +632,14 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     }
     if (tid == 0) {
         for (int st = 0; st < TC_NSTAGE; ++st) {
-            mbar_init(&full[st], TC_WORK_WARPS + 1);     // worker warps + the TMA's expect_tx
+            mbar_init(&full[st], 4 + 1);         // the generating group's warps + the TMA's expect_tx
             mbar_init(&empty[st], 1);
         }
         for (int q = 0; q < 2; ++q) {
             mbar_init(&tfull[q], 1);
             mbar_init(&tempty[q], TC_WORK_WARPS);
+            mbar_init(&rbar[q], TC_WORK_WARPS);
+            mbar_init(&rdone[q], 3);
         }
         mbar_fence_init();
     }
@@ -615,146 +656,170 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // ---------------- control duties (lane 0 of warp 0, one stage behind its own production)
-    TcIssue iq;
-    iq.tmem = tmem;
-    iq.id_pos = umma_idesc_f16(N, false);
-    iq.id_neg = umma_idesc_f16(N, true);
-    iq.smem_base = smem_u32(smem);
-    auto control = [&](int g) {           // whole warp 0: issue the MMAs of stage g = tile * nmst + ms
-        const int tile = g / nmst, ms = g - tile * nmst;
-        const int stage = g % TC_NSTAGE;
-        const int chain = tile * nct + ms / TC_FLUSH, set = chain & 1;
-        const bool first = (ms % TC_FLUSH) == 0;
-        if (first && chain >= 2)
-            mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
-        mbar_wait_bounded(&full[stage], (uint32_t)((g / TC_NSTAGE) & 1));
-        tc_fence_after();
-        if (elect_one()) {
-            tc_issue_stage_bwd(iq, stage, set, first);
-            umma_commit(&empty[stage]);
-            if ((ms % TC_FLUSH) == TC_FLUSH - 1 || ms == nmst - 1) umma_commit(&tfull[set]);
+    // warp roles as in the forward kernel: q = TMEM lane quarter = source rows 32 q .. of the tile,
+    // cg = column group = antennas a0 + 32 cg ..; warp 0 control, warps 1..3 read-out and the
+    // final sum over column groups, warps 4..15 generating groups cg - 1
+    const int q = warp & 3, cg = warp >> 2;
+    const int role = __shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_CG * cg);
+    const float inv_h = 1.f / __ldg(hscale);
+    const float kf = (float)(kappa * 6.283185307179586476925286766559);
+    float aR[TC_CG], aI[TC_CG];
+#pragma unroll
+    for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
+    float gr[3] = {0.f, 0.f, 0.f};
+    int next_read = 0;
+
+    // chain rc -> registers; after the last chain of a source tile: the tile's epilogue
+    auto read_chain = [&](int rc) {
+        tc_read_chain(tfull, tempty, rc, ta0, aR, aI, lane);
+        if (rc % nct != nct - 1) return;
+        const int tile = rc / nct;
+        const long long s = (long long)un.y + (long long)tile * TC_M + 32 * q + lane;
+        const bool valid = s < un.z;
+        double sv[3] = {0.0, 0.0, 0.0};
+        float wk = 0.f;
+        if (valid) {
+            const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
+            sv[0] = s01.x, sv[1] = s01.y, sv[2] = __ldg(shat + 4 * s + 2);
+            if (need_r) wk = __ldg(Acm + (size_t)k * (size_t)S + s) * kf * inv_h;
         }
-        __syncwarp();
-    };
-    const bool ctrl = __shfl_sync(0xffffffffu, warp, 0) == TC_CTRL_WARP;      // warp-uniform
-    {
-        // ---------------- workers: operand row = source (tid & 255) >> 1 of the tile, partner
-        // antennas 4 kq .. 4 kq + 3 of the stage; accumulators: sources 32 q .., antennas 32 cg ..
-        const int kg = tid >> 8, row = (tid & 255) >> 1, kh = tid & 1, kq = 2 * kg + kh;
-        const int roff = (row >> 3) * 256 + kg * 128 + (row & 7) * 16 + kh * 8;
-        const int q = warp & 3, cg = warp >> 2;
-        const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_CG * cg);
-        const unsigned char* Hbase = Hq + ((((size_t)un.x * nfp + k) * nitem + ai) * (size_t)nmst_all + mlo) *
-                                              TcBwdSmem::H_BYTES;
-        const float inv_h = 1.f / __ldg(hscale);
-        const float kf = (float)(kappa * 6.283185307179586476925286766559);
-        float aR[TC_CG], aI[TC_CG];
+        float dacc = 0.f;
+        const double4* pa = pos + a0 + TC_CG * cg;
+#pragma unroll
+        for (int c = 0; c < TC_CG; ++c) {
+            const double4 p = pa[c];
+            float cs, sn;
+            antenna_cis(__fma_rn(p.x, sv[0], __fma_rn(p.y, sv[1], __fma_rn(p.z, sv[2], 1572864.0))),
+                        cs, sn);
+            const float yr = aR[c], yi = aI[c];
+            dacc = fmaf(cs, yr, fmaf(sn, yi, dacc));            // Re(conj(E) y)
+            aR[c] = wk * fmaf(cs, yi, -sn * yr);                // A kappa 2 pi Im(conj(E) y)
+        }
+        if (need_r) {
+            const float fx = (float)sv[0], fy = (float)sv[1], fz = (float)sv[2];
+#pragma unroll
+            for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fx;
+            gr[0] += warp_reduce_scatter32(aI, lane);
+#pragma unroll
+            for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fy;
+            gr[1] += warp_reduce_scatter32(aI, lane);
+#pragma unroll
+            for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fz;
+            gr[2] += warp_reduce_scatter32(aI, lane);
+        }
 #pragma unroll
         for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
-        float gr[3] = {0.f, 0.f, 0.f};
-        int next_read = 0;
-
-        // chain rc -> registers; after the last chain of a source tile: the tile's epilogue
-        auto read_chain = [&](int rc) {
-            tc_read_chain(tfull, tempty, rc, ta0, aR, aI, lane);
-            if (rc % nct != nct - 1) return;
-            const int tile = rc / nct;
-            const long long s = (long long)un.y + (long long)tile * TC_M + 32 * q + lane;
-            const bool valid = s < un.z;
-            double sv[3] = {0.0, 0.0, 0.0};
-            float wk = 0.f;
-            if (valid) {
-                const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
-                sv[0] = s01.x, sv[1] = s01.y, sv[2] = __ldg(shat + 4 * s + 2);
-                if (need_r) wk = __ldg(Acm + (size_t)k * (size_t)S + s) * kf * inv_h;
-            }
-            float dacc = 0.f;
-            const double4* pa = pos + a0 + TC_CG * cg;
-#pragma unroll
-            for (int c = 0; c < TC_CG; ++c) {
-                const double4 p = pa[c];
-                float cs, sn;
-                antenna_cis(__fma_rn(p.x, sv[0], __fma_rn(p.y, sv[1], __fma_rn(p.z, sv[2], 1572864.0))),
-                            cs, sn);
-                const float yr = aR[c], yi = aI[c];
-                dacc = fmaf(cs, yr, fmaf(sn, yi, dacc));            // Re(conj(E) y)
-                aR[c] = wk * fmaf(cs, yi, -sn * yr);                // A kappa 2 pi Im(conj(E) y)
-            }
-            if (need_r) {
-                const float fx = (float)sv[0], fy = (float)sv[1], fz = (float)sv[2];
-#pragma unroll
-                for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fx;
-                gr[0] += warp_reduce_scatter32(aI, lane);
-#pragma unroll
-                for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fy;
-                gr[1] += warp_reduce_scatter32(aI, lane);
-#pragma unroll
-                for (int c = 0; c < TC_CG; ++c) aI[c] = aR[c] * fz;
-                gr[2] += warp_reduce_scatter32(aI, lane);
-            }
-#pragma unroll
-            for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
-            if (need_a) {
-                // sum over the four column groups in a fixed order (deterministic)
-                float* rb = red + (tile & 1) * 4 * TC_M;
-                rb[cg * TC_M + 32 * q + lane] = dacc;
-                named_bar_sync(1, TC_WORKERS);
-                if (cg == 0 && valid) {
-                    const float* r4 = rb + 32 * q + lane;
+        if (need_a) {
+            // sum over the four column groups in a fixed order (deterministic): partials through
+            // shared memory, summed by the read-out warps 1..3 (warp 1 also covers quarter 0)
+            const int buf = tile & 1;
+            float* rb = red + buf * 4 * TC_M;
+            if (tile >= 2) mbar_wait_bounded(&rdone[buf], (uint32_t)(((tile >> 1) - 1) & 1));
+            rb[cg * TC_M + 32 * q + lane] = dacc;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rbar[buf]);
+            if (role >= 1 && role <= 3) {
+                mbar_wait_bounded(&rbar[buf], (uint32_t)((tile >> 1) & 1));
+                for (int qq = (role == 1 ? 0 : role); qq <= role; ++qq) {
+                    const long long s2 = (long long)un.y + (long long)tile * TC_M + 32 * qq + lane;
+                    const float* r4 = rb + 32 * qq + lane;
                     const float tot = ((r4[0] + r4[TC_M]) + r4[2 * TC_M]) + r4[3 * TC_M];
-                    dAcm[((size_t)ai * nfp + k) * (size_t)S + s] = 0.5f * tot * inv_h;
+                    if (s2 < un.z) dAcm[((size_t)ai * nfp + k) * (size_t)S + s2] = 0.5f * tot * inv_h;
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rdone[buf]);
             }
-        };
+        }
+    };
 
+    if (role == TC_CTRL_WARP) {
+        // ---------------- control warp: MMA issue (uniform datapath)
+        TcIssue iq;
+        iq.tmem = tmem;
+        iq.id_pos = umma_idesc_f16(N, false);
+        iq.id_neg = umma_idesc_f16(N, true);
+        iq.smem_base = smem_u32(smem);
         int g = 0;
         for (int tile = 0; tile < ntile; ++tile) {
-            const long long s = (long long)un.y + (long long)tile * TC_M + row;
-            const bool valid = s < un.z;
-            double sv[3] = {0.0, 0.0, 0.0};
-            if (valid) {
-                const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
-                sv[0] = s01.x, sv[1] = s01.y, sv[2] = __ldg(shat + 4 * s + 2);
-            }
             for (int ms = 0; ms < nmst; ++ms, ++g) {
-                if ((ms % TC_FLUSH) == 0) {
-                    const int chain = tile * nct + ms / TC_FLUSH;
-                    while (next_read <= chain - 2) read_chain(next_read++);
-                }
                 const int stage = g % TC_NSTAGE;
-                unsigned char* sbase = smem + stage * TcSmem::STAGE;
-                float c[4], sn[4];
-                const double4* pm = pos + (mlo + ms) * TC_KS + 4 * kq;
+                const int chain = tile * nct + ms / TC_FLUSH, set = chain & 1;
+                const bool first = (ms % TC_FLUSH) == 0;
+                if (first) {
+                    while (next_read <= chain - 2) read_chain(next_read++);
+                    if (chain >= 2)
+                        mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
+                }
+                mbar_wait_bounded(&full[stage], (uint32_t)((g / TC_NSTAGE) & 1));
+                tc_fence_after();
+                if (elect_one()) {
+                    tc_issue_stage_bwd(iq, stage, set, first);
+                    umma_commit(&empty[stage]);
+                    if ((ms % TC_FLUSH) == TC_FLUSH - 1 || ms == nmst - 1) umma_commit(&tfull[set]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (cg >= 1) {
+        // ---------------- generating groups: thread <-> source row 32 q + lane of the tile, all
+        // 16 partner antennas of the stages g = cg - 1 (mod 3)
+        const int row = 32 * q + lane;
+        const int roff = (row >> 3) * 256 + (row & 7) * 16;
+        const unsigned char* Hbase = Hq + ((((size_t)un.x * nfp + k) * nitem + ai) * (size_t)nmst_all + mlo) *
+                                              TcBwdSmem::H_BYTES;
+        int cur_tile = -1;
+        bool valid = false;
+        double sv[3] = {0.0, 0.0, 0.0};
+        for (int g = cg - 1; g < nst; g += TC_GROUPS) {
+            const int tile = g / nmst, ms = g - tile * nmst;
+            {
+                const int chain = tile * nct + ms / TC_FLUSH;
+                while (next_read <= chain - 2) read_chain(next_read++);
+            }
+            if (tile != cur_tile) {
+                cur_tile = tile;
+                const long long s = (long long)un.y + (long long)tile * TC_M + row;
+                valid = s < un.z;
+                sv[0] = sv[1] = sv[2] = 0.0;
+                if (valid) {
+                    const double2 s01 = __ldg(reinterpret_cast<const double2*>(shat + 4 * s));
+                    sv[0] = s01.x, sv[1] = s01.y, sv[2] = __ldg(shat + 4 * s + 2);
+                }
+            }
+            const int stage = g % TC_NSTAGE;
+            unsigned char* sbase = smem + stage * TcSmem::STAGE;
+            if (g >= TC_NSTAGE)
+                mbar_wait_bounded(&empty[stage], (uint32_t)(((g / TC_NSTAGE) - 1) & 1));
+            if (q == 0 && lane == 0) {
+                // this thread also fetches the cotangent operand of the stage
+                mbar_expect_tx(&full[stage], TcBwdSmem::H_BYTES);
+                bulk_g2s(sbase + TcSmem::YR_H, Hbase + (size_t)ms * TcBwdSmem::H_BYTES,
+                         TcBwdSmem::H_BYTES, &full[stage]);
+            }
+#pragma unroll 1
+            for (int kg = 0; kg < 2; ++kg) {
+                float c[8], sn[8];
+                const double4* pm = pos + (mlo + ms) * TC_KS + 8 * kg;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < 8; ++e) {
                     const double4 p = pm[e];
                     antenna_cis(__fma_rn(p.x, sv[0], __fma_rn(p.y, sv[1], __fma_rn(p.z, sv[2], 1572864.0))),
                                 c[e], sn[e]);
                     if (!valid) c[e] = sn[e] = 0.f;
                 }
-                if (g >= TC_NSTAGE)
-                    mbar_wait_bounded(&empty[stage], (uint32_t)(((g / TC_NSTAGE) - 1) & 1));
-                if (tid == 0) {
-                    // this thread also fetches the cotangent operand of the stage
-                    mbar_expect_tx(&full[stage], TcBwdSmem::H_BYTES);
-                    bulk_g2s(sbase + TcSmem::YR_H, Hbase + (size_t)ms * TcBwdSmem::H_BYTES,
-                             TcBwdSmem::H_BYTES, &full[stage]);
-                }
-                store_split(sbase + roff + TcSmem::XR_H, c, sn);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);
-                if (ctrl && g > 0) control(g - 1);
+                store_split8(sbase + roff + kg * 128 + TcSmem::XR_H, c, sn);
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
         }
-        if (ctrl) control(nst - 1);
-        while (next_read < nchain) read_chain(next_read++);
-        if (need_r) {
-            float4* dst = reinterpret_cast<float4*>(drpart) +
-                          (((size_t)blockIdx.x * nfp + k) * 4 + q) * (size_t)(nitem * TC_M) + a0 + TC_CG * cg;
-            dst[lane] = make_float4(gr[0], gr[1], gr[2], 0.f);
-        }
+    }
+    while (next_read < nchain) read_chain(next_read++);
+    if (need_r) {
+        float4* dst = reinterpret_cast<float4*>(drpart) +
+                      (((size_t)blockIdx.x * nfp + k) * 4 + q) * (size_t)(nitem * TC_M) + a0 + TC_CG * cg;
+        dst[lane] = make_float4(gr[0], gr[1], gr[2], 0.f);
     }
     tc_fence_before();
     __syncthreads();
