@@ -43,6 +43,8 @@ _SIGS = {
     "apply_cal": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "apply_cal_bwd_gains": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P,
                             _P],
+    "jones_sandwich": [_P, _P, _P, _L, _P, _P],
+    "jones_sandwich_bwd": [_P, _P, _P, _P, _L, _I, _P, _P, _P, _P],
     "build_airy": [_D, _D, _D, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P, _L, _P],
     "build_airy_bwd": [_P, _D, _D, _D, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _L, _L, _P, _P, _P,
                        _L, _P],

@@ -620,6 +620,174 @@ int launch_gather_times(const T* dIs, long long ldd, const int* pos, int nt, int
     return check_launch("gather_times");
 }
 
+// -------------------------------------------------------------------------------------
+// Jones sandwich of the polarised beam modes (beam_model.py:347, :363; the reference runs it as
+// einsum("ab...,bc...,dc...->ad...")): P[a][d] = sum_{b,c} J1[a][b] C[b][c] J2[d][c] for REAL
+// 2 x 2 Jones matrices and coherencies, element-wise over planes in the tiled layout (HBM
+// bound: 12 plane reads, 4 plane writes).  Planes are addressed through a small table so that
+// the operands need not be stacked.  Backward (one pass): dJ1 = dP (J2 C^T), dJ2 = dP^T (J1 C),
+// dC = J1^T dP J2; when both antennas share one beam model (J2 == J1, `same`) the two Jones
+// gradients are summed into dJ1.
+// -------------------------------------------------------------------------------------
+template <typename T> struct Planes4 {
+    const T* p[4];
+};
+template <typename T> struct PlanesOut4 {
+    T* p[4];
+};
+template <typename T> struct Vec4 {
+    T v[4];
+};
+template <typename T> __device__ __forceinline__ Vec4<T> ld4(const T* p, long long i) {
+    Vec4<T> r;
+    if constexpr (sizeof(T) == 4) {
+        const float4 x = *reinterpret_cast<const float4*>(p + i);
+        r.v[0] = x.x, r.v[1] = x.y, r.v[2] = x.z, r.v[3] = x.w;
+    } else {
+        const double2 x = *reinterpret_cast<const double2*>(p + i);
+        const double2 y = *reinterpret_cast<const double2*>(p + i + 2);
+        r.v[0] = x.x, r.v[1] = x.y, r.v[2] = y.x, r.v[3] = y.y;
+    }
+    return r;
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, long long i, const Vec4<T>& r) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p + i) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    } else {
+        *reinterpret_cast<double2*>(p + i) = make_double2(r.v[0], r.v[1]);
+        *reinterpret_cast<double2*>(p + i + 2) = make_double2(r.v[2], r.v[3]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+jones_sandwich_kernel(Planes4<T> J1, Planes4<T> J2, Planes4<T> C, long long n, PlanesOut4<T> P) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        Vec4<T> j1[4], j2[4], c[4], o[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            j1[m] = ld4(J1.p[m], i);
+            j2[m] = ld4(J2.p[m], i);
+            c[m] = ld4(C.p[m], i);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            // M = J1 C (index [a][c]), P = M J2^T
+            T M[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+                    M[2 * a + cc] = j1[2 * a].v[e] * c[cc].v[e] + j1[2 * a + 1].v[e] * c[2 + cc].v[e];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+                    o[2 * a + d].v[e] = M[2 * a] * j2[2 * d].v[e] + M[2 * a + 1] * j2[2 * d + 1].v[e];
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) st4(P.p[m], i, o[m]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+jones_sandwich_bwd_kernel(Planes4<T> dP, Planes4<T> J1, Planes4<T> J2, Planes4<T> C, long long n,
+                          int same, PlanesOut4<T> dJ1, PlanesOut4<T> dJ2, PlanesOut4<T> dC) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        Vec4<T> g[4], j1[4], j2[4], c[4], o1[4], o2[4], oc[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            g[m] = ld4(dP.p[m], i);
+            j1[m] = ld4(J1.p[m], i);
+            j2[m] = ld4(J2.p[m], i);
+            c[m] = ld4(C.p[m], i);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            T G[4], A[4], B[4], K[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) G[m] = g[m].v[e], A[m] = j1[m].v[e], B[m] = j2[m].v[e], K[m] = c[m].v[e];
+            // N2 = J2 C^T ([d][b]), N1 = J1 C ([a][c])
+            T N2[4], N1[4];
+#pragma unroll
+            for (int d = 0; d < 2; ++d)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    N2[2 * d + b] = B[2 * d] * K[2 * b] + B[2 * d + 1] * K[2 * b + 1];
+                    N1[2 * d + b] = A[2 * d] * K[b] + A[2 * d + 1] * K[2 + b];
+                }
+            T D1[4], D2[4], DC[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    // dJ1[a][b] = sum_d G[a][d] N2[d][b];  dJ2[d=a][c=b] = sum_a' G[a'][d] N1[a'][c]
+                    D1[2 * a + b] = G[2 * a] * N2[b] + G[2 * a + 1] * N2[2 + b];
+                    D2[2 * a + b] = G[a] * N1[b] + G[2 + a] * N1[2 + b];
+                }
+            // dC[b][c] = sum_{a,d} J1[a][b] G[a][d] J2[d][c]: T1 = J1^T G ([b][d]), dC = T1 J2
+            T T1[4];
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int d = 0; d < 2; ++d) T1[2 * b + d] = A[b] * G[d] + A[2 + b] * G[2 + d];
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) DC[2 * b + cc] = T1[2 * b] * B[cc] + T1[2 * b + 1] * B[2 + cc];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                o1[m].v[e] = same ? D1[m] + D2[m] : D1[m];
+                o2[m].v[e] = D2[m];
+                oc[m].v[e] = DC[m];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            if (dJ1.p[m] != nullptr) st4(dJ1.p[m], i, o1[m]);
+            if (!same && dJ2.p[m] != nullptr) st4(dJ2.p[m], i, o2[m]);
+            if (dC.p[m] != nullptr) st4(dC.p[m], i, oc[m]);
+        }
+    }
+}
+
+template <typename T> static int sandwich_grid(long long n) {
+    const long long want = (n / 4 + 255) / 256;
+    const long long cap = 148LL * 16;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+template <typename T>
+int launch_jones_sandwich(const T* const* J1, const T* const* J2, const T* const* C, long long n,
+                          T* const* P, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (n % 4) return set_error("jones_sandwich: plane length must be a multiple of 4");
+    Planes4<T> a, b, c;
+    PlanesOut4<T> o;
+    for (int m = 0; m < 4; ++m) a.p[m] = J1[m], b.p[m] = J2[m], c.p[m] = C[m], o.p[m] = P[m];
+    jones_sandwich_kernel<T><<<sandwich_grid<T>(n), 256, 0, st>>>(a, b, c, n, o);
+    return check_launch("jones_sandwich");
+}
+template <typename T>
+int launch_jones_sandwich_bwd(const T* const* dP, const T* const* J1, const T* const* J2,
+                              const T* const* C, long long n, int same, T* const* dJ1, T* const* dJ2,
+                              T* const* dC, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (n % 4) return set_error("jones_sandwich_bwd: plane length must be a multiple of 4");
+    Planes4<T> g, a, b, c;
+    PlanesOut4<T> o1, o2, oc;
+    for (int m = 0; m < 4; ++m) {
+        g.p[m] = dP[m], a.p[m] = J1[m], b.p[m] = J2[m], c.p[m] = C[m];
+        o1.p[m] = dJ1 ? dJ1[m] : nullptr;
+        o2.p[m] = dJ2 ? dJ2[m] : nullptr;
+        oc.p[m] = dC ? dC[m] : nullptr;
+    }
+    jones_sandwich_bwd_kernel<T><<<sandwich_grid<T>(n), 256, 0, st>>>(g, a, b, c, n, same, o1, o2, oc);
+    return check_launch("jones_sandwich_bwd");
+}
+
 }  // namespace b200rime
 
 using namespace b200rime;
@@ -749,4 +917,25 @@ int b200rime_gather_times_f64(const double* dIs, long long ldd, const int* pos, 
     return launch_gather_times<double>(dIs, ldd, pos, nt, npix, nfreq, dsky, lds, ST(stream));
 }
 
+int b200rime_jones_sandwich_f32(const float* const* J1, const float* const* J2,
+                                const float* const* C, long long n, float* const* P, void* stream) {
+    return launch_jones_sandwich<float>(J1, J2, C, n, P, ST(stream));
+}
+int b200rime_jones_sandwich_f64(const double* const* J1, const double* const* J2,
+                                const double* const* C, long long n, double* const* P,
+                                void* stream) {
+    return launch_jones_sandwich<double>(J1, J2, C, n, P, ST(stream));
+}
+int b200rime_jones_sandwich_bwd_f32(const float* const* dP, const float* const* J1,
+                                    const float* const* J2, const float* const* C, long long n,
+                                    int same, float* const* dJ1, float* const* dJ2,
+                                    float* const* dC, void* stream) {
+    return launch_jones_sandwich_bwd<float>(dP, J1, J2, C, n, same, dJ1, dJ2, dC, ST(stream));
+}
+int b200rime_jones_sandwich_bwd_f64(const double* const* dP, const double* const* J1,
+                                    const double* const* J2, const double* const* C, long long n,
+                                    int same, double* const* dJ1, double* const* dJ2,
+                                    double* const* dC, void* stream) {
+    return launch_jones_sandwich_bwd<double>(dP, J1, J2, C, n, same, dJ1, dJ2, dC, ST(stream));
+}
 }  // extern "C"

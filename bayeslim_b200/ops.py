@@ -82,14 +82,22 @@ def _call(name, sfx, *args):
     _launches += 1
     dev = None
     for a in args:
+        for t in (a if isinstance(a, (list, tuple)) else (a,)):
+            if isinstance(t, torch.Tensor):
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise RuntimeError("b200rime_%s: tensors live on different devices (%s, %s)"
+                                       % (name, dev, t.device))
+
+    def one(a):
         if isinstance(a, torch.Tensor):
-            if dev is None:
-                dev = a.device
-            elif a.device != dev:
-                raise RuntimeError("b200rime_%s: tensors live on different devices (%s, %s)"
-                                   % (name, dev, a.device))
-    conv = [ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor)
-            else (ctypes.c_void_p(0) if a is None else a) for a in args]
+            return ctypes.c_void_p(a.data_ptr())
+        if isinstance(a, (list, tuple)):      # host table of device pointers (None -> NULL)
+            tab = (ctypes.c_void_p * len(a))(*[t.data_ptr() if t is not None else 0 for t in a])
+            return ctypes.cast(tab, ctypes.c_void_p)
+        return ctypes.c_void_p(0) if a is None else a
+    conv = [one(a) for a in args]
     # launch on the device that owns the tensors and on torch's current stream OF THAT DEVICE
     # (not on whatever device happens to be current in the process)
     with torch.cuda.device(dev):
@@ -428,6 +436,60 @@ def build_airy(sky, diam, geom, tab, freqs64, freq_ratio=1.0, square=True, full_
     """sky (Nf, Npix), diam tensor with 1 (D) or 2 (Dew, Dns) elements -> A (1, nchunk, S, KC);
     one launch for all times."""
     return _BuildAiry.apply(sky, diam, geom, tab, freqs64, freq_ratio, square, full_grad)
+
+
+# ----------------------------------------------------------------------------- Jones sandwich
+class _JonesSandwich(torch.autograd.Function):
+    """P[a][d] = sum_{b,c} J1[a][b] C[b][c] J2[d][c] on real tiled planes (jones_sandwich kernels).
+    Inputs: 4 planes of J1, 4 of J2 (the same tensors when both antennas share a beam model),
+    4 of C, index 2 * row + col; output (4, *plane shape)."""
+
+    @staticmethod
+    def forward(ctx, same, *planes):
+        _need_cuda(*planes)
+        planes = [x.contiguous() for x in planes]
+        j1, j2, c = planes[0:4], planes[4:8], planes[8:12]
+        ref = j1[0]
+        sfx = _sfx(ref.dtype)
+        out = torch.empty((4,) + tuple(ref.shape), dtype=ref.dtype, device=ref.device)
+        n = ref.numel()
+        if n % 4:
+            raise ValueError("jones_sandwich needs plane sizes that are multiples of 4 (tiled layout)")
+        _call("jones_sandwich", sfx, j1, j2, c, n, [out[m] for m in range(4)])
+        ctx.save_for_backward(*planes)
+        ctx.same = bool(same)
+        return out
+
+    @staticmethod
+    def backward(ctx, dP):
+        planes = ctx.saved_tensors
+        j1, j2, c = list(planes[0:4]), list(planes[4:8]), list(planes[8:12])
+        dP = dP.contiguous()
+        sfx = _sfx(dP.dtype)
+        n = j1[0].numel()
+        need1 = any(ctx.needs_input_grad[1:5])
+        need2 = any(ctx.needs_input_grad[5:9]) and not ctx.same
+        needc = any(ctx.needs_input_grad[9:13])
+        g1 = torch.empty_like(dP) if need1 or (ctx.same and any(ctx.needs_input_grad[5:9])) else None
+        g2 = torch.empty_like(dP) if need2 else None
+        gc = torch.empty_like(dP) if needc else None
+        tab = lambda g: [g[m] for m in range(4)] if g is not None else None
+        _call("jones_sandwich_bwd", sfx, [dP[m] for m in range(4)], j1, j2, c, n, int(ctx.same),
+              tab(g1), tab(g2), tab(gc))
+        un = lambda g: [g[m] for m in range(4)] if g is not None else [None] * 4
+        # same: the summed Jones gradient goes to the first operand; the second (the same
+        # tensors) gets none, autograd adds nothing twice
+        return (None,) + tuple(un(g1)) + tuple(un(g2)) + tuple(un(gc))
+
+
+def jones_sandwich(J1, J2, C):
+    """J1, J2: 2 x 2 real Jones planes (a (2, 2, *shape) tensor or nested lists of plane tensors;
+    J2 may be J1), C: 2 x 2 real coherency planes -> P (2, 2, *shape) = J1 C J2^T
+    (beam_model.py:363)."""
+    same = J2 is J1
+    flat = lambda X: [X[a][b] for a in range(2) for b in range(2)]
+    out = _JonesSandwich.apply(same, *(flat(J1) + flat(J2) + flat(C)))
+    return out.reshape((2, 2) + tuple(out.shape[1:]))
 
 
 # ----------------------------------------------------------------------------- fringe sum

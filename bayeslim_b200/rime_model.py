@@ -435,7 +435,8 @@ class RIME(utils.Module):
         """Perceived sky of the polarised modes (beam_model.py:343-363) in the tiled layout:
         every Jones element J[a, b, model] is interpolated and every coherency element C[b, c]
         gathered through the FOV cut by the CUDA builder (one launch each, all times), then
-        P = J C J^H is an element-wise torch expression on (nchunk, S, KC) tensors.  Nothing of
+        P = J C J^H is one fused CUDA pass over the planes for real 4-pol operands
+        (ops.jones_sandwich) and an element-wise torch expression otherwise.  Nothing of
         shape (.., Nf, Ns, Nneighbours) is ever formed (the reference's gather temp is 25 GB per
         time at nside 256)."""
         b, R = self.beam, self.beam.R
@@ -454,13 +455,22 @@ class RIME(utils.Module):
                 else ops.build_interp(x2d, None, rec.geom, tab)
             return A[0]
 
-        J = torch.stack([torch.stack([torch.stack([tiled(bmap[a, v, m], True)
-                                                   for m in range(bmap.shape[2])])
+        modelpairs, mp_idx = _beam_model_pairs(b, self.sim_bls)
+        Jp = [[[tiled(bmap[a, v, m], True) for v in range(bmap.shape[1])]
+               for a in range(bmap.shape[0])] for m in range(bmap.shape[2])]     # [model][pol][vec]
+        Cp = [[tiled(sky[v, w], False) for w in range(sky.shape[1])] for v in range(sky.shape[0])]
+        real = not (bmap.is_complex() or sky.is_complex())
+        if real and not b.powerbeam and tuple(bmap.shape[:2]) == (2, 2) and tuple(sky.shape[:2]) == (2, 2):
+            # 4-pol real Jones x real coherency: P = J1 C J2^T in one fused CUDA pass per model
+            # pair (the reference's einsum, beam_model.py:363) -- no stacked operands
+            per_pair = [ops.jones_sandwich(Jp[m1], Jp[m1] if m2 == m1 else Jp[m2], Cp)
+                        for (m1, m2) in modelpairs]
+            psky = per_pair[0].unsqueeze(2) if len(per_pair) == 1 else torch.stack(per_pair, dim=2)
+            return psky, modelpairs, mp_idx
+        J = torch.stack([torch.stack([torch.stack([Jp[m][a][v] for m in range(bmap.shape[2])])
                                       for v in range(bmap.shape[1])])
                          for a in range(bmap.shape[0])])            # (Npol, Nvec, Nmodel, *tile)
-        C = torch.stack([torch.stack([tiled(sky[v, w], False) for w in range(sky.shape[1])])
-                         for v in range(sky.shape[0])])             # (Nvec, Nvec, *tile)
-        modelpairs, mp_idx = _beam_model_pairs(b, self.sim_bls)
+        C = torch.stack([torch.stack(Cp[v]) for v in range(sky.shape[0])])       # (Nvec, Nvec, *tile)
         psky = beam_model.perceived_sky(J, C, modelpairs, b.Npol, b.Nvec, b.powerbeam)
         return psky, modelpairs, mp_idx
 

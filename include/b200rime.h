@@ -336,6 +336,28 @@ int b200rime_tcfringe_bwd_f32(const void* Hq, const float* hscale, const float* 
                               const int* mrange, int nfreq, long long S, int conj, float* dAcm,
                               float* drpart, b200rime_stream_t stream);
 
+/* ---- Jones sandwich of the polarised beam modes -------------------------------------------
+ * P[a][d] = sum_{b,c} J1[a][b] C[b][c] J2[d][c] for real 2 x 2 Jones planes and coherency planes
+ * (beam_model.py:347, :363 einsum "ab...,bc...,dc...->ad..."), element-wise over n elements per
+ * plane (n % 4 == 0; the tiled layout).  J1 / J2 / C / P: HOST arrays of 4 DEVICE plane pointers,
+ * index 2 * row + col.  Backward: dJ1 = dP (J2 C^T), dJ2 = dP^T (J1 C), dC = J1^T dP J2; `same`
+ * != 0 (both antennas use one beam model, J2 == J1): the sum dJ1 + dJ2 is written to dJ1 and dJ2
+ * is not touched.  Output tables (or single entries) may be NULL. */
+int b200rime_jones_sandwich_f32(const float* const* J1, const float* const* J2,
+                                const float* const* C, long long n, float* const* P,
+                                b200rime_stream_t stream);
+int b200rime_jones_sandwich_f64(const double* const* J1, const double* const* J2,
+                                const double* const* C, long long n, double* const* P,
+                                b200rime_stream_t stream);
+int b200rime_jones_sandwich_bwd_f32(const float* const* dP, const float* const* J1,
+                                    const float* const* J2, const float* const* C, long long n,
+                                    int same, float* const* dJ1, float* const* dJ2,
+                                    float* const* dC, b200rime_stream_t stream);
+int b200rime_jones_sandwich_bwd_f64(const double* const* dP, const double* const* J1,
+                                    const double* const* J2, const double* const* C, long long n,
+                                    int same, double* const* dJ1, double* const* dJ2,
+                                    double* const* dC, b200rime_stream_t stream);
+
 /* ---- gain application --------------------------------------
  * V_out = g_1 V g_2^H per baseline: reference calibration._apply_cal (calibration.py:2412-2487),
  * the step that follows the RIME in a BayesLIM Sequential.

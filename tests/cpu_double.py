@@ -356,6 +356,40 @@ def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na, na_pad, nm_p
             drpart[u, :nfreq, 0, :na, :3] = (sgn * 2 * math.pi / C * g)[:, :na]   # caller zeroed
 
 
+def _deref(tab, like):
+    """The double receives the tensors themselves in place of the pointer table."""
+    return tab
+
+
+def jones_sandwich(sfx, J1, J2, C, n, P):
+    a = torch.stack([x.double() for x in J1]).reshape((2, 2) + tuple(J1[0].shape))
+    b = torch.stack([x.double() for x in J2]).reshape((2, 2) + tuple(J2[0].shape))
+    c = torch.stack([x.double() for x in C]).reshape((2, 2) + tuple(C[0].shape))
+    out = torch.einsum("ab...,bc...,dc...->ad...", a, c, b)
+    for m in range(4):
+        P[m].copy_(out[m // 2, m % 2].to(P[m].dtype))
+
+
+def jones_sandwich_bwd(sfx, dP, J1, J2, C, n, same, dJ1, dJ2, dC):
+    sh = tuple(J1[0].shape)
+    a = torch.stack([x.double() for x in J1]).reshape((2, 2) + sh)
+    b = torch.stack([x.double() for x in J2]).reshape((2, 2) + sh)
+    c = torch.stack([x.double() for x in C]).reshape((2, 2) + sh)
+    g = torch.stack([x.double() for x in dP]).reshape((2, 2) + sh)
+    d1 = torch.einsum("ad...,bc...,dc...->ab...", g, c, b)
+    d2 = torch.einsum("ad...,ab...,bc...->dc...", g, a, c)
+    dc = torch.einsum("ab...,ad...,dc...->bc...", a, g, b)
+    if same:
+        d1 = d1 + d2
+    for m in range(4):
+        if dJ1 is not None:
+            dJ1[m].copy_(d1[m // 2, m % 2].to(dJ1[m].dtype))
+        if dJ2 is not None and not same:
+            dJ2[m].copy_(d2[m // 2, m % 2].to(dJ2[m].dtype))
+        if dC is not None:
+            dC[m].copy_(dc[m // 2, m % 2].to(dC[m].dtype))
+
+
 def _cplx(x):
     return torch.complex(x[..., 0].double(), x[..., 1].double())
 
@@ -404,7 +438,8 @@ _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
               build_airy=build_airy, build_airy_bwd=build_airy_bwd,
               antfringe_fwd=antfringe_fwd, antfringe_bwd=antfringe_bwd,
               tcfringe_fwd=tcfringe_fwd, tcfringe_bwd=tcfringe_bwd,
-              apply_cal=apply_cal, apply_cal_bwd_gains=apply_cal_bwd_gains)
+              apply_cal=apply_cal, apply_cal_bwd_gains=apply_cal_bwd_gains,
+              jones_sandwich=jones_sandwich, jones_sandwich_bwd=jones_sandwich_bwd)
 
 
 @contextlib.contextmanager
