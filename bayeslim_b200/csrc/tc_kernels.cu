@@ -11,33 +11,40 @@
 //     shared memory in the UMMA canonical K-major layout -- nothing fringe-shaped, per baseline
 //     or per antenna, reaches HBM;
 //   * every operand is split into two float16 numbers hi + lo (|E| <= 1 and A E scaled by a power
-//     of two into float16 range, so hi + lo carries 22 mantissa bits) and a real product costs
-//     three MMAs (hi.hi + hi.lo + lo.hi; the dropped lo.lo term is 2^-24 relative): float32-grade
-//     results at one third of the float16 tensor rate, which is still ~7x the FP32 FMA pipes;
-//   * the complex product needs four real ones; the minus sign of Im = Er.Yi - Ei.Yr is the
-//     negate-A bit of the instruction descriptor, so X and Y are stored once.
+//     of two into float16 range, so hi + lo carries 22 mantissa bits; lo = v - hi is one
+//     mixed-precision FHFMA) and a real product costs three MMAs (hi.hi + hi.lo + lo.hi; the
+//     dropped lo.lo term is 2^-24 relative): float32-grade results at a third of the float16
+//     tensor rate;
+//   * the B operand stacks the real and the imaginary part: (Re | Im) += Er (Yr | Yi) +
+//     Ei (Yi | -Yr) is six MMAs of width 2 N per 16 sources instead of twelve of width N.
+//     Measured on B200 (scripts/gpu_tc_variants.sh, operands resident, no generation): a
+//     128 x 128 x 16 MMA takes ~116 cycles (55 % of the tensor pipe), 128 x 256 x 16 ~166 (77 %):
+//     there is a fixed cost of ~65 cycles per instruction.
 //
 // Accumulation.  The tensor core adds into its FP32 accumulator with truncation (measured on
 // B200: a chain of n MMAs loses ~0.75 * 2^-24 * n of a coherent sum -- 6e-5 after 8192 sources,
 // profiles/r02_tc_v1_truncation_study.jsonl), so a TMEM chain is kept short (TC_FLUSH stages =
 // 64 sources by default) and then added, with ordinary round-to-nearest FADDs, to float32
-// accumulators held in the registers of eight dedicated warps; two TMEM accumulator sets
-// alternate so that the MMAs of chain c + 1 overlap the read-out of chain c.
+// accumulators held in registers; two TMEM accumulator sets alternate so that the MMAs of chain
+// c + 1 overlap the read-out of chain c.
 //
-// Forward item = (block of 128 first antennas i0.., range of N <= 128 second antennas j0..,
-// channel k, unit of sources).  The CTA is four whole warpgroups (setmaxnreg moves registers
-// from the producers to the accumulator warps):
-//   warps 0..7   accumulators (128 registers each: TMEM lane quarter x column half); warp 0
-//                also issues the MMAs (one elected lane) -- it issues chain c, then reads out
-//                chain c - 1 while the tensor core works -- and stages the source data (unit
-//                vectors, channel row of the perceived sky) ahead of the producers with 1-D TMA
-//                bulk copies;
-//   warps 8..15  producers: thread <-> one X row and one Y row, 8 of the 16 sources of a stage
-//                (= one UMMA K step); a diagonal item computes each antenna term once for both
-//                roles.
+// CTA = 16 warps x 128 registers.  Every warp holds a slice of the register accumulators (TMEM
+// lane quarter warp % 4 x 32 columns warp / 4, real and imaginary) and reads its slice of every
+// chain.  Beyond that the roles are:
+//   warp 0        control: stages the source data (unit vectors, channel row of the perceived
+//                 sky) by 1-D TMA bulk copies and issues the MMAs.  Its code is warp-uniform, so
+//                 descriptors live in uniform registers and a stage costs ~50 instructions.
+//   warps 1..3    read-out only (the backward kernel also gives them the fixed-order sum over
+//                 column groups).
+//   warps 4..15   three generating groups of four warps; group g generates the whole stages
+//                 it = g (mod 3): thread <-> operand row (32 (warp % 4) + lane) in both roles, all
+//                 16 sources.  With one stage per group in flight, a stage may take three stage
+//                 periods: the latency of the per-stage handshakes (mbarrier waits, proxy fence)
+//                 is hidden, which a design where every warp touches every stage cannot do
+//                 (measured: 2380 -> 1850 cycles per stage before the stacked operands).
 // full / empty mbarriers per operand stage, sfull per source slot, tfull / tempty per TMEM set;
-// tcgen05.commit releases stages and hands chains to the accumulator warps, which finally
-// scatter their registers through the antenna-pair table into Vpart[unit][baseline][channel].
+// tcgen05.commit releases stages and hands chains over; finally the registers are scattered
+// through the antenna-pair table into Vpart[unit][baseline][channel].
 //
 // Replaces telescope_model.py:310-358 (gen_fringe) + rime_model.py:426-429 (multiply, sum).
 #include <cuda_fp16.h>
@@ -47,26 +54,25 @@
 namespace b200rime {
 
 #ifndef B200_TC_PROBE
-#define B200_TC_PROBE 0            // timing probes (wrong results): 1 no sine / cosine, 2 no MMAs, 8 no proxy fence
+#define B200_TC_PROBE 0            // timing probes (wrong results): 1 no sine / cosine, 2 no MMAs, 4 no generation
 #endif
 #ifndef B200_TC_FLUSH
 #define B200_TC_FLUSH 4            // stages (of 16 sources) per TMEM accumulation chain
 #endif
 constexpr int TC_M = 128;            // X rows (first antennas) per item = UMMA M
-constexpr int TC_NMAX = 128;         // Y rows (second antennas) per item = UMMA N, at most
+constexpr int TC_NMAX = 128;         // Y rows (second antennas) per item, at most (UMMA N = 2 x this)
 constexpr int TC_KS = 16;            // sources per stage = one kind::f16 UMMA K step
-constexpr int TC_NSTAGE = 6;         // operand stages
+constexpr int TC_NSTAGE = 5;         // operand stages (40 KB each)
 constexpr int TC_NSRC = 8;           // source-data slots (staged TC_NSRC stages ahead)
 constexpr int TC_FLUSH = B200_TC_FLUSH;
-constexpr int TC_WORK_WARPS = 16;    // every warp holds a (lane quarter x 32 columns) slice of the accumulators
-constexpr int TC_WORKERS = TC_WORK_WARPS * 32;
-constexpr int TC_CTRL_WARP = 0;      // stages the sources (TMA) and issues the MMAs (warps 1..3: read-out only)
-constexpr int TC_GROUPS = 3;         // warps 4..15 = three groups of four; group g generates stages it = g (mod 3)
-constexpr int TC_THREADS = TC_WORKERS;            // 512 threads x 128 registers = the register file
+constexpr int TC_WARPS = 16;         // every warp holds a (lane quarter x 32 columns) accumulator slice
+constexpr int TC_THREADS = TC_WARPS * 32;         // 512 threads x 128 registers = the register file
+constexpr int TC_CTRL_WARP = 0;      // stages the sources (TMA) and issues the MMAs
+constexpr int TC_GROUPS = 3;         // warps 4..15: group g generates stages it = g (mod 3)
 constexpr int TC_KC = B200_KC_F32;
-constexpr int TC_TMEM_COLS = 512;    // two accumulator sets of (re, im) x 128 columns
-constexpr int TC_SET_COLS = 256, TC_IM_COL = 128;
-constexpr int TC_CG = 32;            // accumulator columns per worker warp (4 column groups)
+constexpr int TC_TMEM_COLS = 512;    // two accumulator sets of (re | im) x 128 columns
+constexpr int TC_SET_COLS = 256;
+constexpr int TC_CG = 32;            // accumulator columns per warp (4 column groups)
 
 struct TcSmem {
     // one operand array = 128 rows x 16 float16 in the canonical no-swizzle K-major layout:
@@ -74,8 +80,12 @@ struct TcSmem {
     // i.e. 8 x 16-byte core matrices, LBO (K direction) = 128 B, SBO (row direction) = 256 B
     static constexpr int ARR = TC_M * TC_KS * 2;              // 4 KB
     static constexpr int XR_H = 0, XR_L = ARR, XI_H = 2 * ARR, XI_L = 3 * ARR;
-    static constexpr int YR_H = 4 * ARR, YR_L = 5 * ARR, YI_H = 6 * ARR, YI_L = 7 * ARR;
-    static constexpr int STAGE = 8 * ARR;                     // 32 KB
+    // B operands are 2 N rows tall, (re ; im) stacked.  P = (Yr ; Yi) pairs with Er, M = (Yi ; -Yr)
+    // with Ei: both are windows of ONE buffer of three halves (Yr ; Yi ; -Yr), M starting N rows =
+    // (N / 8) * 256 bytes after P (the backward kernel stores (-Hi ; Hr ; Hi): M first, then P).
+    static constexpr int BBUF = 3 * ARR;                      // 12 KB per three-half buffer
+    static constexpr int B_H = 4 * ARR, B_L = B_H + BBUF;
+    static constexpr int STAGE = 4 * ARR + 2 * BBUF;          // 40 KB
     // source slot: 16 x (x, y, z, 0) float64 unit vectors, then 16 float32 sky values
     static constexpr int SRC_SHAT = TC_KS * 32, SRC_A = TC_KS * 4, SRC_SLOT = SRC_SHAT + SRC_A;
     static constexpr int SRC_OFF = TC_NSTAGE * STAGE;
@@ -94,10 +104,9 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(128 >> 4) << 16) |
            ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
 }
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int n, bool neg_a) {
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
     // D = F32 (bits 4..5 = 1), A = B = F16 (0), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
-    return (1u << 4) | (neg_a ? (1u << 13) : 0u) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(TC_M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -125,9 +134,7 @@ __device__ __forceinline__ void tc_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
-#if !(B200_TC_PROBE & 8)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
 }
 // 8 consecutive columns of the warp's 32 TMEM lanes -> 8 registers per thread (issue only)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -140,6 +147,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // mbarrier wait with a bound: a protocol error traps instead of hanging the GPU
@@ -163,31 +182,26 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
 
 // exp(2 pi i frac(p)) for t = p + 1.5 * 2^20, p the phase in cycles (|p| < 2^19) summed onto the
 // offset with FMAs: the offset makes the ulp of t 2^-32 cycles, so the low mantissa word of t is
-// the phase fraction as a 32-bit fixed-point number.  It is turned into a float in
-// [-2^22, 2^22) with an exponent trick and scaled to radians for MUFU sine / cosine.
+// the phase fraction as a signed 32-bit fixed-point number in [-1/2, 1/2): one integer
+// conversion, one scaling to radians, MUFU sine / cosine.
 __device__ __forceinline__ void antenna_cis(double t, float& c, float& s) {
 #if B200_TC_PROBE & 1
     c = __uint_as_float(__double2loint(t)) * 1e-30f + 0.5f;
     s = 0.25f;
     return;
 #endif
-    const uint32_t lo = (uint32_t)__double2loint(t);
-    const float fb = __uint_as_float((lo >> 9) ^ 0x4B400000u) - 12582912.0f;
-    const float ang = fb * 7.4901405e-07f;          // 2 pi / 2^23
+    const float ang = __int2float_rn(__double2loint(t)) * 1.4629180792671596e-09f;   // 2 pi / 2^32
     c = __cosf(ang);
     s = __sinf(ang);
 }
-__device__ __forceinline__ double phase_fma(const double (&p)[3], const double4& sv) {
-    return __fma_rn(p[0], sv.x, __fma_rn(p[1], sv.y, __fma_rn(p[2], sv.z, 1572864.0)));
-}
 
-// hi / lo float16 split of 4 values -> two 8-byte half rows.  lo = v - float(hi) is one
+// hi / lo float16 split of 8 values -> two 16-byte core-matrix rows.  lo = v - float(hi) is one
 // mixed-precision FMA (FHFMA: float16 x float16 + float32), exact before its final rounding.
-__device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo) {
-    uint32_t h[2], l[2];
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
     const unsigned short m1 = 0xBC00;               // -1.0 in float16
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 4; ++q) {
         const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
         const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hh);
         float l0, l1;
@@ -197,30 +211,13 @@ __device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo
         h[q] = hu;
         l[q] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    hi = make_uint2(h[0], h[1]);
-    lo = make_uint2(l[0], l[1]);
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// (cos, sin) of 4 sources -> the four arrays (re_hi, re_lo, im_hi, im_lo) of one operand
-__device__ __forceinline__ void store_split(unsigned char* dst, const float (&c)[4], const float (&s)[4]) {
-    uint2 hi, lo;
-    split4(c, hi, lo);
-    *reinterpret_cast<uint2*>(dst) = hi;
-    *reinterpret_cast<uint2*>(dst + TcSmem::ARR) = lo;
-    split4(s, hi, lo);
-    *reinterpret_cast<uint2*>(dst + 2 * TcSmem::ARR) = hi;
-    *reinterpret_cast<uint2*>(dst + 3 * TcSmem::ARR) = lo;
+__device__ __forceinline__ uint4 neg_half8(const uint4& v) {      // sign flip of 8 float16
+    return make_uint4(v.x ^ 0x80008000u, v.y ^ 0x80008000u, v.z ^ 0x80008000u, v.w ^ 0x80008000u);
 }
-
-// hi / lo split of 8 values -> two 16-byte core-matrix rows
-__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
-    const float a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
-    uint2 h0, l0, h1, l1;
-    split4(a, h0, l0);
-    split4(b, h1, l1);
-    hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
-    lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
-}
-// (cos, sin) of 8 sources -> the four arrays (re_hi, re_lo, im_hi, im_lo) of one operand row
+// (cos, sin) of 8 sources -> the four arrays (re_hi, re_lo, im_hi, im_lo) of an A operand row
 __device__ __forceinline__ void store_split8(unsigned char* dst, const float (&c)[8], const float (&s)[8]) {
     uint4 hi, lo;
     split8(c, hi, lo);
@@ -241,52 +238,34 @@ __device__ __forceinline__ void cis8(const double (&p)[3], const unsigned char* 
     }
 }
 
-// one lane of a converged warp
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred P;\n"
-        "elect.sync _|P, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, P;\n"
-        "}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
 struct TcIssue {                 // state of the issuing warp (warp-uniform values)
-    uint32_t tmem, id_pos, id_neg, smem_base;
+    uint32_t tmem, idesc, smem_base;
+    uint32_t poff, moff;         // byte offsets of the P and M windows inside a B buffer
 };
 
+// the six MMAs of one stage: (Re | Im) += A_re (P) + A_im (M), three float16 split terms each
 __device__ __forceinline__ void tc_issue_stage(const TcIssue& q, int stage, int set, bool first) {
-    const uint32_t d_re = q.tmem + set * TC_SET_COLS, d_im = d_re + TC_IM_COL;
+    const uint32_t d = q.tmem + set * TC_SET_COLS;            // Re columns [0, N), Im [N, 2 N)
     const uint32_t b = q.smem_base + stage * TcSmem::STAGE;
-    const uint64_t xrh = umma_desc_kmajor(b + TcSmem::XR_H), xrl = umma_desc_kmajor(b + TcSmem::XR_L),
-                   xih = umma_desc_kmajor(b + TcSmem::XI_H), xil = umma_desc_kmajor(b + TcSmem::XI_L),
-                   yrh = umma_desc_kmajor(b + TcSmem::YR_H), yrl = umma_desc_kmajor(b + TcSmem::YR_L),
-                   yih = umma_desc_kmajor(b + TcSmem::YI_H), yil = umma_desc_kmajor(b + TcSmem::YI_L);
-    const uint32_t acc = first ? 0u : 1u;
-    // Re V = Er.Yr + Ei.Yi
-    umma_f16(d_re, xrh, yrh, q.id_pos, acc);
-    umma_f16(d_re, xrh, yrl, q.id_pos, 1u);
-    umma_f16(d_re, xrl, yrh, q.id_pos, 1u);
-    umma_f16(d_re, xih, yih, q.id_pos, 1u);
-    umma_f16(d_re, xih, yil, q.id_pos, 1u);
-    umma_f16(d_re, xil, yih, q.id_pos, 1u);
-    // Im V = Er.Yi - Ei.Yr
-    umma_f16(d_im, xrh, yih, q.id_pos, acc);
-    umma_f16(d_im, xrh, yil, q.id_pos, 1u);
-    umma_f16(d_im, xrl, yih, q.id_pos, 1u);
-    umma_f16(d_im, xih, yrh, q.id_neg, 1u);
-    umma_f16(d_im, xih, yrl, q.id_neg, 1u);
-    umma_f16(d_im, xil, yrh, q.id_neg, 1u);
+    const uint64_t arh = umma_desc_kmajor(b + TcSmem::XR_H), arl = umma_desc_kmajor(b + TcSmem::XR_L),
+                   aih = umma_desc_kmajor(b + TcSmem::XI_H), ail = umma_desc_kmajor(b + TcSmem::XI_L),
+                   bph = umma_desc_kmajor(b + TcSmem::B_H + q.poff),
+                   bpl = umma_desc_kmajor(b + TcSmem::B_L + q.poff),
+                   bmh = umma_desc_kmajor(b + TcSmem::B_H + q.moff),
+                   bml = umma_desc_kmajor(b + TcSmem::B_L + q.moff);
+    umma_f16(d, arh, bph, q.idesc, first ? 0u : 1u);
+    umma_f16(d, arh, bpl, q.idesc, 1u);
+    umma_f16(d, arl, bph, q.idesc, 1u);
+    umma_f16(d, aih, bmh, q.idesc, 1u);
+    umma_f16(d, aih, bml, q.idesc, 1u);
+    umma_f16(d, ail, bmh, q.idesc, 1u);
 }
 
-// one worker warp adds accumulator set `set` (its 32 TMEM lanes x its 32 columns, re and im) to
-// its register accumulators and hands the set back to the issuing lane
+// one warp adds accumulator set rc & 1 (its 32 TMEM lanes x its 32 columns, re at column 0 and im
+// at column im_col of the set) to its register accumulators and hands the set back
 __device__ __forceinline__ void tc_read_chain(uint64_t* tfull, uint64_t* tempty, int rc,
-                                              uint32_t ta0, float (&aR)[TC_CG], float (&aI)[TC_CG],
-                                              int lane) {
+                                              uint32_t ta0, uint32_t im_col, float (&aR)[TC_CG],
+                                              float (&aI)[TC_CG], int lane) {
     const int set = rc & 1;
     mbar_wait_bounded(&tfull[set], (uint32_t)((rc >> 1) & 1));
     tc_fence_after();
@@ -295,7 +274,7 @@ __device__ __forceinline__ void tc_read_chain(uint64_t* tfull, uint64_t* tempty,
     for (int g = 0; g < TC_CG / 8; ++g) {
         uint32_t vr[8], vi[8];
         tmem_ld8(ta + 8 * g, vr);
-        tmem_ld8(ta + TC_IM_COL + 8 * g, vi);
+        tmem_ld8(ta + im_col + 8 * g, vi);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -309,16 +288,16 @@ __device__ __forceinline__ void tc_read_chain(uint64_t* tfull, uint64_t* tempty,
 }
 
 // -------------------------------------------------------------------------------------
-// forward.  grid = (nitems * nfreq, nunits), block = 544.
+// forward.  grid = (nitems * nfreq, nunits), block = 512.
 //   Acm      float [Nfp][S]     perceived sky, channel-major (row k = channel k over the packed
 //                                source axis): the 16 values of a stage are one 64-byte bulk copy
 //   items    int32 [nitems][4]  {i0, j0, N, 0}: X rows = antennas i0 .. i0 + 127, Y rows =
 //                                antennas j0 .. j0 + N - 1 (N a multiple of 32, <= 128)
 //   pair_bl  int32 [ldp][ldp]   (baseline << 1 | conj) of V_ij = sum conj(E_i) A E_j, or -1
 //   ascale   float [1]          power of two that brings max |A| into [2^14, 2^15)
-// Worker thread p: operand row (p & 255) >> 1, sources 4 kq .. 4 kq + 3 of the stage with
-// kq = 2 (p >> 8) + (p & 1) (pairs of lanes fill one 16-byte core-matrix row); accumulators: TMEM
-// lane quarter warp & 3, columns 32 (warp >> 2) .. + 31.
+// A operand X = E_i (re, im; hi, lo), B windows P = (Yr ; Yi), M = (Yi ; -Yr) of the buffer
+// (Yr ; Yi ; -Yr) with Y = A E_j:
+//   Re V = Er.Yr + Ei.Yi,   Im V = Er.Yi - Ei.Yr.
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ ascale,
@@ -356,7 +335,7 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
         for (int st = 0; st < TC_NSRC; ++st) mbar_init(&sfull[st], 1);
         for (int q = 0; q < 2; ++q) {
             mbar_init(&tfull[q], 1);
-            mbar_init(&tempty[q], TC_WORK_WARPS);
+            mbar_init(&tempty[q], TC_WARPS);
         }
         mbar_fence_init();
     }
@@ -374,112 +353,125 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
     const uint32_t tmem = *tmem_slot;
     const float* Ak = Acm + (size_t)k * (size_t)S;
 
-    // warp roles: q = TMEM lane quarter (and operand rows 32 q ..), cg = accumulator column group;
-    // warp 0 = control, warps 1..3 read-out only, warps 4..15 = generating groups cg - 1
+    // q = TMEM lane quarter (and operand rows 32 q ..), cg = accumulator column group
     const int q = warp & 3, cg = warp >> 2;
     const int role = __shfl_sync(0xffffffffu, warp, 0);              // warp-uniform warp index
     const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_CG * cg);
+    const uint32_t im_col = (uint32_t)N;
     const float sc = __ldg(ascale);
     float aR[TC_CG], aI[TC_CG];
 #pragma unroll
     for (int c = 0; c < TC_CG; ++c) aR[c] = aI[c] = 0.f;
     int next_read = 0;
-    {
-        if (role == TC_CTRL_WARP) {
-            // ---------------- control warp: source staging by TMA, MMA issue (uniform datapath)
-            TcIssue iq;
-            iq.tmem = tmem;
-            iq.id_pos = umma_idesc_f16(N, false);
-            iq.id_neg = umma_idesc_f16(N, true);
-            iq.smem_base = smem_u32(smem);
-            auto stage_sources = [&](int st) {
-                const int slot = st % TC_NSRC;
-                unsigned char* dst = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
-                const long long s0 = (long long)un.y + (long long)st * TC_KS;
-                mbar_expect_tx(&sfull[slot], TcSmem::SRC_SLOT);
-                bulk_g2s(dst, shat + 4 * s0, TcSmem::SRC_SHAT, &sfull[slot]);
-                bulk_g2s(dst + TcSmem::SRC_SHAT, Ak + s0, TcSmem::SRC_A, &sfull[slot]);
-            };
-            if (elect_one())
-                for (int st = 0; st < min(nst, TC_NSRC); ++st) stage_sources(st);
-            __syncwarp();
-            for (int it = 0; it < nst; ++it) {
-                const int stage = it % TC_NSTAGE, chain = it / TC_FLUSH, set = chain & 1;
-                const bool first = (it % TC_FLUSH) == 0;
-                if (first) {
-                    // this warp's own share of the read-out, then: the set's previous chain has
-                    // been read out by everybody
-                    while (next_read <= chain - 2)
-                        tc_read_chain(tfull, tempty, next_read++, ta0, aR, aI, lane);
-                    if (chain >= 2)
-                        mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
-                }
-                mbar_wait_bounded(&full[stage], (uint32_t)((it / TC_NSTAGE) & 1));
-                tc_fence_after();
-                if (elect_one()) {
-                    tc_issue_stage(iq, stage, set, first);
-                    umma_commit(&empty[stage]);       // stage free once these MMAs have read it
-                    if ((it % TC_FLUSH) == TC_FLUSH - 1 || it == nst - 1) umma_commit(&tfull[set]);
-                    // the owning group has consumed the source slot of this stage: refill it
-                    if (it + TC_NSRC < nst) stage_sources(it + TC_NSRC);
-                }
-                __syncwarp();
-            }
-        } else if (cg >= 1) {
-            // ---------------- generating groups: thread <-> operand row 32 q + lane in both roles,
-            // all 16 sources of the stages it = cg - 1 (mod 3)
-            const int row = 32 * q + lane;
-            const int nx = min(TC_M, na - i0), ny = min(N, na - j0);      // live X / Y rows
-            const bool xlive = row < nx, ylive = row < ny, diag = (i0 == j0);
-            const double kappa = sgn_over_c * freqs[k];
-            // antenna positions in cycles per unit direction cosine: phase = r' . shat
-            double xp[3] = {0.0, 0.0, 0.0}, yp[3] = {0.0, 0.0, 0.0};
-            if (xlive) {
-                const double* a = antv + 4 * (size_t)(i0 + row);
-                xp[0] = kappa * a[0], xp[1] = kappa * a[1], xp[2] = kappa * a[2];
-            }
-            if (ylive) {
-                const double* a = antv + 4 * (size_t)(j0 + row);
-                yp[0] = kappa * a[0], yp[1] = kappa * a[1], yp[2] = kappa * a[2];
-            }
-            const int roff = (row >> 3) * 256 + (row & 7) * 16;
-            for (int it = cg - 1; it < nst; it += TC_GROUPS) {
-                while (next_read <= it / TC_FLUSH - 2)
-                    tc_read_chain(tfull, tempty, next_read++, ta0, aR, aI, lane);
-                const int stage = it % TC_NSTAGE, slot = it % TC_NSRC;
-                mbar_wait_bounded(&sfull[slot], (uint32_t)((it / TC_NSRC) & 1));
-                if (it >= TC_NSTAGE)
-                    mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
-                const unsigned char* src = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
-                unsigned char* dst = smem + stage * TcSmem::STAGE + roff;
-#pragma unroll 1
-                for (int kg = 0; kg < ((B200_TC_PROBE & 4) ? 0 : 2); ++kg) {
-                    float c[8], s[8];
-                    const unsigned char* sh = src + kg * 8 * 32;
-                    if (xlive || (diag && ylive)) cis8(xp, sh, c, s);
-                    if (xlive) store_split8(dst + kg * 128 + TcSmem::XR_H, c, s);
-                    if (ylive) {
-                        if (!diag) cis8(yp, sh, c, s);
-                        const float4 a0 = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT)[2 * kg];
-                        const float4 a1 = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT)[2 * kg + 1];
-                        const float a[8] = {a0.x * sc, a0.y * sc, a0.z * sc, a0.w * sc,
-                                            a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc};
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            c[e] *= a[e];
-                            s[e] *= a[e];
-                        }
-                        store_split8(dst + kg * 128 + TcSmem::YR_H, c, s);
-                    }
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);
-            }
-        }
-        while (next_read < nchain) tc_read_chain(tfull, tempty, next_read++, ta0, aR, aI, lane);
 
-        // ---- scatter through the pair table
+    if (role == TC_CTRL_WARP) {
+        // ---------------- control warp: source staging by TMA, MMA issue (uniform datapath)
+        TcIssue iq;
+        iq.tmem = tmem;
+        iq.idesc = umma_idesc_f16(2 * N);
+        iq.smem_base = smem_u32(smem);
+        iq.poff = 0;
+        iq.moff = (uint32_t)((N >> 3) * 256);
+        auto stage_sources = [&](int st) {
+            const int slot = st % TC_NSRC;
+            unsigned char* dst = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
+            const long long s0 = (long long)un.y + (long long)st * TC_KS;
+            mbar_expect_tx(&sfull[slot], TcSmem::SRC_SLOT);
+            bulk_g2s(dst, shat + 4 * s0, TcSmem::SRC_SHAT, &sfull[slot]);
+            bulk_g2s(dst + TcSmem::SRC_SHAT, Ak + s0, TcSmem::SRC_A, &sfull[slot]);
+        };
+        if (elect_one())
+            for (int st = 0; st < min(nst, TC_NSRC); ++st) stage_sources(st);
+        __syncwarp();
+        for (int it = 0; it < nst; ++it) {
+            const int stage = it % TC_NSTAGE, chain = it / TC_FLUSH, set = chain & 1;
+            const bool first = (it % TC_FLUSH) == 0;
+            if (first) {
+                // this warp's own share of the read-out, then: the set's previous chain has
+                // been read out by everybody
+                while (next_read <= chain - 2)
+                    tc_read_chain(tfull, tempty, next_read++, ta0, im_col, aR, aI, lane);
+                if (chain >= 2)
+                    mbar_wait_bounded(&tempty[set], (uint32_t)(((chain >> 1) - 1) & 1));
+            }
+            mbar_wait_bounded(&full[stage], (uint32_t)((it / TC_NSTAGE) & 1));
+            tc_fence_after();
+            if (elect_one()) {
+                tc_issue_stage(iq, stage, set, first);
+                umma_commit(&empty[stage]);       // stage free once these MMAs have read it
+                if ((it % TC_FLUSH) == TC_FLUSH - 1 || it == nst - 1) umma_commit(&tfull[set]);
+                // the owning group has consumed the source slot of this stage: refill it
+                if (it + TC_NSRC < nst) stage_sources(it + TC_NSRC);
+            }
+            __syncwarp();
+        }
+    } else if (cg >= 1) {
+        // ---------------- generating groups: thread <-> operand row 32 q + lane in both roles,
+        // all 16 sources of the stages it = cg - 1 (mod 3)
+        const int row = 32 * q + lane;
+        const int nx = min(TC_M, na - i0), ny = min(N, na - j0);      // live X / Y rows
+        const bool xlive = row < nx, ylive = row < ny, diag = (i0 == j0);
+        const double kappa = sgn_over_c * freqs[k];
+        // antenna positions in cycles per unit direction cosine: phase = r' . shat
+        double xp[3] = {0.0, 0.0, 0.0}, yp[3] = {0.0, 0.0, 0.0};
+        if (xlive) {
+            const double* a = antv + 4 * (size_t)(i0 + row);
+            xp[0] = kappa * a[0], xp[1] = kappa * a[1], xp[2] = kappa * a[2];
+        }
+        if (ylive) {
+            const double* a = antv + 4 * (size_t)(j0 + row);
+            yp[0] = kappa * a[0], yp[1] = kappa * a[1], yp[2] = kappa * a[2];
+        }
+        const int roff = (row >> 3) * 256 + (row & 7) * 16;
+        const int half2 = (N >> 3) * 256;              // second half of a stacked operand
+        for (int it = cg - 1; it < nst; it += TC_GROUPS) {
+            while (next_read <= it / TC_FLUSH - 2)
+                tc_read_chain(tfull, tempty, next_read++, ta0, im_col, aR, aI, lane);
+            const int stage = it % TC_NSTAGE, slot = it % TC_NSRC;
+            mbar_wait_bounded(&sfull[slot], (uint32_t)((it / TC_NSRC) & 1));
+            if (it >= TC_NSTAGE)
+                mbar_wait_bounded(&empty[stage], (uint32_t)(((it / TC_NSTAGE) - 1) & 1));
+            const unsigned char* src = smem + TcSmem::SRC_OFF + slot * TcSmem::SRC_SLOT;
+            unsigned char* dst = smem + stage * TcSmem::STAGE + roff;
+#pragma unroll 1
+            for (int kg = 0; kg < ((B200_TC_PROBE & 4) ? 0 : 2); ++kg) {
+                float c[8], s[8];
+                const unsigned char* sh = src + kg * 8 * 32;
+                if (xlive || (diag && ylive)) cis8(xp, sh, c, s);
+                if (xlive) store_split8(dst + kg * 128 + TcSmem::XR_H, c, s);
+                if (ylive) {
+                    if (!diag) cis8(yp, sh, c, s);
+                    const float4 a0 = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT)[2 * kg];
+                    const float4 a1 = reinterpret_cast<const float4*>(src + TcSmem::SRC_SHAT)[2 * kg + 1];
+                    const float a[8] = {a0.x * sc, a0.y * sc, a0.z * sc, a0.w * sc,
+                                        a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        c[e] *= a[e];
+                        s[e] *= a[e];
+                    }
+                    // (Yr ; Yi ; -Yr), hi and lo parts
+                    unsigned char* d = dst + kg * 128;
+                    uint4 rh, rl, ih, il;
+                    split8(c, rh, rl);
+                    split8(s, ih, il);
+                    *reinterpret_cast<uint4*>(d + TcSmem::B_H) = rh;
+                    *reinterpret_cast<uint4*>(d + TcSmem::B_H + half2) = ih;
+                    *reinterpret_cast<uint4*>(d + TcSmem::B_H + 2 * half2) = neg_half8(rh);
+                    *reinterpret_cast<uint4*>(d + TcSmem::B_L) = rl;
+                    *reinterpret_cast<uint4*>(d + TcSmem::B_L + half2) = il;
+                    *reinterpret_cast<uint4*>(d + TcSmem::B_L + 2 * half2) = neg_half8(rl);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+        }
+    }
+    while (next_read < nchain) tc_read_chain(tfull, tempty, next_read++, ta0, im_col, aR, aI, lane);
+
+    // ---- scatter through the pair table
+    {
         const int ai = i0 + 32 * q + lane;
         if (ai < na && TC_CG * cg < N) {
             const float inv = 1.f / sc;
@@ -509,23 +501,25 @@ tc_fringe_fwd_kernel(const float* __restrict__ Acm, const float* __restrict__ as
 }
 
 // -------------------------------------------------------------------------------------
-// backward.  grid = (nunits, nitem * nfreq), block = 544 (units fastest: CTAs that run together
+// backward.  grid = (nunits, nitem * nfreq), block = 512 (units fastest: CTAs that run together
 // share the cotangent operand of their (antenna block, channel) through L2).
 //
 // With the Hermitian cotangent matrix H[a][m] (ant_kernels.cu) the adjoints are
 //   y_a[s] = sum_m H[a][m] E_m[s],  p = conj(E_a[s]) y_a[s],
 //   dL/dA[s] = 1/2 sum_a Re p,      dL/dr_a = sum_s shat_s A_s (2 pi sgn nu / c) Im p.
 // y is a GEMM with M = sources (tiles of 128), N = antennas a (items of 128), K = partner antennas
-// m: the A operand E_m[s] is generated in shared memory (worker thread <-> source row, 4 of the
-// 16 antennas of a stage), the B operand H is fetched by TMA from a copy the host has scaled,
-// split into float16 hi / lo parts and laid out in the UMMA canonical order
-//   Hq[t][k][item][stage of 16 m][re_hi | re_lo | im_hi | im_lo][128 rows a x 16 m, canonical].
+// m: the A operand E_m[s] is generated in shared memory (generating thread <-> source row, all 16
+// antennas of a stage), the B operands come by TMA from a copy the host has scaled, split into
+// float16 hi / lo parts, stacked (re ; im) and laid out in the UMMA canonical order
+//   Hq[t][k][item][stage of 16 m][hi | lo][(-Hi ; Hr ; Hi): 384 rows x 16 m, canonical],
+//   M = (-Hi ; Hr) (rows 0..255) pairs with Ei, P = (Hr ; Hi) (rows 128..383) with Er:
+//   Re y = Er.Hr - Ei.Hi, Im y = Er.Hi + Ei.Hr
 // Chains of TC_FLUSH stages are added to register accumulators as in the forward kernel; after
-// the last chain of a source tile every worker regenerates E_a for its source and its 32 antennas,
+// the last chain of a source tile every warp regenerates E_a for its source and its 32 antennas,
 // forms p and reduces: dL/dA over its columns, then across the four column groups in a fixed
-// order through shared memory (one float per source and channel, written channel-major); dL/dr
-// over the 32 sources of the warp with a transposed shuffle reduction (lane <-> antenna),
-// accumulated over the tiles of the unit.
+// order through shared memory (summed by the read-out warps 1..3; one float per source and
+// channel, written channel-major); dL/dr over the 32 sources of the warp with a transposed
+// shuffle reduction (lane <-> antenna), accumulated over the tiles of the unit.
 //   mrange [nitem][2]: stages of 16 partner antennas [lo, hi) that hold cotangent entries for the
 //   item.  When only dL/dA is wanted H is the doubled lower triangle (a > m) and item ib stops
 //   after its own antennas; a baseline group that covers only some antenna blocks skips the
@@ -541,32 +535,8 @@ struct TcBwdSmem {
     static constexpr int BAR_OFF = RED_OFF + 2 * 4 * TC_M * 4;
     static constexpr int TMEM_OFF = BAR_OFF + (2 * TC_NSTAGE + 8) * 8;
     static constexpr int TOTAL = TMEM_OFF + 16;
-    static constexpr int H_BYTES = 4 * TcSmem::ARR;            // one stage of the cotangent operand
+    static constexpr int H_BYTES = 2 * TcSmem::BBUF;           // one stage of the cotangent operands (24 KB)
 };
-
-__device__ __forceinline__ void tc_issue_stage_bwd(const TcIssue& q, int stage, int set, bool first) {
-    const uint32_t d_re = q.tmem + set * TC_SET_COLS, d_im = d_re + TC_IM_COL;
-    const uint32_t b = q.smem_base + stage * TcSmem::STAGE;
-    const uint64_t erh = umma_desc_kmajor(b + TcSmem::XR_H), erl = umma_desc_kmajor(b + TcSmem::XR_L),
-                   eih = umma_desc_kmajor(b + TcSmem::XI_H), eil = umma_desc_kmajor(b + TcSmem::XI_L),
-                   hrh = umma_desc_kmajor(b + TcSmem::YR_H), hrl = umma_desc_kmajor(b + TcSmem::YR_L),
-                   hih = umma_desc_kmajor(b + TcSmem::YI_H), hil = umma_desc_kmajor(b + TcSmem::YI_L);
-    const uint32_t acc = first ? 0u : 1u;
-    // Re y = Er.Hr - Ei.Hi
-    umma_f16(d_re, erh, hrh, q.id_pos, acc);
-    umma_f16(d_re, erh, hrl, q.id_pos, 1u);
-    umma_f16(d_re, erl, hrh, q.id_pos, 1u);
-    umma_f16(d_re, eih, hih, q.id_neg, 1u);
-    umma_f16(d_re, eih, hil, q.id_neg, 1u);
-    umma_f16(d_re, eil, hih, q.id_neg, 1u);
-    // Im y = Er.Hi + Ei.Hr
-    umma_f16(d_im, erh, hih, q.id_pos, acc);
-    umma_f16(d_im, erh, hil, q.id_pos, 1u);
-    umma_f16(d_im, erl, hih, q.id_pos, 1u);
-    umma_f16(d_im, eih, hrh, q.id_pos, 1u);
-    umma_f16(d_im, eih, hrl, q.id_pos, 1u);
-    umma_f16(d_im, eil, hrh, q.id_pos, 1u);
-}
 
 // v[i] summed over the 32 lanes, result for index i = lane left in v[0] (31 shuffles)
 __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
@@ -598,7 +568,6 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     const int a0 = ai * TC_M;
     // all 128 columns are computed: the operand rows of antennas >= na are zero, so are their
     // sums, and the epilogue needs no column mask
-    const int N = TC_NMAX;
     const int nmst_all = nm_pad / TC_KS;
     const int2 mr = mrange[ai];
     const int mlo = max(0, mr.x), nmst = min(nmst_all, mr.y) - mlo;
@@ -637,8 +606,8 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
         }
         for (int q = 0; q < 2; ++q) {
             mbar_init(&tfull[q], 1);
-            mbar_init(&tempty[q], TC_WORK_WARPS);
-            mbar_init(&rbar[q], TC_WORK_WARPS);
+            mbar_init(&tempty[q], TC_WARPS);
+            mbar_init(&rbar[q], TC_WARPS);
             mbar_init(&rdone[q], 3);
         }
         mbar_fence_init();
@@ -657,8 +626,7 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     const uint32_t tmem = *tmem_slot;
 
     // warp roles as in the forward kernel: q = TMEM lane quarter = source rows 32 q .. of the tile,
-    // cg = column group = antennas a0 + 32 cg ..; warp 0 control, warps 1..3 read-out and the
-    // final sum over column groups, warps 4..15 generating groups cg - 1
+    // cg = column group = antennas a0 + 32 cg ..
     const int q = warp & 3, cg = warp >> 2;
     const int role = __shfl_sync(0xffffffffu, warp, 0);
     const uint32_t ta0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_CG * cg);
@@ -672,7 +640,7 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
 
     // chain rc -> registers; after the last chain of a source tile: the tile's epilogue
     auto read_chain = [&](int rc) {
-        tc_read_chain(tfull, tempty, rc, ta0, aR, aI, lane);
+        tc_read_chain(tfull, tempty, rc, ta0, (uint32_t)TC_NMAX, aR, aI, lane);
         if (rc % nct != nct - 1) return;
         const int tile = rc / nct;
         const long long s = (long long)un.y + (long long)tile * TC_M + 32 * q + lane;
@@ -737,9 +705,10 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
         // ---------------- control warp: MMA issue (uniform datapath)
         TcIssue iq;
         iq.tmem = tmem;
-        iq.id_pos = umma_idesc_f16(N, false);
-        iq.id_neg = umma_idesc_f16(N, true);
+        iq.idesc = umma_idesc_f16(2 * TC_NMAX);
         iq.smem_base = smem_u32(smem);
+        iq.moff = 0;                         // (-Hi ; Hr ; Hi): M = first two halves, P = last two
+        iq.poff = TcSmem::ARR;
         int g = 0;
         for (int tile = 0; tile < ntile; ++tile) {
             for (int ms = 0; ms < nmst; ++ms, ++g) {
@@ -754,7 +723,7 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
                 mbar_wait_bounded(&full[stage], (uint32_t)((g / TC_NSTAGE) & 1));
                 tc_fence_after();
                 if (elect_one()) {
-                    tc_issue_stage_bwd(iq, stage, set, first);
+                    tc_issue_stage(iq, stage, set, first);
                     umma_commit(&empty[stage]);
                     if ((ms % TC_FLUSH) == TC_FLUSH - 1 || ms == nmst - 1) umma_commit(&tfull[set]);
                 }
@@ -792,9 +761,9 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
             if (g >= TC_NSTAGE)
                 mbar_wait_bounded(&empty[stage], (uint32_t)(((g / TC_NSTAGE) - 1) & 1));
             if (q == 0 && lane == 0) {
-                // this thread also fetches the cotangent operand of the stage
+                // this thread also fetches the cotangent operands of the stage
                 mbar_expect_tx(&full[stage], TcBwdSmem::H_BYTES);
-                bulk_g2s(sbase + TcSmem::YR_H, Hbase + (size_t)ms * TcBwdSmem::H_BYTES,
+                bulk_g2s(sbase + TcSmem::B_H, Hbase + (size_t)ms * TcBwdSmem::H_BYTES,
                          TcBwdSmem::H_BYTES, &full[stage]);
             }
 #pragma unroll 1

@@ -851,9 +851,10 @@ class TcTiling:
         """G (nbl, nt, nf) complex64 -> (Hq, hscale): the Hermitian cotangent matrix
         H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m), 2 Re G_b for autos (lower_only: the
         doubled lower triangle a > m), scaled by the power of two hscale into float16 range,
-        split into float16 hi / lo parts and laid out as the UMMA B operand of tcfringe_bwd:
-        [nt][Nfp][item][stage of 16 m][re_hi | re_lo | im_hi | im_lo][16 row groups][2 k groups]
-        [8 rows][8 k]."""
+        split into float16 hi / lo parts and laid out as the stacked UMMA B operands of
+        tcfringe_bwd, the three-half buffers (-Hi ; Hr ; Hi) whose rows 0..255 / 128..383 are the
+        operands M = (-Hi ; Hr) / P = (Hr ; Hi):
+        [nt][Nfp][item][stage of 16 m][hi | lo][3 halves][16 row groups][2 k groups][8 rows][8 k]."""
         nbl, nt, nf = G.shape
         Gq = G.permute(1, 2, 0)                                    # (nt, nf, nbl)
         H = torch.zeros(nt, nfp, self.apad, self.nm_pad, dtype=torch.complex64, device=G.device)
@@ -877,9 +878,12 @@ class TcTiling:
         hi = Hr.to(torch.float16)
         lo = (Hr - hi.to(torch.float32)).to(torch.float16)
         del Hr, H
-        Q = torch.stack([hi[..., 0], lo[..., 0], hi[..., 1], lo[..., 1]], dim=2)   # (nt,nfp,4,a,m)
+        # stacked B operands of tcfringe_bwd: the three-half buffer (-Hi ; Hr ; Hi), hi and lo parts
+        # (M = (-Hi ; Hr) = rows 0..255, P = (Hr ; Hi) = rows 128..383)
+        Q = torch.stack([-hi[..., 1], hi[..., 0], hi[..., 1],
+                         -lo[..., 1], lo[..., 0], lo[..., 1]], dim=2)              # (nt,nfp,6,a,m)
         del hi, lo
-        Q = Q.reshape(nt, nfp, 4, self.nitem_bwd, 16, 8, self.nm_pad // 16, 2, 8)
+        Q = Q.reshape(nt, nfp, 6, self.nitem_bwd, 16, 8, self.nm_pad // 16, 2, 8)
         Q = Q.permute(0, 1, 3, 6, 2, 4, 7, 5, 8).contiguous()
         return Q, hscale
 

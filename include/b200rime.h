@@ -315,12 +315,14 @@ int b200rime_tcfringe_fwd_f32(const float* Acm, const float* ascale, const doubl
  * (M = sources, N = antennas a, K = partner antennas m), then p = conj(E_a) y_a,
  * dL/dA = 1/2 sum_a Re p and dL/dr_a = sum_s shat_s A_s (2 pi sgn nu / c) Im p (autograd of
  * rime_model.py:429 w.r.t. psky and of telescope_model.py:356 w.r.t. the antenna positions).
- *   Hq      float16 [nt][Nfp][nitem][nm_pad/16][4][16][2][8][8]: the Hermitian cotangent matrix
+ *   Hq      float16 [nt][Nfp][nitem][nm_pad/16][2][3][16][2][8][8]: the Hermitian cotangent matrix
  *           (as for antfringe_bwd: H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m),
  *           2 Re G_b for autos; when only dL/dA is wanted the doubled lower triangle a > m is
- *           enough), times hscale, split into float16 hi + lo, as UMMA K-major B operands:
- *           [item of 128 antennas a][stage of 16 m][re_hi | re_lo | im_hi | im_lo]
- *           [a / 8][m / 8][a % 8][m % 8]
+ *           enough), times hscale, split into float16 hi + lo, as STACKED UMMA K-major B operands
+ *           (one MMA of width 256 feeds the real and the imaginary accumulator):
+ *           [item of 128 antennas a][stage of 16 m][hi | lo][-Im H ; Re H ; Im H][a / 8][m / 8]
+ *           [a % 8][m % 8]; rows 0..255 of a buffer are the operand M = (-Im H ; Re H), rows
+ *           128..383 the operand P = (Re H ; Im H)
  *   hscale  float [1]   power of two that brings max |H| into [2^14, 2^15)
  *   Acm     float [Nfp][S] channel-major perceived sky (only for drpart, else NULL)
  *   nitem = ceil(na / 128), nm_pad = na rounded up to 16, na <= 512

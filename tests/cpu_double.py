@@ -292,12 +292,14 @@ def tcfringe_bwd(sfx, Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, 
     """Contract of b200rime_tcfringe_bwd_f32 (operand layout decoded back to the dense matrix)."""
     M = _lib.TC_ROWS
     nt, nfp = Hq.shape[0], Hq.shape[1]
-    assert Hq.shape[2:] == (nitem, nm_pad // 16, 4, 16, 2, 8, 8) and Hq.dtype == torch.float16
+    assert Hq.shape[2:] == (nitem, nm_pad // 16, 6, 16, 2, 8, 8) and Hq.dtype == torch.float16
     assert nitem == -(-na // M) and nm_pad % 16 == 0 and na <= nm_pad <= 512
-    # (nt,nfp,item,mst,4,rg,kg,r8,k8) -> (nt,nfp,4,item,rg,r8,mst,kg,k8) -> (nt,nfp,4,a,m)
-    Q = Hq.permute(0, 1, 4, 2, 5, 7, 3, 6, 8).reshape(nt, nfp, 4, nitem * M, nm_pad).double()
+    # (nt,nfp,item,mst,6,rg,kg,r8,k8) -> (nt,nfp,6,item,rg,r8,mst,kg,k8) -> (nt,nfp,6,a,m)
+    # planes: hi (-im ; re ; im), lo (-im ; re ; im)
+    Q = Hq.permute(0, 1, 4, 2, 5, 7, 3, 6, 8).reshape(nt, nfp, 6, nitem * M, nm_pad).double()
+    assert torch.equal(Q[:, :, 0], -Q[:, :, 2]) and torch.equal(Q[:, :, 3], -Q[:, :, 5])
     sc = float(hscale[0])
-    H = torch.complex(Q[:, :, 0] + Q[:, :, 1], Q[:, :, 2] + Q[:, :, 3]) / sc     # (nt, f, a, m)
+    H = torch.complex(Q[:, :, 1] + Q[:, :, 4], Q[:, :, 2] + Q[:, :, 5]) / sc     # (nt, f, a, m)
     sgn = -1.0 if conj else 1.0
     antp = torch.zeros(nitem * M, 4, dtype=torch.float64)
     antp[:na] = antv[:na].double()
