@@ -26,6 +26,8 @@ lib.b200rime_kc.argtypes = [_I]
 lib.b200rime_microbench.argtypes = [_I, _I, ctypes.POINTER(_D), ctypes.POINTER(_D)]
 lib.b200rime_airy_bwd_blocks.argtypes = [_I, _I]
 lib.b200rime_chisq_blocks.argtypes = [_I, _I]
+lib.b200rime_eq2top_f64.argtypes = [_P, _P, _L, ctypes.POINTER(_D), ctypes.POINTER(_D), _P, _P, _P]
+lib.b200rime_eq2top_f64.restype = _I
 
 _SIGS = {
     "fringe_sum_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _I, _P, _P],

@@ -7,9 +7,11 @@ Differences that matter:
   * ``TelescopeModel.eq2top`` answers from ``conv_cache`` (the reference's own cache, keyed
     exactly as rime_model.py:345 builds the key) and, on a miss, from astropy's ICRS -> AltAz
     when astropy is importable (the reference's own call).  Without astropy (this image) it
-    warns once and uses a rigid sky rotation about the celestial pole (no precession /
-    nutation / aberration -- parity with astropy is unpinned); ``eq2top_fn``
-    overrides both.
+    warns once and computes apparent places itself (IAU 1976 precession, IAU 1980 nutation
+    leading terms, annual aberration, apparent sidereal time; arcsecond-grade, parity with
+    astropy is unpinned): the per-time rotation is built on the host, the
+    per-source part runs in the CUDA kernel b200rime_eq2top when the model lives on a GPU;
+    ``eq2top_fn`` overrides both.
   * ``ArrayModel.gen_fringe`` keeps the reference signature and semantics for callers
     outside the RIME (imaging), but ``rime_model.RIME`` never calls it: the fringe is
     generated inside the CUDA kernels (ops.fringe_sum).
@@ -50,10 +52,18 @@ class TelescopeModel:
         key = key if key is not None else self.hash(time, ra)
         if key in self.conv_cache:
             return self.conv_cache[key]
-        ra_n, dec_n = utils.tensor2numpy(ra), utils.tensor2numpy(dec)
-        fn = self.eq2top_fn if self.eq2top_fn is not None else eq2top
-        angs = fn(self.location, time, ra_n, dec_n)
-        angs = torch.as_tensor(np.asarray(angs), device=self.device, dtype=self.dtype)
+        dev = torch.device(self.device) if self.device is not None else None
+        if self.eq2top_fn is None and not _have_astropy() and dev is not None and dev.type == 'cuda':
+            # the per-source part on the device
+            _warn_no_astropy()
+            angs = eq2top_device(self.location, time, ra, dec, dev)
+            if self.dtype is not None:
+                angs = angs.to(self.dtype)
+        else:
+            ra_n, dec_n = utils.tensor2numpy(ra), utils.tensor2numpy(dec)
+            fn = self.eq2top_fn if self.eq2top_fn is not None else eq2top
+            angs = fn(self.location, time, ra_n, dec_n)
+            angs = torch.as_tensor(np.asarray(angs), device=self.device, dtype=self.dtype)
         if store:
             self.conv_cache[key] = angs
         return angs
@@ -92,23 +102,125 @@ def _astropy_eq2top(location, time, ra, dec):
     return out.zen.deg, out.az.deg
 
 
+def _have_astropy():
+    try:
+        import astropy.coordinates  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
+def _warn_no_astropy():
+    global _WARNED_NO_ASTROPY
+    if not _WARNED_NO_ASTROPY:
+        import warnings
+        warnings.warn("bayeslim_b200: astropy is not installed; eq2top computes apparent places "
+                      "itself (IAU 1976 precession, IAU 1980 nutation leading terms, annual "
+                      "aberration; no UT1-UTC, polar motion or refraction: arcsecond-grade). Inject "
+                      "TelescopeModel.conv_cache or eq2top_fn for astropy-grade angles.")
+        _WARNED_NO_ASTROPY = True
+
+
 def eq2top(location, time, ra, dec):
     """(ra, dec) [deg] -> (zen, az) [deg] at `location` (lon, lat[, alt]) and Julian date `time`.
     With astropy installed this is the reference's ICRS -> AltAz transformation
     (telescope_model.py:469-502).  Without it (this image) it falls back, with a warning, to
-    eq2top_rigid: a rotation about the celestial pole, arcminutes away from astropy for J2000
-    coordinates observed today -- inject conv_cache or eq2top_fn for survey-grade geometry."""
-    global _WARNED_NO_ASTROPY
+    eq2top_apparent."""
     try:
         return _astropy_eq2top(location, time, ra, dec)
     except ImportError:
-        if not _WARNED_NO_ASTROPY:
-            import warnings
-            warnings.warn("bayeslim_b200: astropy is not installed; eq2top falls back to a rigid "
-                          "sky rotation (no precession / nutation / aberration). Inject "
-                          "TelescopeModel.conv_cache or eq2top_fn for astropy-grade angles.")
-            _WARNED_NO_ASTROPY = True
-        return eq2top_rigid(location, time, ra, dec)
+        _warn_no_astropy()
+        return eq2top_apparent(location, time, ra, dec)
+
+
+def _rot(axis, ang):
+    """Passive rotation matrix R_axis(ang) (IAU SOFA convention: rotates the frame by +ang)."""
+    c, s = np.cos(ang), np.sin(ang)
+    if axis == 1:
+        return np.array([[1, 0, 0], [0, c, s], [0, -s, c]])
+    if axis == 2:
+        return np.array([[c, 0, -s], [0, 1, 0], [s, 0, c]])
+    return np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]])
+
+
+def icrs_to_enu(location, jd_utc):
+    """(m9, v3): the 3 x 3 rotation from ICRS/J2000 unit vectors to local (East, North, Up) at
+    `location` (east lon, lat [deg]) and UTC Julian date, and the observer's velocity / c in the
+    same frame (annual aberration).  Precession: IAU 1976 (zeta, z, theta); nutation: the nine
+    largest terms of the IAU 1980 series; sidereal time: IAU 1982 GMST (UT1 = UTC) plus the
+    equation of the equinoxes.  Frame bias, polar motion, diurnal aberration and refraction are
+    left out (each < 0.4 arcsec)."""
+    asec = np.pi / 180.0 / 3600.0
+    jd_tt = jd_utc + 69.184 / 86400.0
+    T = (jd_tt - 2451545.0) / 36525.0
+    zeta = (2306.2181 * T + 0.30188 * T ** 2 + 0.017998 * T ** 3) * asec
+    z = (2306.2181 * T + 1.09468 * T ** 2 + 0.018203 * T ** 3) * asec
+    theta = (2004.3109 * T - 0.42665 * T ** 2 - 0.041833 * T ** 3) * asec
+    P = _rot(3, -z) @ _rot(2, theta) @ _rot(3, -zeta)
+    d2r = np.pi / 180.0
+    Om = (125.04452 - 1934.136261 * T) * d2r          # lunar node
+    Ls = (280.4665 + 36000.7698 * T) * d2r            # mean longitude of the Sun
+    Lm = (218.3165 + 481267.8813 * T) * d2r           # ... of the Moon
+    Ms = (357.52772 + 35999.050340 * T) * d2r         # mean anomaly of the Sun
+    Mm = (134.96298 + 477198.867398 * T) * d2r        # ... of the Moon
+    dpsi = (-17.1996 * np.sin(Om) - 1.3187 * np.sin(2 * Ls) - 0.2274 * np.sin(2 * Lm)
+            + 0.2062 * np.sin(2 * Om) + 0.1426 * np.sin(Ms) + 0.0712 * np.sin(Mm)
+            - 0.0517 * np.sin(2 * Ls + Ms) - 0.0386 * np.sin(2 * Lm - Om)
+            - 0.0301 * np.sin(2 * Lm + Mm)) * asec
+    deps = (9.2025 * np.cos(Om) + 0.5736 * np.cos(2 * Ls) + 0.0977 * np.cos(2 * Lm)
+            - 0.0895 * np.cos(2 * Om) + 0.0054 * np.cos(Ms) + 0.0224 * np.cos(2 * Ls + Ms)
+            + 0.0200 * np.cos(2 * Lm - Om) + 0.0129 * np.cos(2 * Lm + Mm)) * asec
+    eps0 = (84381.448 - 46.8150 * T - 0.00059 * T ** 2 + 0.001813 * T ** 3) * asec
+    N = _rot(1, -(eps0 + deps)) @ _rot(3, -dpsi) @ _rot(1, eps0)
+    d = jd_utc - 2451545.0
+    Tu = d / 36525.0
+    gmst = (280.46061837 + 360.98564736629 * d + 0.000387933 * Tu ** 2 - Tu ** 3 / 38710000.0) * d2r
+    gast = gmst + dpsi * np.cos(eps0 + deps)
+    lon, lat = location[0] * d2r, location[1] * d2r
+    # true equator of date -> local meridian frame (x' to the meridian, y' east, z' pole)
+    Rl = _rot(3, gast + lon)
+    # -> East, North, Up
+    H = np.array([[0.0, 1.0, 0.0],
+                  [-np.sin(lat), 0.0, np.cos(lat)],
+                  [np.cos(lat), 0.0, np.sin(lat)]])
+    m9 = H @ Rl @ N @ P
+    # annual aberration: Earth's velocity is 90 deg behind the Sun's apparent longitude
+    lam = Ls + (1.914602 - 0.004817 * T) * d2r * np.sin(Ms) + 0.019993 * d2r * np.sin(2 * Ms)
+    kappa = 20.49552 * asec
+    v_date = kappa * np.array([np.sin(lam), -np.cos(lam) * np.cos(eps0), -np.cos(lam) * np.sin(eps0)])
+    v3 = P.T @ v_date                                  # mean equator of date -> J2000
+    return np.ascontiguousarray(m9, dtype=np.float64), np.ascontiguousarray(v3, dtype=np.float64)
+
+
+def eq2top_apparent(location, time, ra, dec):
+    """Host (numpy) evaluation of icrs_to_enu's transformation: (ra, dec) [deg] -> (zen, az) [deg]."""
+    m9, v3 = icrs_to_enu(location, float(time))
+    ra = np.asarray(ra, dtype=np.float64) * D2R
+    dec = np.asarray(dec, dtype=np.float64) * D2R
+    p = np.stack([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)]) + v3[:, None]
+    p /= np.linalg.norm(p, axis=0)
+    e, n, u = m9 @ p
+    return np.arccos(np.clip(u, -1, 1)) / D2R, np.mod(np.arctan2(e, n), 2 * np.pi) / D2R
+
+
+def eq2top_device(location, time, ra, dec, device):
+    """The same on the GPU: (2, Nsrc) float64 tensor [zen, az] (b200rime_eq2top kernel)."""
+    import ctypes
+    from . import _lib
+    m9, v3 = icrs_to_enu(location, float(time))
+    ra_t = torch.as_tensor(ra).to(device=device, dtype=torch.float64).contiguous()
+    dec_t = torch.as_tensor(dec).to(device=device, dtype=torch.float64).contiguous()
+    out = torch.empty(2, ra_t.numel(), dtype=torch.float64, device=device)
+    dp = ctypes.POINTER(ctypes.c_double)
+    with torch.cuda.device(device):
+        rc = _lib.lib.b200rime_eq2top_f64(
+            ctypes.c_void_p(ra_t.data_ptr()), ctypes.c_void_p(dec_t.data_ptr()), ra_t.numel(),
+            m9.ctypes.data_as(dp), v3.ctypes.data_as(dp), ctypes.c_void_p(out[0].data_ptr()),
+            ctypes.c_void_p(out[1].data_ptr()),
+            ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    if rc != 0:
+        raise _lib.B200RimeError(_lib.lib.b200rime_last_error().decode())
+    return out
 
 
 def eq2top_rigid(location, time, ra, dec):

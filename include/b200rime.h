@@ -338,6 +338,18 @@ int b200rime_tcfringe_bwd_f32(const void* Hq, const float* hscale, const float* 
                               const int* mrange, int nfreq, long long S, int conj, float* dAcm,
                               float* drpart, b200rime_stream_t stream);
 
+/* ---- equatorial -> topocentric angles on the device ----------
+ * The per-source part of TelescopeModel.eq2top (telescope_model.py:469-502, astropy ICRS -> AltAz
+ * on the host in the reference): p = unit(ra, dec); p += v3 (annual aberration, first order),
+ * renormalise; (E, N, U) = m9 p; zen = acos U, az = atan2(E, N) in [0, 360) degrees.  m9 (row-major
+ * 3 x 3, ICRS -> East / North / Up at the observation time) and v3 (observer velocity / c, ICRS;
+ * NULL = no aberration) are HOST arrays (telescope_model.icrs_to_enu builds them: IAU 1976
+ * precession, IAU 1980 nutation leading terms, apparent sidereal time, latitude).  ra, dec, zen,
+ * az: device float64 [n].  No refraction. */
+int b200rime_eq2top_f64(const double* ra_deg, const double* dec_deg, long long n, const double* m9,
+                        const double* v3, double* zen_deg, double* az_deg,
+                        b200rime_stream_t stream);
+
 /* ---- Jones sandwich of the polarised beam modes -------------------------------------------
  * P[a][d] = sum_{b,c} J1[a][b] C[b][c] J2[d][c] for real 2 x 2 Jones planes and coherency planes
  * (beam_model.py:347, :363 einsum "ab...,bc...,dc...->ad..."), element-wise over n elements per

@@ -693,3 +693,63 @@ def jones_gains(params, param_type, freqs=None, refant_idx=None):
     else:
         raise ValueError(param_type)
     return p, g
+
+
+# --------------------------------------------------------------------------
+# apparent-place eq2top -- PARITY UNPINNED against astropy
+# --------------------------------------------------------------------------
+def eq2top_apparent(jd_utc, ra_deg, dec_deg, lon_deg, lat_deg):
+    """ICRS/J2000 (ra, dec) -> (zen, az) [deg] in the classical spherical-trigonometry form
+    (Meeus, Astronomical Algorithms, ch. 21-23): rigorous IAU 1976 precession of (alpha, delta),
+    first-order nutation (23.1) and annual aberration (23.2, eccentricity terms dropped) corrections,
+    apparent sidereal time, then altitude / azimuth (13.5, 13.6).  Stands in for the astropy call of
+    telescope_model.py:469-502, which cannot be pinned here (astropy absent, no golden values in
+    the reference); the product builds the same transformation as one rotation matrix
+    (telescope_model.icrs_to_enu), so the two derivations check each other to second order in the
+    20-arcsecond corrections."""
+    asec = np.pi / 180 / 3600
+    d2r = np.pi / 180
+    a0 = np.asarray(ra_deg, dtype=np.float64) * d2r
+    d0 = np.asarray(dec_deg, dtype=np.float64) * d2r
+    T = (jd_utc + 69.184 / 86400.0 - 2451545.0) / 36525.0
+    zeta = (2306.2181 * T + 0.30188 * T ** 2 + 0.017998 * T ** 3) * asec
+    z = (2306.2181 * T + 1.09468 * T ** 2 + 0.018203 * T ** 3) * asec
+    th = (2004.3109 * T - 0.42665 * T ** 2 - 0.041833 * T ** 3) * asec
+    A = np.cos(d0) * np.sin(a0 + zeta)
+    B = np.cos(th) * np.cos(d0) * np.cos(a0 + zeta) - np.sin(th) * np.sin(d0)
+    C = np.sin(th) * np.cos(d0) * np.cos(a0 + zeta) + np.cos(th) * np.sin(d0)
+    al = np.arctan2(A, B) + z
+    de = np.arcsin(np.clip(C, -1, 1))
+    Om = (125.04452 - 1934.136261 * T) * d2r
+    Ls = (280.4665 + 36000.7698 * T) * d2r
+    Lm = (218.3165 + 481267.8813 * T) * d2r
+    Ms = (357.52772 + 35999.050340 * T) * d2r
+    Mm = (134.96298 + 477198.867398 * T) * d2r
+    dpsi = (-17.1996 * np.sin(Om) - 1.3187 * np.sin(2 * Ls) - 0.2274 * np.sin(2 * Lm)
+            + 0.2062 * np.sin(2 * Om) + 0.1426 * np.sin(Ms) + 0.0712 * np.sin(Mm)
+            - 0.0517 * np.sin(2 * Ls + Ms) - 0.0386 * np.sin(2 * Lm - Om)
+            - 0.0301 * np.sin(2 * Lm + Mm)) * asec
+    deps = (9.2025 * np.cos(Om) + 0.5736 * np.cos(2 * Ls) + 0.0977 * np.cos(2 * Lm)
+            - 0.0895 * np.cos(2 * Om) + 0.0054 * np.cos(Ms) + 0.0224 * np.cos(2 * Ls + Ms)
+            + 0.0200 * np.cos(2 * Lm - Om) + 0.0129 * np.cos(2 * Lm + Mm)) * asec
+    eps0 = (84381.448 - 46.8150 * T - 0.00059 * T ** 2 + 0.001813 * T ** 3) * asec
+    eps = eps0 + deps
+    lam = Ls + (1.914602 - 0.004817 * T) * d2r * np.sin(Ms) + 0.019993 * d2r * np.sin(2 * Ms)
+    kap = 20.49552 * asec
+    # nutation (Meeus 23.1) and aberration (23.2) corrections of the mean place of date
+    da = ((np.cos(eps0) + np.sin(eps0) * np.sin(al) * np.tan(de)) * dpsi - np.cos(al) * np.tan(de) * deps
+          - kap * (np.cos(al) * np.cos(lam) * np.cos(eps0) + np.sin(al) * np.sin(lam)) / np.cos(de))
+    dd = (np.sin(eps0) * np.cos(al) * dpsi + np.sin(al) * deps
+          - kap * (np.cos(lam) * np.cos(eps0) * (np.tan(eps0) * np.cos(de) - np.sin(al) * np.sin(de))
+                   + np.cos(al) * np.sin(de) * np.sin(lam)))
+    al, de = al + da, de + dd
+    d = jd_utc - 2451545.0
+    Tu = d / 36525.0
+    gmst = (280.46061837 + 360.98564736629 * d + 0.000387933 * Tu ** 2 - Tu ** 3 / 38710000.0) * d2r
+    H = gmst + dpsi * np.cos(eps) + lon_deg * d2r - al
+    phi = lat_deg * d2r
+    sin_alt = np.sin(phi) * np.sin(de) + np.cos(phi) * np.cos(de) * np.cos(H)
+    zen = np.arccos(np.clip(sin_alt, -1, 1)) / d2r
+    az = np.mod(np.arctan2(-np.cos(de) * np.sin(H),
+                           np.sin(de) * np.cos(phi) - np.cos(de) * np.cos(H) * np.sin(phi)), 2 * np.pi) / d2r
+    return zen, az
