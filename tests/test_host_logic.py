@@ -335,3 +335,58 @@ def test_pointing_offset_through_host_logic(which):
         assert relmax(leaves["antvecs"].grad, g["grad_antvecs_interp"]) < 1e-9
     else:
         assert "pack" in calls and "build_airy" not in calls
+
+
+def test_cache_keys_and_user_level_clearing():
+    """the telescope cache is keyed (sky name, Nsources, time)
+    (rime_model.py:345-357), so two skies with the same name and length alias each other's
+    geometry until telescope.clear_cache(); replacing a cache entry or clearing the caches must
+    change / reproduce the result; beam.R.clear_cache() and array.clear_cache() keep working."""
+    g = load("rime_pixel_interp")
+    with emulated_kernels():
+        rime, _ = mc.build_pixel_interp(g, 'cpu', torch.float64, params=())
+        with torch.no_grad():
+            V0 = rime().data.clone()
+            npix = len(g["ra"])
+            keys = [(rime.sky.name, npix, t) for t in rime.sim_times]
+            assert all(k in rime.telescope.conv_cache for k in keys)
+            # 1. a replaced cache entry is picked up (the geometry record follows the tensors);
+            # the interpolation weights are cached under the same injected key, in the reference
+            # as here (utils.py:757-811), so the user clears the response cache with it
+            za = rime.telescope.conv_cache[keys[0]]
+            rime.telescope.conv_cache[keys[0]] = torch.stack([za[0] * 0.9, za[1]])
+            rime.beam.R.clear_cache()
+            V1 = rime().data.clone()
+            assert float((V1[:, :, :, 0] - V0[:, :, :, 0]).abs().max()) > 0
+            assert torch.equal(V1[:, :, :, 1:], V0[:, :, :, 1:])
+            rime.telescope.conv_cache[keys[0]] = za
+            rime.beam.R.clear_cache()
+            assert torch.equal(rime().data, V0)
+            # 2. clearing everything and re-injecting the same angles reproduces the result
+            rime.telescope.clear_cache()
+            rime.array.clear_cache()
+            rime.beam.R.clear_cache()
+            assert len(rime.telescope.conv_cache) == 0
+            for k, z in zip(keys, g["zen_az"]):
+                rime.telescope.conv_cache[k] = torch.as_tensor(z)
+            assert float((rime().data - V0).abs().max()) < 1e-13 * float(V0.abs().max())
+            # 3. the aliasing quirk: a second sky of the same name and length, at other
+            # positions, is simulated with the FIRST sky's cached angles ...
+            ang2 = rime.sky.angs.clone()
+            ang2[0] = (ang2[0] + 7.0) % 360
+            sky2 = ba.sky_model.PixelSky(rime.sky.params.detach().clone(), ang2, float(g["px_area"]),
+                                         R=rime.sky.R, parameter=False, name=rime.sky.name)
+            rime2 = ba.RIME(sky2, rime.telescope, rime.beam, rime.array, rime.sim_bls,
+                            rime.sim_times, rime.freqs, device='cpu')
+            from oracle import rime_oracle as orc
+            calls = []
+            rime.telescope.eq2top_fn = lambda loc, t, ra, dec: (calls.append(t) or
+                                                                orc.eq2top_synth(t, ra, dec, lat=loc[1]))
+            V2 = rime2().data
+            assert torch.equal(V2, V0) and calls == []
+            # ... until the telescope cache is cleared: then its own geometry is computed
+            rime.telescope.clear_cache()
+            rime.beam.R.clear_cache()
+            V3 = rime2().data
+            assert len(calls) == len(rime.sim_times)
+            assert float((V3 - V0).abs().max()) > 1e-6 * float(V0.abs().max())
