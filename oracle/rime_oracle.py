@@ -163,7 +163,20 @@ def fov_cut(zen, fov):
 # --------------------------------------------------------------------------
 # beams
 # --------------------------------------------------------------------------
-def airy_disk(zen, az, Dew, freqs, Dns=None, freq_ratio=1.0, square=True):
+def j1_trapezoid(x, Ntau=100):
+    """J1 from the Bessel integral (1/pi) int_0^pi cos(tau - x sin tau) dtau on Ntau nodes with
+    end weights 1/2 (special.py:498-533, the brute_force branch).  Differentiable in x."""
+    tau = torch.linspace(0, math.pi, Ntau, dtype=x.dtype)
+    h = tau[1] - tau[0]
+    acc = torch.zeros_like(x)
+    for i in range(Ntau):
+        w = 0.5 if i in (0, Ntau - 1) else 1.0
+        acc = acc + w * torch.cos(tau[i] - x * torch.sin(tau[i]))
+    return acc * h / math.pi
+
+
+def airy_disk(zen, az, Dew, freqs, Dns=None, freq_ratio=1.0, square=True, brute_force=False,
+              Ntau=100):
     """(2 J1(x)/x)^(2|1) with x = pi nu D(az) sin(min(zen, 90deg)) / c, clipped at 1e-10.
 
     zen, az in RADIANS (beam_model.py:1418-1482).  J1 = torch.special.bessel_j1
@@ -180,20 +193,23 @@ def airy_disk(zen, az, Dew, freqs, Dns=None, freq_ratio=1.0, square=True):
     freqs = torch.as_tensor(freqs)
     x = diameter * torch.sin(zen) * math.pi * freqs.reshape(-1, 1) * freq_ratio / C_LIGHT
     x = x.clip(1e-10)
-    beam = 2.0 * torch.special.bessel_j1(x) / x
+    j1 = j1_trapezoid(x, Ntau) if brute_force else torch.special.bessel_j1(x)
+    beam = 2.0 * j1 / x
     if square:
         beam = beam ** 2
     return beam
 
 
-def airy_response(params, zen, az, freqs, freq_ratio=1.0, powerbeam=True):
+def airy_response(params, zen, az, freqs, freq_ratio=1.0, powerbeam=True, brute_force=False,
+                  Ntau=100):
     """AiryResponse.__call__ (beam_model.py:956-985): zen/az in DEGREES, params
     (Npol, Nvec, Nmodel, 1, 1|2) -> beam (Npol, Nvec, Nmodel, Nf, Ns)."""
     Dew = params[..., 0:1]
     Dns = params[..., 1:2] if params.shape[-1] > 1 else None
     zen = torch.as_tensor(zen)
     az = torch.as_tensor(az)
-    return airy_disk(zen * D2R, az * D2R, Dew, freqs, Dns, freq_ratio, square=powerbeam)
+    return airy_disk(zen * D2R, az * D2R, Dew, freqs, Dns, freq_ratio, square=powerbeam,
+                     brute_force=brute_force, Ntau=Ntau)
 
 
 def gauss_response(params, zen, az, powerbeam=True):

@@ -164,6 +164,38 @@ def gold_rime_point_airy():
          grad_antvecs=array.antvecs.grad, fov=180.0)
 
 
+def gold_rime_airy_brute():
+    """AiryResponse(brute_force=True): the differentiable trapezoid J1 (special.py:498-535) through
+    the RIME; the gradient to the Airy diameter is the FULL one here."""
+    rng = np.random.default_rng(12)
+    freqs = torch.linspace(100e6, 200e6, 6)
+    times = np.linspace(2458148.15, 2458148.25, 2)
+    ants, vecs, array = hera_array(2, freqs)
+    bls = [(ants[i], ants[j]) for i in range(len(ants)) for j in range(i + 1, len(ants))]
+    Ns = 40
+    ra = rng.uniform(0, 360, Ns)
+    dec = np.degrees(np.arcsin(rng.uniform(-1, np.sin(np.radians(29)), Ns)))
+    angs = torch.as_tensor(np.stack([ra, dec]))
+    params = torch.zeros(1, 1, 2, Ns)
+    params[0, 0, 0] = torch.as_tensor(np.exp(rng.normal(size=Ns)))
+    params[0, 0, 1] = torch.as_tensor(rng.normal(-0.8, 0.2, Ns))
+    R = ba.sky_model.PointSkyResponse(freqs, freq_mode='powerlaw', f0=150e6)
+    sky = ba.sky_model.PointSky(params.clone(), angs, R=R, parameter=True)
+    bp = torch.ones(1, 1, 1, 1, 1) * 14.0
+    beam = ba.beam_model.PixelBeam(bp.clone(), freqs,
+                                   R=ba.beam_model.AiryResponse(powerbeam=True, brute_force=True, Ntau=64),
+                                   pol='e', powerbeam=True, fov=180, parameter=True)
+    tel = ba.telescope_model.TelescopeModel(LOC)
+    rime = ba.rime_model.RIME(sky, tel, beam, array, bls, times, freqs)
+    zen_az = inject_geometry(rime, sky.name, ra, dec, rime.sim_times)
+    vd = rime()
+    G = cotangent(vd.data.shape, 101)
+    backward_with(vd.data, G)
+    save("rime_airy_brute", antvecs=vecs, ants=ants, bls=bls, freqs=freqs, times=times,
+         ra=ra, dec=dec, zen_az=zen_az, sky_params=params, f0=150e6, beam_params=bp, Ntau=64,
+         vis=vd.data, G=G, grad_sky=sky.params.grad, grad_beam=beam.params.grad, fov=180.0)
+
+
 def healpix_sky(nside, freqs, rng, dec_max=59.27852):
     theta, phi = orc.healpix_pix2ang(nside)
     dec = np.pi / 2 - theta
@@ -596,6 +628,7 @@ if __name__ == "__main__":
     gold_airy()
     gold_rect_interp()
     gold_rime_point_airy()
+    gold_rime_airy_brute()
     gold_rime_pixel_interp()
     gold_rime_pointing()
     gold_rime_batched()

@@ -33,7 +33,15 @@ def _array(g, freqs, device, dtype, param=False):
     return ants, array
 
 
-def build_point_airy(g, device, dtype=torch.float64, params=("sky", "beam", "antvecs")):
+def build_airy_brute(g, device, dtype=torch.float64):
+    """AiryResponse(brute_force=True): no fused builder, the generic torch-response route."""
+    return build_point_airy(g, device, dtype, params=("sky", "beam"),
+                            response=ba.beam_model.AiryResponse(powerbeam=True, brute_force=True,
+                                                                Ntau=int(g["Ntau"])))
+
+
+def build_point_airy(g, device, dtype=torch.float64, params=("sky", "beam", "antvecs"),
+                     response=None):
     freqs = _t(g["freqs"], torch.float64, device)
     ants, array = _array(g, freqs, device, dtype, param="antvecs" in params)
     R = ba.sky_model.PointSkyResponse(freqs.to(dtype), freq_mode='powerlaw', f0=float(g["f0"]),
@@ -42,7 +50,8 @@ def build_point_airy(g, device, dtype=torch.float64, params=("sky", "beam", "ant
                                 _t(np.stack([g["ra"], g["dec"]]), torch.float64, device), R=R,
                                 parameter="sky" in params)
     beam = ba.beam_model.PixelBeam(_t(g["beam_params"], dtype, device), freqs,
-                                   R=ba.beam_model.AiryResponse(powerbeam=True), pol='e',
+                                   R=response if response is not None
+                                   else ba.beam_model.AiryResponse(powerbeam=True), pol='e',
                                    powerbeam=True, fov=float(g["fov"]), parameter="beam" in params)
     tel = ba.telescope_model.TelescopeModel(LOC, device=device)
     times = g["times"]
@@ -187,6 +196,7 @@ CASES = {
     "rime_pixel_interp": (build_pixel_interp, dict(sky="grad_sky", beam="grad_beam",
                                                    antvecs="grad_antvecs")),
     "rime_2pol": (build_2pol, dict(sky="grad_sky")),
+    "rime_airy_brute": (build_airy_brute, dict(sky="grad_sky", beam="grad_beam")),
     "rime_4pol": (build_4pol, dict(sky="grad_sky", beam="grad_beam", antvecs="grad_antvecs")),
     "rime_multimodel": (build_multimodel, dict(sky="grad_sky")),
     "rime_databls": (build_databls, dict(sky="grad_sky")),

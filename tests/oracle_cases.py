@@ -35,7 +35,7 @@ def real_loss(V, G):
     return torch.sum(G.real * V.real + G.imag * V.imag)
 
 
-def oracle_point_airy(g, dtype=torch.float64):
+def oracle_point_airy(g, dtype=torch.float64, brute_force=False):
     antvecs = tt(g["antvecs"], dtype, grad=True)
     sky_params = tt(g["sky_params"], dtype, grad=True)
     beam_params = tt(g["beam_params"], dtype, grad=True)
@@ -45,7 +45,8 @@ def oracle_point_airy(g, dtype=torch.float64):
     blvecs = orc.get_blvecs(antvecs, ants, bls)
     sky = orc.point_sky_response(sky_params, freqs, 'powerlaw', f0=float(g["f0"]))
     zenaz = [(tt(za[0], dtype), tt(za[1], dtype)) for za in g["zen_az"]]
-    beam_fn = lambda z, a: orc.airy_response(beam_params, z, a, freqs, powerbeam=True)
+    kw = dict(brute_force=True, Ntau=int(g["Ntau"])) if brute_force else {}
+    beam_fn = lambda z, a: orc.airy_response(beam_params, z, a, freqs, powerbeam=True, **kw)
     V = orc.rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=float(g["fov"]))
     return V, dict(sky=sky_params, beam=beam_params, antvecs=antvecs)
 

@@ -145,6 +145,15 @@ def test_rime_point_airy_vs_reference():
     _check(V, leaves, g, dict(sky="grad_sky", beam="grad_beam_truncated", antvecs="grad_antvecs"))
 
 
+def test_rime_airy_brute_force_vs_reference():
+    """AiryResponse(brute_force=True): trapezoid Bessel integral (special.py:498-533); the
+    gradient to the dish diameter is the full one (no truncation at bessel_j1)."""
+    g = oc.load("rime_airy_brute")
+    V, leaves = oc.oracle_point_airy(g, brute_force=True)
+    _check(V, leaves, g, dict(sky="grad_sky", beam="grad_beam"))
+    assert np.abs(g["grad_beam"]).max() > 0
+
+
 def test_rime_pixel_interp_vs_reference():
     g = oc.load("rime_pixel_interp")
     V, leaves = oc.oracle_pixel_interp(g)
