@@ -34,7 +34,7 @@ eq2top_kernel(const double* __restrict__ ra, const double* __restrict__ dec, lon
         const double e = a.m[0] * px + a.m[1] * py + a.m[2] * pz;
         const double nn = a.m[3] * px + a.m[4] * py + a.m[5] * pz;
         const double u = a.m[6] * px + a.m[7] * py + a.m[8] * pz;
-        zen[i] = acos(fmin(1.0, fmax(-1.0, u))) * r2d;
+        zen[i] = atan2(sqrt(e * e + nn * nn), u) * r2d;      // well conditioned at the zenith
         double azd = atan2(e, nn) * r2d;
         if (azd < 0.0) azd += 360.0;
         az[i] = azd;

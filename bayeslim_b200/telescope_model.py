@@ -200,7 +200,8 @@ def eq2top_apparent(location, time, ra, dec):
     p = np.stack([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)]) + v3[:, None]
     p /= np.linalg.norm(p, axis=0)
     e, n, u = m9 @ p
-    return np.arccos(np.clip(u, -1, 1)) / D2R, np.mod(np.arctan2(e, n), 2 * np.pi) / D2R
+    # atan2 form: arccos(u) loses half the digits near the zenith
+    return np.arctan2(np.hypot(e, n), u) / D2R, np.mod(np.arctan2(e, n), 2 * np.pi) / D2R
 
 
 def eq2top_device(location, time, ra, dec, device):

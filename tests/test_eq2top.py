@@ -25,8 +25,9 @@ def _angsep(z1, a1, z2, a2):
     d2r = np.pi / 180
     v = lambda z, a: np.stack([np.sin(z * d2r) * np.sin(a * d2r), np.sin(z * d2r) * np.cos(a * d2r),
                                np.cos(z * d2r)])
-    c = np.clip((v(z1, a1) * v(z2, a2)).sum(0), -1, 1)
-    return np.degrees(np.arccos(c))
+    # from the chord, not arccos of the dot product (whose rounding alone is 1e-6 deg near 0)
+    chord = np.sqrt(((v(z1, a1) - v(z2, a2)) ** 2).sum(0))
+    return np.degrees(2 * np.arcsin(np.clip(chord / 2, 0, 1)))
 
 
 @pytest.mark.parametrize("jd", [2451545.0, 2458148.2, 2460676.75])
