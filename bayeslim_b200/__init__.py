@@ -12,7 +12,7 @@ lies on the path; ``ops`` and ``_lib`` are the binding of the C-ABI CUDA library
 package without it raises.
 """
 from . import _lib                      # noqa: F401  (fails loudly if the library is missing)
-from . import utils, paramdict, dataset, healpix, telescope_model, sky_model, beam_model
+from . import utils, paramdict, dataset, healpix, sph_harm, telescope_model, sky_model, beam_model
 from . import ops, rime_model, imaging, calibration, parallel, optim
 from .utils import D2R, _float, _cfloat
 from .paramdict import ParamDict

@@ -64,6 +64,17 @@ _ANT_SIGS = {
     "tcfringe_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _I, _P, _P],
     "tcfringe_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _L, _I, _P, _P, _P],
 }
+_ANT_SIGS.update({
+    "cgemm_pack_a": [_P, _P, _L, _L, _I, _I, _P, _I, _P, _P],
+    "cgemm_pack_b": [_P, _P, _L, _L, _I, _I, _P, _I, _P, _P],
+    "cgemm": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _L, _P, _P],
+})
+lib.b200rime_cgemm_f64.argtypes = [_P, _P, _L, _L, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P, _L, _P]
+lib.b200rime_cgemm_f64.restype = _I
+lib.b200rime_cgemm_a_bytes.argtypes = [_I, _I]
+lib.b200rime_cgemm_a_bytes.restype = _L
+lib.b200rime_cgemm_b_bytes.argtypes = [_I, _I]
+lib.b200rime_cgemm_b_bytes.restype = _L
 for _name, _sig in _ANT_SIGS.items():        # float32 only
     _fn = getattr(lib, "b200rime_%s_f32" % _name)
     _fn.argtypes = _sig

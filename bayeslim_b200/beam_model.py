@@ -17,7 +17,7 @@ import math
 import numpy as np
 import torch
 
-from . import utils
+from . import utils, sph_harm
 from .utils import _float, _cfloat, D2R
 
 C_LIGHT = 2.99792458e8
@@ -291,6 +291,88 @@ class PixelResponse(utils.PixInterp):
     def set_beam_cache(self, params):
         self.beam_cache = self.forward(params)
         return self.beam_cache
+
+
+class YlmResponse(PixelResponse, sph_harm.AlmModel):
+    """Spherical-harmonic beam: params (Npol, Nvec, Nmodel, Ndeg, Ncoeff) hold a_lm coefficients
+    that are forward-modelled to the pixel map (Npol, Nvec, Nmodel, Nfreqs, Npix)
+    (beam_model.py:1019-1267).  mode 'interpolate' (the RIME mode): the map at the fixed
+    (theta, phi) is set once per forward as beam_cache -- by the CUDA tensor-core product
+    (ops.alm_forward) -- and interpolated at the source directions by the fused builder like any
+    PixelResponse; mode 'generate' evaluates the harmonics at every (zen, az) it is called with.
+    The polynomial compression along l (lm_poly_setup, experimental in the reference) is not
+    provided."""
+
+    def __init__(self, l, m, freqs, pixtype='healpix', beam0=None, comp_params=False,
+                 mode='interpolate', device=None, interp_mode='nearest', theta=None, phi=None,
+                 theta_grid=None, phi_grid=None, nside=None, powerbeam=True, realbeam=True,
+                 log=False, freq_mode='channel', freq_LM=None, Ylm_kwargs=None, Rchi=None,
+                 separable=False, interp_cache_depth=None, taper_kwargs=None, LM=None,
+                 norm_pix=None):
+        realbeam = True if powerbeam else realbeam
+        PixelResponse.__init__(self, freqs, pixtype, nside=nside, beam0=beam0,
+                               interp_mode=interp_mode, theta=theta, phi=phi, freq_mode=freq_mode,
+                               comp_params=comp_params, freq_LM=freq_LM, Rchi=Rchi,
+                               theta_grid=theta_grid, phi_grid=phi_grid, norm_pix=norm_pix,
+                               interp_cache_depth=interp_cache_depth, powerbeam=powerbeam,
+                               realbeam=realbeam, device=device, log=log,
+                               taper_kwargs=taper_kwargs)
+        sph_harm.AlmModel.__init__(self, l, m, default_kw=Ylm_kwargs, real_output=realbeam, LM=LM)
+        self.mode = mode
+        self.separable = separable
+        self.device = device
+        self.lm_poly_setup()
+        self._args = dict(mode=mode, interp_mode=interp_mode, freq_mode=freq_mode)
+
+    def lm_poly_setup(self, lm_poly_kwargs=None):
+        if lm_poly_kwargs not in (None, {}):
+            raise NotImplementedError("polynomial compression along l is not provided")
+        self._lm_poly = False
+
+    def forward(self, params, zen, az, *args):
+        """a_lm -> pixel beam at (zen, az) [deg] (beam_model.py:1166-1233)."""
+        if not utils.check_devices(params.device, self.device):
+            params = params.to(self.device)
+        if self.LM is not None:
+            params = self.LM(params)
+        if self.comp_params and not torch.is_complex(params):
+            params = utils.viewcomp(params)
+        p = params if self.freq_mode == 'channel' else self.freq_LM(params)
+        Ylm, alm_mult = self.get_Ylm(zen, az, h=utils.arr_hash(zen), separable=self.separable)
+        beam = self.forward_alm(p, Ylm=Ylm, alm_mult=alm_mult, ignoreLM=True)
+        if self.log:
+            beam = torch.exp(beam)
+        elif self.powerbeam:
+            beam = torch.abs(beam)
+        if self.beam0 is not None:
+            beam = beam + self.beam0
+        if self.taper_kwargs is not None:
+            beam = beam * beam_edge_taper(zen, device=beam.device, **self.taper_kwargs)
+        if self.norm_pix is not None:
+            beam = beam / beam[..., self.norm_pix:self.norm_pix + 1].detach().abs()
+        return beam
+
+    def __call__(self, params, zen, az, *args):
+        if self.mode == 'generate':
+            return self.forward(params, zen, az)
+        if self.beam_cache is None:
+            self.set_beam_cache(params)
+        return self.interp(self.beam_cache, zen, az)
+
+    def set_beam_cache(self, params):
+        if self.separable:
+            self.beam_cache = self.forward(params, self.theta_grid, self.phi_grid)
+        else:
+            self.beam_cache = self.forward(params, self.theta, self.phi)
+        return self.beam_cache
+
+    def push(self, device):
+        if self.beam_cache is not None:
+            self.beam_cache = utils.push(self.beam_cache, device)
+        LM, self.LM = self.LM, None           # pushed once, by AlmModel.push
+        PixelResponse.push(self, device)
+        self.LM = LM
+        sph_harm.AlmModel.push(self, device)
 
 
 class GaussResponse:

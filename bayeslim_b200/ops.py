@@ -1157,3 +1157,133 @@ def fringe_sum(A, blvecs, geom, freqs64, nfreq, conj=False, uniform=True):
     """A (nplane, nchunk, S, KC) real, blvecs (Nbl, 3) -> V (nplane, Nbl, Nt, Nf) complex:
     V[p, b, t, f] = sum_s A[p, f, s] exp(+-2 pi i (b . shat_s) nu_f / c)."""
     return _FringeSum.apply(A, blvecs, geom, freqs64, nfreq, conj, uniform)
+
+
+# ----------------------------------------------------------------------------- a_lm -> map
+def _pow2_scale(x):
+    """Power of two that brings max|x| into [2^14, 2^15) (device float32 [1], no host sync)."""
+    amax = x.detach().abs().amax().clamp_min(1e-30).to(torch.float32)
+    return torch.exp2(14.0 - torch.floor(torch.log2(amax))).reshape(1).contiguous()
+
+
+def _re_im(x):
+    """(re view, im view or None, element stride in floats) of a real / complex tensor."""
+    if x.is_complex():
+        v = torch.view_as_real(x)
+        return v[..., 0], v[..., 1], 2
+    return x, None, 1
+
+
+class AlmPlan:
+    """The constant operand of AlmModel.forward_alm (sph_harm.py:1289-1373): the Ylm matrix
+    (Ncoeff, Npix) of one set of angles, prepared once for both directions of the product.
+
+    float32 sessions: packed for the tensor-core GEMM (b200rime_cgemm_pack_b_f32) as
+    Y[pixel][mode] for the forward map and conj(Y)[mode][pixel] for the adjoint (12 bytes per
+    complex entry each: float16 hi + lo of (re; im; -re)).  float64 sessions keep the matrix as
+    it is (b200rime_cgemm_f64 reads strided operands)."""
+
+    def __init__(self, Ylm):
+        _need_cuda(Ylm)
+        assert Ylm.ndim == 2
+        self.ncoeff, self.npix = int(Ylm.shape[0]), int(Ylm.shape[1])
+        self.complex = Ylm.is_complex()
+        self.f64 = _real(Ylm.dtype) == torch.float64
+        self.device = Ylm.device
+        self.Ylm = Ylm.detach().contiguous()
+        if self.f64:
+            return
+        Y = self.Ylm
+        re, im, w = _re_im(Y)
+        self.scale = _pow2_scale(Y)
+        C, P = self.ncoeff, self.npix
+        self.Bq_fwd = torch.empty(_lib.lib.b200rime_cgemm_b_bytes(P, C), dtype=torch.uint8,
+                                  device=self.device)
+        _call("cgemm_pack_b", "f32", re, im, w, w * P, P, C, self.scale, 0, self.Bq_fwd)
+        self.Bq_adj = torch.empty(_lib.lib.b200rime_cgemm_b_bytes(C, P), dtype=torch.uint8,
+                                  device=self.device)
+        _call("cgemm_pack_b", "f32", re, im, w * P, w, C, P, self.scale, 1, self.Bq_adj)
+        self.Ylm = None              # the packed copies are all the GEMM needs
+
+
+def _ksplit(M, N, K, device):
+    """Split of the k axis that fills the SMs when there are few output tiles; every split keeps
+    at least 8 stages of 16."""
+    tiles = ((M + _lib.TC_ROWS - 1) // _lib.TC_ROWS) * ((N + _lib.TC_COLS_MAX - 1) // _lib.TC_COLS_MAX)
+    nkst = (K + 15) // 16
+    if tiles >= sm_count(device):
+        return 1
+    return int(max(1, min(nkst // 8, (2 * sm_count(device)) // tiles, 64)))
+
+
+def _cgemm_f32(X, Bq, bscale, M, N, K, x_conj, real_out):
+    """out (M, N) = X (M, K) . Y^T through the packed Y; X real or complex64, row-major."""
+    dev = X.device
+    re, im, w = _re_im(X.contiguous())
+    sa = _pow2_scale(X)
+    Aq = torch.empty(_lib.lib.b200rime_cgemm_a_bytes(M, K), dtype=torch.uint8, device=dev)
+    # the MMA pairing forms conj(X) Y: pack -Im X for the plain product
+    _call("cgemm_pack_a", "f32", re, im, w * K, w, M, K, sa, 0 if x_conj else 1, Aq)
+    out = torch.empty((M, N), dtype=torch.float32 if real_out else torch.complex64, device=dev)
+    ks = _ksplit(M, N, K, dev)
+    part = torch.empty((ks,) + tuple(out.shape), dtype=out.dtype, device=dev) if ks > 1 else None
+    _call("cgemm", "f32", Aq, Bq, M, N, K, ks, 1 if im is None else 0, 1 if real_out else 0,
+          sa, bscale, out, N, part)
+    return out
+
+
+def _cgemm_f64(X, Y, y_rows_are_k, conj_y, real_out):
+    """out (M, N) = X (M, K) . Y'^T, Y' = Y^T (y_rows_are_k: Y is (K, N)) or Y (N, K)."""
+    dev = X.device
+    X = X.contiguous()
+    xr, xi, wx = _re_im(X)
+    yr, yi, wy = _re_im(Y)
+    M, K = X.shape
+    if y_rows_are_k:
+        N = Y.shape[1]
+        syn, syk = wy, wy * N
+    else:
+        N = Y.shape[0]
+        syn, syk = wy * K, wy
+    out = torch.empty((M, N), dtype=torch.float64 if real_out else torch.complex128, device=dev)
+    _call("cgemm", "f64", xr, xi, wx * K, wx, yr, yi, syn, syk, M, N, K, 0, 1 if conj_y else 0,
+          1 if real_out else 0, out, N)
+    return out
+
+
+class _AlmForward(torch.autograd.Function):
+    """out = p Ylm (real part when real_out); backward dL/dp = G conj(Ylm)^T."""
+
+    @staticmethod
+    def forward(ctx, p, plan, real_out):
+        _need_cuda(p)
+        ctx.plan, ctx.p_complex, ctx.real_out = plan, p.is_complex(), real_out
+        M, K = p.shape
+        assert K == plan.ncoeff, "params (%d modes) do not match Ylm (%d)" % (K, plan.ncoeff)
+        if plan.f64:
+            return _cgemm_f64(p.to(torch.complex128 if p.is_complex() else torch.float64),
+                              plan.Ylm, True, False, real_out)
+        p = p.to(torch.complex64 if p.is_complex() else torch.float32)
+        return _cgemm_f32(p, plan.Bq_fwd, plan.scale, M, plan.npix, K, False, real_out)
+
+    @staticmethod
+    def backward(ctx, G):
+        plan = ctx.plan
+        G = G.contiguous()
+        if ctx.real_out and G.is_complex():
+            G = G.real.contiguous()
+        M = G.shape[0]
+        real_grad = not ctx.p_complex
+        if plan.f64:
+            g = _cgemm_f64(G, plan.Ylm, False, True, real_grad)
+        else:
+            g = _cgemm_f32(G, plan.Bq_adj, plan.scale, M, plan.ncoeff, plan.npix, False, real_grad)
+        return g, None, None
+
+
+def alm_forward(p, plan, real_out=False):
+    """(..., Ncoeff) coefficients -> (..., Npix) map through the Ylm of `plan`
+    (AlmModel.forward_alm's einsum "...i,ij->...j", sph_harm.py:1366)."""
+    lead = p.shape[:-1]
+    out = _AlmForward.apply(p.reshape(-1, p.shape[-1]), plan, bool(real_out))
+    return out.reshape(lead + (plan.npix,))

@@ -70,6 +70,16 @@ class _GeometryRecord:
         self.interp = {}      # (id(R), interp_mode, dtype) -> ops.InterpTable
 
 
+def _is_interp_response(R):
+    """Responses whose beam is a pixel map (beam_cache, set once per forward) interpolated at the
+    source directions: PixelResponse, and YlmResponse in 'interpolate' mode (its map comes from
+    the CUDA spherical-harmonic product)."""
+    name = R.__class__.__name__
+    if getattr(R, 'Rchi', None) is not None:
+        return False
+    return name == 'PixelResponse' or (name == 'YlmResponse' and getattr(R, 'mode', None) == 'interpolate')
+
+
 class RIME(utils.Module):
     """Radio interferometric measurement equation,
     V_pq(t, nu) = sum_s A_p(s, nu) I(s, nu) A_q(s, nu)^H exp(2 pi i b_pq . s nu / c)."""
@@ -355,7 +365,7 @@ class RIME(utils.Module):
         if rname == 'AiryResponse' and not getattr(R, 'brute_force', False) \
                 and getattr(R, 'taper_kwargs', None) is None and not offset:
             return 'airy'
-        if rname == 'PixelResponse' and getattr(R, 'Rchi', None) is None:
+        if _is_interp_response(R):
             return 'interp'
         return None
 
@@ -364,7 +374,7 @@ class RIME(utils.Module):
         mode: Jones and coherency planes are then built by the CUDA interpolation / gather
         kernels directly in the tiled layout and combined element-wise."""
         b, R = self.beam, self.beam.R
-        return R.__class__.__name__ == 'PixelResponse' and getattr(R, 'Rchi', None) is None
+        return _is_interp_response(R)
 
     def _build_airy(self, sky, rec, dev):
         b, R = self.beam, self.beam.R

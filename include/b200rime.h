@@ -338,6 +338,43 @@ int b200rime_tcfringe_bwd_f32(const void* Hq, const float* hscale, const float* 
                               const int* mrange, int nfreq, long long S, int conj, float* dAcm,
                               float* drpart, b200rime_stream_t stream);
 
+/* ---- spherical-harmonic forward model on the tensor cores -----
+ * AlmModel.forward_alm (sph_harm.py:1289-1373: einsum "...i,ij->...j" of the coefficients with the
+ * Ylm matrix) behind YlmResponse.forward / set_beam_cache (beam_model.py:1166-1250), and its
+ * adjoint to the coefficients (autograd of the same einsum in the reference):
+ *     out[m][n] = sum_k X[m][k] Y[n][k]      complex, float32-grade (three float16 split MMAs per
+ *                                            real product, FP32 accumulation in tensor memory)
+ * Operands are first PACKED (split into float16 hi + lo, multiplied by a power of two `scale`
+ * that brings max|.| into [2^14, 2^15), laid out in the UMMA canonical K-major order, one
+ * contiguous block per (block of 128 rows, stage of 16 k)):
+ *   cgemm_pack_a: X, element (row, k) at re[row * stride_row + k * stride_k] (+ im[...], NULL for a
+ *                 real operand; strides in floats, so a complex64 tensor passes re = ptr,
+ *                 im = ptr + 1 and doubled strides) -> Aq, cgemm_a_bytes(M, K) bytes
+ *   cgemm_pack_b: Y likewise (N rows) -> Bq, cgemm_b_bytes(N, K) bytes
+ *   negate_im = 1 packs the complex conjugate.
+ * cgemm: a_real = 1 promises Im X = 0 (half the MMAs); real_out = 1 stores Re out only.
+ *   out   float [M][ldo] (real_out) or complex64 [M][ldo]  (ldo in elements, >= N)
+ *   ksplit > 1 splits the k axis over grid.y (1 <= ksplit <= ceil(K / 16)); `part`
+ *   [ksplit][M][ldo] elements of workspace is then required and summed in index order. */
+long long b200rime_cgemm_a_bytes(int M, int K);
+long long b200rime_cgemm_b_bytes(int N, int K);
+int b200rime_cgemm_pack_a_f32(const float* re, const float* im, long long stride_row,
+                              long long stride_k, int M, int K, const float* scale, int negate_im,
+                              void* Aq, b200rime_stream_t stream);
+int b200rime_cgemm_pack_b_f32(const float* re, const float* im, long long stride_row,
+                              long long stride_k, int N, int K, const float* scale, int negate_im,
+                              void* Bq, b200rime_stream_t stream);
+int b200rime_cgemm_f32(const void* Aq, const void* Bq, int M, int N, int K, int ksplit, int a_real,
+                       int real_out, const float* scale_a, const float* scale_b, float* out,
+                       long long ldo, float* part, b200rime_stream_t stream);
+/* float64 sessions: the same product on the FP64 pipes straight from strided operands (no pack
+ * pass, no tensor cores): X element (m, k) at xr[m * stride_xm + k * stride_xk] (xi likewise or
+ * NULL), Y element (n, k) at yr[n * stride_yn + k * stride_yk]; conj_x / conj_y conjugate. */
+int b200rime_cgemm_f64(const double* xr, const double* xi, long long stride_xm, long long stride_xk,
+                       const double* yr, const double* yi, long long stride_yn, long long stride_yk,
+                       int M, int N, int K, int conj_x, int conj_y, int real_out, double* out,
+                       long long ldo, b200rime_stream_t stream);
+
 /* ---- equatorial -> topocentric angles on the device ----------
  * The per-source part of TelescopeModel.eq2top (telescope_model.py:469-502, astropy ICRS -> AltAz
  * on the host in the reference): p = unit(ra, dec); p += v3 (annual aberration, first order),

@@ -769,3 +769,82 @@ def eq2top_apparent(jd_utc, ra_deg, dec_deg, lon_deg, lat_deg):
     az = np.mod(np.arctan2(-np.cos(de) * np.sin(H),
                            np.sin(de) * np.cos(phi) - np.cos(de) * np.cos(H) * np.sin(phi)), 2 * np.pi) / d2r
     return zen, az
+
+
+# --------------------------------------------------------------------------
+# spherical-harmonic beam
+# --------------------------------------------------------------------------
+def sph_harm_matrix(l, m, theta, phi):
+    """Orthonormal Y_lm(theta, phi) (Ncoeff, Npix), complex128, theta / phi in RADIANS:
+    sqrt((2l+1)/(4 pi) (l-m)!/(l+m)!) P_l^m(cos theta) exp(i m phi) with the Condon-Shortley
+    phase -- what gen_sph2pix(method='sphere') returns (sph_harm.py:255-475).  Independent of
+    scipy: normalised associated Legendre functions by the standard three-term recurrence
+    in l started from P_m^m."""
+    l = np.asarray(l).astype(int)
+    m = np.asarray(m).astype(int)
+    theta = np.asarray(theta, dtype=np.float64)
+    phi = np.asarray(phi, dtype=np.float64)
+    x, s = np.cos(theta), np.sin(theta)
+    out = np.zeros((len(l), len(theta)), dtype=np.complex128)
+    for i, (li, mi) in enumerate(zip(l, m)):
+        ma = abs(mi)
+        # normalised P_ma^ma = (-1)^ma sqrt((2ma+1)!! / (4 pi (2ma)!!)) sin^ma
+        pmm = np.full_like(x, math.sqrt(1.0 / (4 * math.pi)))
+        for k in range(1, ma + 1):
+            pmm = -pmm * s * math.sqrt((2 * k + 1) / (2.0 * k))
+        if li == ma:
+            p = pmm
+        else:
+            pm1 = x * math.sqrt(2 * ma + 3) * pmm
+            p0, p1 = pmm, pm1
+            for ll in range(ma + 2, li + 1):
+                a = math.sqrt((4.0 * ll * ll - 1) / (ll * ll - ma * ma))
+                b = math.sqrt(((ll - 1.0) ** 2 - ma * ma) / (4.0 * (ll - 1) ** 2 - 1))
+                p0, p1 = p1, a * (x * p1 - b * p0)
+            p = p1
+        y = p * np.exp(1j * ma * phi)
+        if mi < 0:
+            y = (-1) ** ma * np.conj(y)
+        out[i] = y
+    return out
+
+
+def alm_forward(params, Ylm, alm_mult=None, real_output=False):
+    """AlmModel.forward_alm, non-separable branch (sph_harm.py:1344-1373): optional
+    multiplication of the coefficients, einsum "...i,ij->...j", real part if real_output."""
+    if torch.is_complex(Ylm) and not torch.is_complex(params):
+        params = torch.view_as_complex(params)
+    if alm_mult is not None:
+        params = params * alm_mult
+    out = torch.einsum("...i,ij->...j", params.to(torch.result_type(params, Ylm)), Ylm)
+    return out.real if real_output else out
+
+
+def alm_forward_separable(params, Theta, Phi, alm_mult=None, real_output=False):
+    """AlmModel.forward_alm, separable branch (sph_harm.py:1354-1362): (..., Ncoeff) ->
+    (..., Ntheta * Nphi)."""
+    if torch.is_complex(Phi) and not torch.is_complex(params):
+        params = torch.view_as_complex(params)
+    if alm_mult is not None:
+        params = params * alm_mult
+    x = torch.einsum("ct,...c->...tc", Theta.to(params.dtype), params)
+    x = torch.einsum("...tc,cp->...tp", x, Phi)
+    out = x.reshape(x.shape[:-2] + (Theta.shape[1] * Phi.shape[1],))
+    return out.real if real_output else out
+
+
+def ylm_response_forward(params, Ylm, alm_mult=None, powerbeam=True, realbeam=True, log=False,
+                         beam0=None, comp_params=False):
+    """YlmResponse.forward (beam_model.py:1166-1233) for freq_mode 'channel', no taper / norm:
+    a_lm (Npol, Nvec, Nmodel, Nf, Ncoeff[, 2]) -> beam map (Npol, Nvec, Nmodel, Nf, Npix)."""
+    if comp_params and not torch.is_complex(params):
+        params = torch.view_as_complex(params)
+    realbeam = True if powerbeam else realbeam
+    beam = alm_forward(params, Ylm, alm_mult, real_output=realbeam)
+    if log:
+        beam = torch.exp(beam)
+    elif powerbeam:
+        beam = torch.abs(beam)
+    if beam0 is not None:
+        beam = beam + beam0
+    return beam
