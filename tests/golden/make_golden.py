@@ -196,6 +196,83 @@ def gold_rime_airy_brute():
          vis=vd.data, G=G, grad_sky=sky.params.grad, grad_beam=beam.params.grad, fov=180.0)
 
 
+def gold_alm():
+    """AlmModel.forward_alm (sph_harm.py:1289-1373): full and separable transforms, complex and
+    real output, alm_mult; Ylm from the reference's gen_sph2pix(high_prec=False) (lmax 8, m >= 0);
+    gradients to the coefficients."""
+    rng = np.random.default_rng(31)
+    l, m = ba.sph_harm.gen_lm(8, real_field=True)
+    theta = np.degrees(np.arccos(rng.uniform(0, 1, 150)))
+    phi = rng.uniform(0, 360, 150)
+    out = dict(l=l, m=m, theta=theta, phi=phi)
+    g = torch.Generator().manual_seed(5)
+    params = torch.complex(torch.randn(2, 3, len(l), generator=g), torch.randn(2, 3, len(l), generator=g))
+    out["params"] = params
+    for tag, real in (("complex", False), ("real", True)):
+        A = ba.sph_harm.AlmModel(l, m, real_output=real, default_kw=dict(high_prec=False))
+        A.setup_Ylm(theta, phi, generate=True)
+        out["Ylm"], out["alm_mult"] = A.Ylm, A.alm_mult
+        p = params.clone().requires_grad_()
+        y = A(p)
+        G = cotangent(y.shape, 7) if not real else cotangent(y.shape, 7).real
+        (backward_with(y, G) if not real else torch.sum(G * y).backward())
+        out["out_" + tag], out["G_" + tag], out["grad_" + tag] = y, G, p.grad
+    # separable grid
+    tg, pg = np.linspace(2, 88, 7), np.linspace(0, 330, 12)
+    A = ba.sph_harm.AlmModel(l, m, real_output=True, default_kw=dict(high_prec=False))
+    A.setup_Ylm(tg, pg, generate=True, separable=True)
+    p = params.clone().requires_grad_()
+    y = A(p)
+    G = cotangent(y.shape, 9).real
+    torch.sum(G * y).backward()
+    out.update(theta_grid=tg, phi_grid=pg, Theta=A.Ylm[0], Phi=A.Ylm[1], out_sep=y, G_sep=G,
+               grad_sep=p.grad)
+    save("alm_forward", **out)
+
+
+def gold_rime_ylm():
+    """Spherical-harmonic beam through the RIME (beam_model.py:1019-1267): YlmResponse in
+    'interpolate' mode on a rect grid (a_lm -> beam_cache once per forward, bilinear
+    interpolation at the sources), complex coefficients in 2-real form (comp_params), a_lm as
+    perturbation about an Airy beam0, HEALPix nside-4 PixelSky; gradients to sky, a_lm, antvecs."""
+    rng = np.random.default_rng(41)
+    freqs = torch.linspace(100e6, 200e6, 7)
+    times = np.linspace(2458148.15, 2458148.25, 2)
+    ants, vecs, array = hera_array(2, freqs, set_param=True)
+    bls = [(0, 1), (0, 2), (0, 3), (1, 5), (2, 6), (0, 6), (3, 4), (1, 1)]
+    ra, dec, px_area, sparams = healpix_sky(4, freqs, rng)
+    angs = torch.as_tensor(np.stack([ra, dec]))
+    sky = ba.sky_model.PixelSky(sparams.clone(), angs, px_area,
+                                R=ba.sky_model.PixelSkyResponse(freqs), parameter=True)
+    theta, phi, b_theta, b_phi, airy = rect_airy_beam(freqs, 5.0, 10.0)
+    l, m = ba.sph_harm.gen_lm(6, real_field=True)
+    beam0 = torch.as_tensor(airy[None, None, None, :, :]).clone()
+    R = ba.beam_model.YlmResponse(l, m, freqs, pixtype='rect', mode='interpolate',
+                                  interp_mode='linear', theta=b_theta, phi=b_phi,
+                                  theta_grid=theta, phi_grid=phi, powerbeam=True,
+                                  comp_params=True, beam0=beam0, freq_mode='channel',
+                                  Ylm_kwargs=dict(high_prec=False))
+    R.setup_Ylm(b_theta, b_phi, generate=True)
+    Ylm, alm_mult = R.Ylm, R.alm_mult
+    g = torch.Generator().manual_seed(6)
+    bp = 0.02 * torch.randn(1, 1, 1, len(freqs), len(l), 2, generator=g) \
+        / (1.0 + torch.as_tensor(l, dtype=torch.float64))[:, None]
+    beam = ba.beam_model.PixelBeam(bp.clone(), freqs, R=R, pol='e', powerbeam=True, fov=180,
+                                   parameter=True)
+    tel = ba.telescope_model.TelescopeModel(LOC)
+    rime = ba.rime_model.RIME(sky, tel, beam, array, bls, times, freqs)
+    zen_az = inject_geometry(rime, sky.name, ra, dec, rime.sim_times)
+    vd = rime()
+    G = cotangent(vd.data.shape, 103)
+    backward_with(vd.data, G)
+    bc = ba.beam_model.YlmResponse.forward(R, bp, b_theta, b_phi).detach()
+    save("rime_ylm", antvecs=vecs, ants=ants, bls=bls, freqs=freqs, times=times, ra=ra, dec=dec,
+         zen_az=zen_az, sky_params=sparams, px_area=px_area, beam_params=bp, beam0=beam0, l=l, m=m,
+         theta_grid=theta, phi_grid=phi, Ylm_sample=Ylm[:, ::23], alm_mult=alm_mult,
+         beam_cache=bc, vis=vd.data, G=G, grad_sky=sky.params.grad, grad_beam=beam.params.grad,
+         grad_antvecs=array.antvecs.grad, fov=180.0)
+
+
 def healpix_sky(nside, freqs, rng, dec_max=59.27852):
     theta, phi = orc.healpix_pix2ang(nside)
     dec = np.pi / 2 - theta
@@ -630,6 +707,8 @@ if __name__ == "__main__":
     gold_rime_point_airy()
     gold_rime_airy_brute()
     gold_rime_pixel_interp()
+    gold_alm()
+    gold_rime_ylm()
     gold_rime_pointing()
     gold_rime_batched()
     gold_rime_2pol()

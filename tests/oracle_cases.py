@@ -96,6 +96,36 @@ def oracle_pixel_interp(g, dtype=torch.float64, interp_mode='linear', grad=True)
     return V, dict(sky=sky_params, beam=beam_params, antvecs=antvecs)
 
 
+def ylm_grid_matrix(g):
+    """Ylm at the rect beam grid of the rime_ylm fixture, from the oracle's own recurrence."""
+    ph, th = np.meshgrid(np.asarray(g["phi_grid"]), np.asarray(g["theta_grid"]))
+    Y = orc.sph_harm_matrix(g["l"], g["m"], np.radians(th.ravel()), np.radians(ph.ravel()))
+    return torch.as_tensor(Y)
+
+
+def oracle_ylm(g, dtype=torch.float64):
+    """rime_ylm fixture: a_lm --YlmResponse.forward--> beam_cache --bilinear interp--> RIME."""
+    antvecs = tt(g["antvecs"], dtype, grad=True)
+    sky_params = tt(g["sky_params"], dtype, grad=True)
+    beam_params = tt(g["beam_params"], dtype, grad=True)
+    freqs = tt(g["freqs"], dtype)
+    ants = [int(a) for a in g["ants"]]
+    bls = bl_list(g["bls"])
+    blvecs = orc.get_blvecs(antvecs, ants, bls)
+    sky = sky_params * float(g["px_area"])
+    zenaz = [(tt(za[0], dtype), tt(za[1], dtype)) for za in g["zen_az"]]
+    Ylm = ylm_grid_matrix(g)
+    beam_cache = orc.ylm_response_forward(beam_params, Ylm, tt(g["alm_mult"], dtype), powerbeam=True,
+                                          beam0=tt(g["beam0"], dtype), comp_params=True)
+
+    def beam_fn(z, a):
+        inds, wgts = orc.rect_interp_weights(g["theta_grid"], g["phi_grid"], z, a, 'linear')
+        return orc.interp_map(beam_cache, inds, wgts.to(dtype))
+
+    V = orc.rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=float(g["fov"]))
+    return V, dict(sky=sky_params, beam=beam_params, antvecs=antvecs), beam_cache
+
+
 def oracle_2pol(g, dtype=torch.float64):
     antvecs = tt(g["antvecs"], dtype)
     sky_params = tt(g["sky_params"], dtype, grad=True)

@@ -154,6 +154,37 @@ def test_rime_airy_brute_force_vs_reference():
     assert np.abs(g["grad_beam"]).max() > 0
 
 
+def test_alm_forward_vs_reference():
+    """AlmModel.forward_alm (sph_harm.py:1289-1373): full / separable, complex / real output."""
+    g = oc.load("alm_forward")
+    Y, am = torch.as_tensor(g["Ylm"]), torch.as_tensor(g["alm_mult"])
+    # the oracle's own Ylm recurrence reproduces the reference's gen_sph2pix (m >= 0)
+    Yo = orc.sph_harm_matrix(g["l"], g["m"], np.radians(g["theta"]), np.radians(g["phi"]))
+    assert np.abs(Yo - g["Ylm"]).max() < 1e-13
+    for tag, real in (("complex", False), ("real", True)):
+        p = oc.tt(g["params"], torch.complex128, grad=True)
+        y = orc.alm_forward(p, Y, am, real_output=real)
+        assert relmax(y, g["out_" + tag]) < 1e-13
+        G = torch.as_tensor(g["G_" + tag])
+        (oc.real_loss(y, G) if not real else torch.sum(G * y)).backward()
+        assert relmax(p.grad, g["grad_" + tag]) < 1e-12
+    p = oc.tt(g["params"], torch.complex128, grad=True)
+    y = orc.alm_forward_separable(p, torch.as_tensor(g["Theta"]), torch.as_tensor(g["Phi"]), am,
+                                  real_output=True)
+    assert relmax(y, g["out_sep"]) < 1e-13
+    torch.sum(torch.as_tensor(g["G_sep"]) * y).backward()
+    assert relmax(p.grad, g["grad_sep"]) < 1e-12
+
+
+def test_rime_ylm_vs_reference():
+    """YlmResponse in interpolate mode through the RIME (beam_model.py:1019-1267)."""
+    g = oc.load("rime_ylm")
+    assert np.abs(oc.ylm_grid_matrix(g).numpy()[:, ::23] - g["Ylm_sample"]).max() < 1e-13
+    V, leaves, beam_cache = oc.oracle_ylm(g)
+    assert relmax(beam_cache, g["beam_cache"]) < 1e-12
+    _check(V, leaves, g, dict(sky="grad_sky", beam="grad_beam", antvecs="grad_antvecs"))
+
+
 def test_rime_pixel_interp_vs_reference():
     g = oc.load("rime_pixel_interp")
     V, leaves = oc.oracle_pixel_interp(g)
