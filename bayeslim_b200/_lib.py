@@ -47,8 +47,8 @@ _SIGS = {
                             _P],
     "jones_sandwich": [_P, _P, _P, _L, _P, _P],
     "jones_sandwich_bwd": [_P, _P, _P, _P, _L, _I, _P, _P, _P, _P],
-    "build_airy": [_D, _D, _D, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P, _L, _P],
-    "build_airy_bwd": [_P, _D, _D, _D, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _L, _L, _P, _P, _P,
+    "build_airy": [_D, _D, _P, _D, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _L, _L, _P, _P, _L, _P],
+    "build_airy_bwd": [_P, _D, _D, _P, _D, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _L, _L, _P, _P, _P,
                        _L, _P],
 }
 for _name, _sig in _SIGS.items():

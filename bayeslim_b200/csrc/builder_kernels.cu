@@ -337,6 +337,7 @@ interp_transpose_kernel(const T* __restrict__ dBI, long long ldd, const int* __r
 // ---- Airy beam x sky -------------------------------------------------------------------
 template <typename T> struct AiryArgs {
     double Dew, Dns, kfac;   // kfac = pi * freq_ratio / c
+    const double* diam;      // device (Dew, Dns) overriding the two host values, or nullptr
     int square, asym;
     const T* sinzen;
     const T* sin2az;
@@ -364,6 +365,10 @@ build_airy_kernel(AiryArgs<T> a, const T* __restrict__ sky, long long lds,
     __shared__ T tile[KC][TS + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int chunk = blockIdx.y;
+    if (a.diam != nullptr) {
+        a.Dew = a.diam[0];
+        a.Dns = a.asym ? a.diam[1] : a.Dew;
+    }
     const int s = blockIdx.x * TS + tx;
     const int pix = (s < ns) ? cut[s] : -1;
     const bool live = pix >= 0;
@@ -397,6 +402,10 @@ build_airy_bwd_kernel(const T* __restrict__ dA, AiryArgs<T> a, int full_grad,
     __shared__ double red[2][BUILD_THREADS / 32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int chunk = blockIdx.y;
+    if (a.diam != nullptr) {
+        a.Dew = a.diam[0];
+        a.Dns = a.asym ? a.diam[1] : a.Dew;
+    }
     load_tile<T, KC>(tile, dA, S, soff + (long long)blockIdx.x * TS, chunk, TS);
     __syncthreads();
     const int s = blockIdx.x * TS + tx;
@@ -570,11 +579,12 @@ int launch_interp_transpose(const T* dBI, long long ldd, const int* rowptr, cons
     return check_launch("interp_transpose");
 }
 template <typename T>
-AiryArgs<T> make_airy(double Dew, double Dns, double freq_ratio, int square, const T* sinzen,
+AiryArgs<T> make_airy(double Dew, double Dns, const double* diam_dev, double freq_ratio, int square, const T* sinzen,
                       const T* sin2az, const double* freqs) {
     AiryArgs<T> a;
     a.Dew = Dew;
     a.Dns = Dns;
+    a.diam = diam_dev;
     a.kfac = 3.14159265358979323846 * freq_ratio / C_LIGHT;
     a.square = square;
     a.asym = sin2az != nullptr;
@@ -584,7 +594,7 @@ AiryArgs<T> make_airy(double Dew, double Dns, double freq_ratio, int square, con
     return a;
 }
 template <typename T>
-int launch_build_airy(double Dew, double Dns, double freq_ratio, int square, const T* sinzen,
+int launch_build_airy(double Dew, double Dns, const double* diam_dev, double freq_ratio, int square, const T* sinzen,
                       const T* sin2az, const double* freqs, const T* sky, long long lds,
                       const int* cut, int nfreq, int ns, int ns_pad, long long soff, long long S,
                       T* A, T* Bout, long long ldo, cudaStream_t st) {
@@ -593,12 +603,12 @@ int launch_build_airy(double Dew, double Dns, double freq_ratio, int square, con
         return set_error("build_airy: bad padding/offset");
     dim3 grid(ns_pad / TS, nchunks<T>(nfreq));
     build_airy_kernel<T><<<grid, BUILD_THREADS, 0, st>>>(
-        make_airy<T>(Dew, Dns, freq_ratio, square, sinzen, sin2az, freqs), sky, lds, cut, nfreq, ns,
+        make_airy<T>(Dew, Dns, diam_dev, freq_ratio, square, sinzen, sin2az, freqs), sky, lds, cut, nfreq, ns,
         soff, S, A, Bout, ldo);
     return check_launch("build_airy");
 }
 template <typename T>
-int launch_build_airy_bwd(const T* dA, double Dew, double Dns, double freq_ratio, int square,
+int launch_build_airy_bwd(const T* dA, double Dew, double Dns, const double* diam_dev, double freq_ratio, int square,
                           int full_grad, const T* sinzen, const T* sin2az, const double* freqs,
                           const T* sky, long long lds, const int* cut, int nfreq, int ns,
                           long long soff, long long S, T* dsky, double* dD, T* dIs, long long ldd,
@@ -607,7 +617,7 @@ int launch_build_airy_bwd(const T* dA, double Dew, double Dns, double freq_ratio
     if (soff % TS) return set_error("build_airy_bwd: bad offset");
     dim3 grid((ns + TS - 1) / TS, nchunks<T>(nfreq));
     build_airy_bwd_kernel<T><<<grid, BUILD_THREADS, 0, st>>>(
-        dA, make_airy<T>(Dew, Dns, freq_ratio, square, sinzen, sin2az, freqs), full_grad, sky, lds,
+        dA, make_airy<T>(Dew, Dns, diam_dev, freq_ratio, square, sinzen, sin2az, freqs), full_grad, sky, lds,
         cut, nfreq, ns, soff, S, dsky, dD, dIs, ldd);
     return check_launch("build_airy_bwd");
 }
@@ -867,20 +877,20 @@ int b200rime_interp_transpose_f64(const double* dBI, long long ldd, const int* r
     return launch_interp_transpose<double>(dBI, ldd, rowptr, col, val, npix, nfreq, dbmap, ldb,
                                            ST(stream));
 }
-int b200rime_build_airy_f32(double Dew, double Dns, double freq_ratio, int square,
+int b200rime_build_airy_f32(double Dew, double Dns, const double* diam_dev, double freq_ratio, int square,
                             const float* sinzen, const float* sin2az, const double* freqs,
                             const float* sky, long long lds, const int* cut, int nfreq, int ns,
                             int ns_pad, long long soff, long long S, float* A, float* Bout,
                             long long ldo, void* stream) {
-    return launch_build_airy<float>(Dew, Dns, freq_ratio, square, sinzen, sin2az, freqs, sky, lds,
+    return launch_build_airy<float>(Dew, Dns, diam_dev, freq_ratio, square, sinzen, sin2az, freqs, sky, lds,
                                     cut, nfreq, ns, ns_pad, soff, S, A, Bout, ldo, ST(stream));
 }
-int b200rime_build_airy_f64(double Dew, double Dns, double freq_ratio, int square,
+int b200rime_build_airy_f64(double Dew, double Dns, const double* diam_dev, double freq_ratio, int square,
                             const double* sinzen, const double* sin2az, const double* freqs,
                             const double* sky, long long lds, const int* cut, int nfreq, int ns,
                             int ns_pad, long long soff, long long S, double* A, double* Bout,
                             long long ldo, void* stream) {
-    return launch_build_airy<double>(Dew, Dns, freq_ratio, square, sinzen, sin2az, freqs, sky, lds,
+    return launch_build_airy<double>(Dew, Dns, diam_dev, freq_ratio, square, sinzen, sin2az, freqs, sky, lds,
                                      cut, nfreq, ns, ns_pad, soff, S, A, Bout, ldo, ST(stream));
 }
 int b200rime_airy_bwd_blocks(int nfreq, int ns) {
@@ -888,23 +898,23 @@ int b200rime_airy_bwd_blocks(int nfreq, int ns) {
     // divided into its own KC; use the finer (f64) chunking as the upper bound
     return ((ns + TS - 1) / TS) * ((nfreq + Cfg<double>::KC - 1) / Cfg<double>::KC);
 }
-int b200rime_build_airy_bwd_f32(const float* dA, double Dew, double Dns, double freq_ratio,
+int b200rime_build_airy_bwd_f32(const float* dA, double Dew, double Dns, const double* diam_dev, double freq_ratio,
                                 int square, int full_grad, const float* sinzen,
                                 const float* sin2az, const double* freqs, const float* sky,
                                 long long lds, const int* cut, int nfreq, int ns, long long soff,
                                 long long S, float* dsky, double* dD, float* dIs, long long ldd,
                                 void* stream) {
-    return launch_build_airy_bwd<float>(dA, Dew, Dns, freq_ratio, square, full_grad, sinzen, sin2az,
+    return launch_build_airy_bwd<float>(dA, Dew, Dns, diam_dev, freq_ratio, square, full_grad, sinzen, sin2az,
                                         freqs, sky, lds, cut, nfreq, ns, soff, S, dsky, dD, dIs, ldd,
                                         ST(stream));
 }
-int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, double freq_ratio,
+int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, const double* diam_dev, double freq_ratio,
                                 int square, int full_grad, const double* sinzen,
                                 const double* sin2az, const double* freqs, const double* sky,
                                 long long lds, const int* cut, int nfreq, int ns, long long soff,
                                 long long S, double* dsky, double* dD, double* dIs, long long ldd,
                                 void* stream) {
-    return launch_build_airy_bwd<double>(dA, Dew, Dns, freq_ratio, square, full_grad, sinzen,
+    return launch_build_airy_bwd<double>(dA, Dew, Dns, diam_dev, freq_ratio, square, full_grad, sinzen,
                                          sin2az, freqs, sky, lds, cut, nfreq, ns, soff, S, dsky, dD,
                                          dIs, ldd, ST(stream));
 }

@@ -384,25 +384,26 @@ class _BuildAiry(torch.autograd.Function):
         dtype, sfx = sky.dtype, _sfx(sky.dtype)
         sky = sky.contiguous()
         nfreq = sky.shape[0]
-        d = diam.detach().double().cpu().reshape(-1)
-        Dew = float(d[0])
-        asym = d.numel() > 1
-        Dns = float(d[1]) if asym else Dew
+        # the diameters stay on the device (no host synchronisation; CUDA-graph capturable)
+        asym = diam.numel() > 1
+        d = diam.detach().double().reshape(-1)
+        ddev = torch.stack([d[0], d[1] if asym else d[0]]).to(sky.device).contiguous()
+        Dew = Dns = 0.0
         kc = _lib.KC[sfx]
         S = max(geom.S, 1)
         A = torch.empty(1, nchunks(nfreq, dtype), S, kc, dtype=dtype, device=sky.device)
         if geom.S > 0:
-            _call("build_airy", sfx, Dew, Dns, float(freq_ratio), int(square), tab.sinzen,
+            _call("build_airy", sfx, Dew, Dns, ddev, float(freq_ratio), int(square), tab.sinzen,
                   tab.sin2az if asym else None, freqs64, sky, sky.shape[1], tab.cut, nfreq, geom.S,
                   geom.S, 0, geom.S, A[0], None, 0)
-        ctx.save_for_backward(sky, freqs64)
+        ctx.save_for_backward(sky, freqs64, ddev)
         ctx.meta = (geom, tab, Dew, Dns, asym, float(freq_ratio), int(square), int(full_grad),
                     diam.shape, diam.dtype, diam.device)
         return A
 
     @staticmethod
     def backward(ctx, dA):
-        sky, freqs64 = ctx.saved_tensors
+        sky, freqs64, diam_dev = ctx.saved_tensors
         geom, tab, Dew, Dns, asym, ratio, square, full_grad, dshape, ddtype, ddev = ctx.meta
         dA = dA.contiguous()
         sfx = _sfx(sky.dtype)
@@ -417,7 +418,7 @@ class _BuildAiry(torch.autograd.Function):
             if need_d:
                 nb = _lib.lib.b200rime_airy_bwd_blocks(nfreq, S)
                 dD = torch.zeros(nb, 2, dtype=torch.float64, device=sky.device)
-            _call("build_airy_bwd", sfx, dA[0], Dew, Dns, ratio, square, full_grad, tab.sinzen,
+            _call("build_airy_bwd", sfx, dA[0], Dew, Dns, diam_dev, ratio, square, full_grad, tab.sinzen,
                   tab.sin2az if asym else None, freqs64, sky, sky.shape[1], tab.cut, nfreq, S, 0, S,
                   None, dD, dIs, S)
             if need_sky:
@@ -555,11 +556,19 @@ class _ChisqEpilogue:
         return torch.stack([q.sum() for q in self.parts]).sum()
 
 
+_UBEG_CACHE = {}      # small index tables, uploaded once (no host-to-device copy per step)
+
+
 def _batch_ubeg(ubeg, ta, tb, u0, u1, device):
     """Unit offsets of the times ta..tb of a launch, relative to its first unit u0 (a split time
     has the single range [0, u1 - u0))."""
-    rel = np.clip(np.asarray(ubeg[ta:tb + 1], dtype=np.int64), u0, u1) - u0
-    return torch.as_tensor(rel.astype(np.int32), device=device)
+    key = (tuple(ubeg[ta:tb + 1]), u0, u1, str(device))
+    if key not in _UBEG_CACHE:
+        if len(_UBEG_CACHE) > 256:
+            _UBEG_CACHE.clear()
+        rel = np.clip(np.asarray(ubeg[ta:tb + 1], dtype=np.int64), u0, u1) - u0
+        _UBEG_CACHE[key] = torch.as_tensor(rel.astype(np.int32), device=device)
+    return _UBEG_CACHE[key]
 
 
 def _run_fwd_baseline(A, blv, geom, freqs64, nfreq, conj, uniform, epilogue=None):

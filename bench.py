@@ -414,6 +414,9 @@ def main():
                     help="times per step per GPU (c5: times of the fixed job)")
     ap.add_argument("--pass", dest="mode", default="fwdbwd", choices=["fwdbwd", "fwd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the step (forward + loss + backward) into a CUDA graph and "
+                         "time its replay (rime_model.GraphedStep; single-minibatch workloads)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -466,10 +469,21 @@ def main():
                                                                  world)
     fwd_only = args.mode == "fwd"
 
+    graphed = []
+
     def step(e2e_buffers=None):
         if e2e_buffers is not None:
             for p, h in zip(params, e2e_buffers["h_in"]):
                 p.data.copy_(h, non_blocking=True)
+        if graphed:
+            total = graphed[0]()                       # one graph launch: forward + loss + backward
+            if world > 1:
+                parallel.allreduce_gradients(params)
+            if e2e_buffers is not None:
+                for p, h in zip(params, e2e_buffers["h_out"]):
+                    h.copy_(p.grad, non_blocking=True)
+                e2e_buffers["loss"] = float(total)
+            return total
         for p in params:
             p.grad = None
         total = None
@@ -535,6 +549,18 @@ def main():
         ms_step = timed(args.steps)
         ksum = kt.summary()
     launches = ops.launch_count() - launches0
+    ms_eager = None
+    if args.graph:
+        # per-kernel durations come from the eager pass above; the reported step is the replay
+        assert len(batches) == 1 and not fwd_only, "--graph: one minibatch, forward + backward"
+        from bayeslim_b200.rime_model import GraphedStep
+        if rime.Nbatch > 1:
+            rime.batch_idx = batches[0]
+        graphed.append(GraphedStep(rime, lambda vd: (vd.data.real ** 2 + vd.data.imag ** 2).sum(),
+                                   params))
+        for _ in range(3):
+            step()
+        ms_eager, ms_step = ms_step, timed(args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end: parameters from pinned host memory in, loss (+ gradients) out, every step
@@ -699,6 +725,12 @@ def main():
         kernel_share_of_step={n: v / ms_step for n, v in kernel_ms.items()},
         kernel_launches_per_step={n: d["launches"] / args.steps for n, d in k.items()},
     )
+    if args.graph:
+        line["cuda_graph"] = dict(
+            note="the timed step is ONE replay of a CUDA graph holding the forward, the loss and "
+                 "the backward (rime_model.GraphedStep); gpu_launches counts the library kernels "
+                 "inside the replayed graphs; per-kernel durations are from the eager pass",
+            ms_per_step_eager=ms_eager, graph_replays_per_step=1)
     if world == 1 and not args.no_cpu_baseline:
         try:
             r = reference_arm(args.workload, 1, 1, mode=args.mode, size="small")

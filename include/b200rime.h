@@ -209,13 +209,16 @@ int b200rime_interp_transpose_f64(const double* dBI, long long ldd, const int* r
  *   D(s) = Dns + sin2az[s] * (Dew - Dns),  B = (2 J1(x)/x)^(square ? 2 : 1)
  *   A[f][soff+s] = B * sky[f*lds + cut[s]]
  * sinzen = sin(min(zen, 90 deg)), sin2az = sin(az)^2: real [ns], precomputed per time.
+ * diam_dev (optional): DEVICE float64 [2] = (Dew, Dns) that overrides the two host arguments, so
+ * that a caller holding the diameters on the device needs no host synchronisation (and the launch
+ * can be captured into a CUDA graph).
  * Bout (optional, may be NULL): row-major (Nf, ns) copy of B with row stride ldo. */
-int b200rime_build_airy_f32(double Dew, double Dns, double freq_ratio, int square,
+int b200rime_build_airy_f32(double Dew, double Dns, const double* diam_dev, double freq_ratio, int square,
                             const float* sinzen, const float* sin2az, const double* freqs,
                             const float* sky, long long lds, const int* cut, int nfreq, int ns,
                             int ns_pad, long long soff, long long S, float* A, float* Bout,
                             long long ldo, b200rime_stream_t stream);
-int b200rime_build_airy_f64(double Dew, double Dns, double freq_ratio, int square,
+int b200rime_build_airy_f64(double Dew, double Dns, const double* diam_dev, double freq_ratio, int square,
                             const double* sinzen, const double* sin2az, const double* freqs,
                             const double* sky, long long lds, const int* cut, int nfreq, int ns,
                             int ns_pad, long long soff, long long S, double* A, double* Bout,
@@ -227,13 +230,13 @@ int b200rime_build_airy_f64(double Dew, double Dns, double freq_ratio, int squar
  * d(2J1/x)/dx = 2 J0/x - 4 J1/x^2; full_grad == 0 reproduces the reference's autograd,
  * which treats J1(x) as a constant (torch.special.bessel_j1 has no derivative formula). */
 int b200rime_airy_bwd_blocks(int nfreq, int ns);
-int b200rime_build_airy_bwd_f32(const float* dA, double Dew, double Dns, double freq_ratio,
+int b200rime_build_airy_bwd_f32(const float* dA, double Dew, double Dns, const double* diam_dev, double freq_ratio,
                                 int square, int full_grad, const float* sinzen,
                                 const float* sin2az, const double* freqs, const float* sky,
                                 long long lds, const int* cut, int nfreq, int ns, long long soff,
                                 long long S, float* dsky, double* dD, float* dIs, long long ldd,
                                 b200rime_stream_t stream);
-int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, double freq_ratio,
+int b200rime_build_airy_bwd_f64(const double* dA, double Dew, double Dns, const double* diam_dev, double freq_ratio,
                                 int square, int full_grad, const double* sinzen,
                                 const double* sin2az, const double* freqs, const double* sky,
                                 long long lds, const int* cut, int nfreq, int ns, long long soff,

@@ -191,8 +191,10 @@ def _airy(Dew, Dns, ratio, square, sinzen, sin2az, freqs, nfreq, T):
     return xr, x, J1, h, dxdDew, dxdDns
 
 
-def build_airy(sfx, Dew, Dns, ratio, square, sinzen, sin2az, freqs, sky, lds, cut, nfreq, ns,
-               ns_pad, soff, S, A, Bout, ldo):
+def build_airy(sfx, Dew, Dns, diam_dev, ratio, square, sinzen, sin2az, freqs, sky, lds, cut, nfreq,
+               ns, ns_pad, soff, S, A, Bout, ldo):
+    if diam_dev is not None:
+        Dew, Dns = float(diam_dev[0]), float(diam_dev[1])
     live, c = _live(cut, ns)
     sz = sinzen[:ns]
     s2 = sin2az[:ns] if sin2az is not None else None
@@ -201,8 +203,10 @@ def build_airy(sfx, Dew, Dns, ratio, square, sinzen, sin2az, freqs, sky, lds, cu
     pack(sfx, (B * sky[:, c] * live[None]).contiguous(), ns, nfreq, ns, ns_pad, soff, S, A)
 
 
-def build_airy_bwd(sfx, dA, Dew, Dns, ratio, square, full_grad, sinzen, sin2az, freqs, sky, lds, cut,
-                   nfreq, ns, soff, S, dsky, dD, dIs, ldd):
+def build_airy_bwd(sfx, dA, Dew, Dns, diam_dev, ratio, square, full_grad, sinzen, sin2az, freqs, sky,
+                   lds, cut, nfreq, ns, soff, S, dsky, dD, dIs, ldd):
+    if diam_dev is not None:
+        Dew, Dns = float(diam_dev[0]), float(diam_dev[1])
     live, c = _live(cut, ns)
     g = _A_rows(dA, nfreq)[:, soff:soff + ns] * live[None]
     sz = sinzen[:ns]
