@@ -239,6 +239,45 @@ build_interp_t_kernel(const T* __restrict__ bmapT, long long ldt, const int* __r
     __syncthreads();
     T* dst = A + ((size_t)chunk * (size_t)S + (size_t)soff + (size_t)blockIdx.x * TS) * KC;
     const T* bcol = bmapT + (size_t)chunk * KC;
+    if constexpr (sizeof(T) == 4 && NNN == 4 && KC == 64) {
+        // float32, bilinear: a HALF-warp owns a source, a lane four channels -- every neighbour
+        // read is one 16-byte load (four requests of 256 bytes per source instead of eight of
+        // 128), all eight loads of a thread's two sources in flight before the first use
+        const int half = tx >> 4, c4 = (tx & 15) * 4;
+        float4 v[SPW / 2][4];
+        float w[SPW / 2][4];
+        bool lv[SPW / 2];
+#pragma unroll
+        for (int j = 0; j < SPW / 2; ++j) {
+            const int sl = ty * SPW + 2 * j + half;
+            const int s = blockIdx.x * TS + sl;
+            lv[j] = spix[sl] >= 0;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                v[j][n] = make_float4(0.f, 0.f, 0.f, 0.f);
+                w[j][n] = 0.f;
+                if (lv[j]) {
+                    const int ix = __ldg(inds + (size_t)s * 4 + n);
+                    w[j][n] = (float)__ldg(wgts + (size_t)s * 4 + n);
+                    v[j][n] = __ldg(reinterpret_cast<const float4*>(
+                        reinterpret_cast<const float*>(bcol) + (size_t)ix * ldt + c4));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SPW / 2; ++j) {
+            const int sl = ty * SPW + 2 * j + half;
+            float4 b;
+            b.x = v[j][0].x * w[j][0] + v[j][1].x * w[j][1] + v[j][2].x * w[j][2] + v[j][3].x * w[j][3];
+            b.y = v[j][0].y * w[j][0] + v[j][1].y * w[j][1] + v[j][2].y * w[j][2] + v[j][3].y * w[j][3];
+            b.z = v[j][0].z * w[j][0] + v[j][1].z * w[j][1] + v[j][2].z * w[j][2] + v[j][3].z * w[j][3];
+            b.w = v[j][0].w * w[j][0] + v[j][1].w * w[j][1] + v[j][2].w * w[j][2] + v[j][3].w * w[j][3];
+            b.x *= (float)tile[c4][sl], b.y *= (float)tile[c4 + 1][sl];
+            b.z *= (float)tile[c4 + 2][sl], b.w *= (float)tile[c4 + 3][sl];
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + (size_t)sl * KC + c4) = b;
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < SPW; ++j) {
         const int sl = ty * SPW + j;

@@ -79,9 +79,16 @@ class VisData(TensorData):
         self.ants = antpos.ants if antpos is not None else None
 
     def setup_data(self, bls, times, freqs, pol=None, data=None, flags=None, cov=None,
-                   cov_axis=None, icov=None, history='', file=None):
+                   cov_axis=None, icov=None, history='', file=None, _blnums=None):
+        """_blnums (extension): (device tensor, numpy array) of the baseline numbers prepared by
+        the caller (RIME caches them per baseline group, so that a forward neither copies them
+        to the device nor synchronises to read them back)."""
         self.data = data
-        self._set_bls(bls)
+        if _blnums is not None:
+            self._blnums, self.blnums = _blnums
+            self.Nbls = len(self.blnums)
+        else:
+            self._set_bls(bls)
         self.times = torch.as_tensor(times)
         self.Ntimes = len(times)
         self.freqs = torch.as_tensor(freqs)

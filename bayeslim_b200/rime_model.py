@@ -152,6 +152,7 @@ class RIME(utils.Module):
         self._bl_meta = {}
         self._ant_tilings = {}
         self._tc_tilings = {}
+        self._blnum_cache = {}
         if data_bls is None:
             self.data_bl_groups = self.sim_bl_groups
             self._sim2data = {k: None for k in sim_bl_groups}
@@ -247,8 +248,16 @@ class RIME(utils.Module):
     def _baseline_meta(self, dev, dtype):
         """(blvecs on the compute device, uniform-frequency flag) for the current group."""
         if getattr(self.array.antvecs, 'requires_grad', False):
-            # follow the live parameter (fresh graph every forward)
-            blvecs = self.array.get_blvecs(self.sim_bls)
+            # follow the live parameter (fresh graph every forward); the antenna-row tables of
+            # the group are uploaded once (no host-to-device copy per step: capturable)
+            av = self.array.antvecs
+            ikey = (self._bl_key, str(av.device), 'rows')
+            if ikey not in self._bl_meta:
+                i, j = self._antenna_rows()
+                self._bl_meta[ikey] = (torch.as_tensor(i, dtype=torch.long, device=av.device),
+                                       torch.as_tensor(j, dtype=torch.long, device=av.device))
+            i0, i1 = self._bl_meta[ikey]
+            blvecs = av.index_select(0, i1) - av.index_select(0, i0)
         else:
             blvecs = self.sim_blvecs
         blvecs = blvecs.to(dev)
@@ -540,8 +549,12 @@ class RIME(utils.Module):
                        eq2top_fn=self.telescope.eq2top_fn)
         telescope = self.telescope.__class__(self.telescope.location, **tkw)
         vd.setup_meta(telescope, self.array.to_antpos())
+        bkey = (self._bl_key, str(vis.device))
+        if bkey not in self._blnum_cache:
+            nums = np.asarray(utils.ants2blnum(list(self.data_bls)))
+            self._blnum_cache[bkey] = (torch.as_tensor(nums, device=vis.device), nums)
         vd.setup_data(self.data_bls, self.sim_times, self.freqs, pol=pol, data=vis, flags=None,
-                      cov=None, history=self._history())
+                      cov=None, history=self._history(), _blnums=self._blnum_cache[bkey])
         return vd
 
     def _sum_model_pairs(self, tiled, per_time, modelpairs, mp_idx, sky, rec, dev, blvecs, f64,
