@@ -148,7 +148,11 @@ class RIME(utils.Module):
         self.sim_bl_groups = sim_bl_groups
         self.all_sim_bls = [bl for g in sim_bl_groups.values() for bl in g]
         self.Nbl_groups = len(sim_bl_groups)
-        self.sim_blvec_groups = {k: self.array.get_blvecs(v) for k, v in sim_bl_groups.items()}
+        # detached: a parameter antvecs is followed through _baseline_meta at every forward; a
+        # cached tensor with a graph would pin antvecs' gradient accumulator to the stream of
+        # this call (which breaks CUDA-graph capture of the backward)
+        self.sim_blvec_groups = {k: self.array.get_blvecs(v).detach()
+                                 for k, v in sim_bl_groups.items()}
         self._bl_meta = {}
         self._ant_tilings = {}
         self._tc_tilings = {}
