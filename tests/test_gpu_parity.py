@@ -863,3 +863,36 @@ def test_graphed_step_replays_the_eager_step(name):
     for a, b in zip(grads2, g3):
         assert torch.equal(a, b)
     assert float((l2 - l0).abs()) > 0
+
+
+@pytest.mark.skipif(DOUBLE or torch.cuda.device_count() < 2, reason="needs two CUDA devices")
+def test_model_on_a_non_current_device():
+    """kernels launch on the device that owns the tensors and on torch's current
+    stream of THAT device; per-device function attributes (dynamic shared memory) are set on every
+    device a process drives.  The process's current device stays cuda:0 throughout."""
+    assert torch.cuda.current_device() == 0
+    dev = 'cuda:1'
+    for name in ("rime_point_airy", "rime_pixel_interp"):
+        g = oc.load(name)
+        build, gkeys = mc.CASES[name]
+        rime, leaves = build(g, dev, torch.float32)
+        V = rime().data
+        assert V.device == torch.device(dev)
+        assert relmax(V, g["vis"]) < TOL[torch.float32]
+        G = torch.as_tensor(g["G"]).to(device=dev, dtype=V.dtype)
+        torch.sum(G.real * V.real + G.imag * V.imag).backward()
+        for k, gk in gkeys.items():
+            assert relmax(leaves[k].grad, g[gk]) < 5 * TOL[torch.float32], (k, gk)
+    # kernels that need more than 48 KB of dynamic shared memory, first use on cuda:1
+    rime = workloads.pixel_interp(16, 96, 1, dev, torch.float32, antpos_param=True)
+    assert rime._tc_tiling(torch.device(dev)) is not None
+    V = rime().data
+    (V.real ** 2 + V.imag ** 2).sum().backward()
+    ref = workloads.pixel_interp(16, 96, 1, 'cuda:0', torch.float32, antpos_param=True)
+    V0 = ref().data
+    assert relmax(V, V0.to(dev)) < 1e-6
+    Y = torch.randn(40, 300, dtype=torch.complex64, device=dev)
+    p = torch.randn(6, 40, dtype=torch.complex64, device=dev)
+    out = ops.alm_forward(p, ops.AlmPlan(Y))
+    assert relmax(out, p.cpu().to(torch.complex128) @ Y.cpu().to(torch.complex128)) < 1e-5
+    assert torch.cuda.current_device() == 0
