@@ -563,6 +563,70 @@ tc_fringe_bwd_kernel(const unsigned char* __restrict__ Hq, const float* __restri
     }
 }
 
+// -------------------------------------------------------------------------------------
+// Cotangent operand of the backward kernel, straight from the autograd cotangent:
+//   H[a][m] = G_b for b = (m, a), conj(G_b) for b = (a, m), 2 Re G_b for an auto-correlation
+//   (lower_only: the doubled lower triangle a > m; the upper one is zero)
+// scaled by hscale, split into float16 hi / lo and written as the stacked three-half buffers
+// (-Hi ; Hr ; Hi) in UMMA canonical order (layout in the header of tc_fringe_bwd_kernel).
+// Thread <-> (channel, group of 8 partner antennas, antenna row, stage, item, time), channel
+// fastest: the eight gathers of a warp read 256 contiguous bytes of G each, the pair-table
+// lookups are warp-uniform.  Replaces a chain of index_put / scale / split / stack / permute
+// passes over a (Nt, Nfp, Na, Na) complex matrix (1.1 GB per time at HERA-350 x 1024 channels).
+//   G        float2 [nbl][..][nf], element (b, t, k) at G[b * ldb + t * nf + k]
+//   pair_bl  int32 [ldp][ldp]  (baseline << 1 | swapped) of the pair (x <= y), -1: none
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tc_pack_cotangent_kernel(const float2* __restrict__ G, long long ldb, const int* __restrict__ pair_bl,
+                         int ldp, int nt, int nf, int nfp, int na, int nitem, int nstage,
+                         int lower_only, const float* __restrict__ hscale,
+                         unsigned char* __restrict__ Hq) {
+    const long long total = (long long)nt * nitem * nstage * TC_M * 2 * nfp;
+    const float sc = __ldg(hscale);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long r = idx;
+        const int k = (int)(r % nfp); r /= nfp;
+        const int kg = (int)(r % 2); r /= 2;
+        const int row = (int)(r % TC_M); r /= TC_M;
+        const int stage = (int)(r % nstage); r /= nstage;
+        const int item = (int)(r % nitem);
+        const int t = (int)(r / nitem);
+        const int a = item * TC_M + row;
+        float hr[8], hi[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int m = stage * TC_KS + kg * 8 + e;
+            hr[e] = hi[e] = 0.f;
+            if (k >= nf || a >= na || m >= na || (lower_only && m > a)) continue;
+            const int x = min(a, m), y = max(a, m);
+            const int ent = __ldg(pair_bl + (size_t)x * ldp + y);
+            if (ent < 0) continue;
+            const float2 g = __ldg(G + (size_t)(ent >> 1) * ldb + (size_t)t * nf + k);
+            if (a == m) {
+                hr[e] = 2.f * g.x * sc;
+            } else {
+                // first antenna of the listed baseline: x, or y when the listing was swapped
+                const int first = (ent & 1) ? y : x;
+                const float w = lower_only ? 2.f * sc : sc;
+                hr[e] = g.x * w;
+                hi[e] = (first == m) ? g.y * w : -g.y * w;
+            }
+        }
+        uint4 rh, rl, ih, il;
+        split8(hr, rh, rl);
+        split8(hi, ih, il);
+        unsigned char* d = Hq + ((((size_t)t * nfp + k) * nitem + item) * nstage + stage) * (2 * TcSmem::BBUF)
+                           + (row >> 3) * 256 + kg * 128 + (row & 7) * 16;
+        *reinterpret_cast<uint4*>(d) = neg_half8(ih);
+        *reinterpret_cast<uint4*>(d + TcSmem::ARR) = rh;
+        *reinterpret_cast<uint4*>(d + 2 * TcSmem::ARR) = ih;
+        *reinterpret_cast<uint4*>(d + TcSmem::BBUF) = neg_half8(il);
+        *reinterpret_cast<uint4*>(d + TcSmem::BBUF + TcSmem::ARR) = rl;
+        *reinterpret_cast<uint4*>(d + TcSmem::BBUF + 2 * TcSmem::ARR) = il;
+    }
+}
+
 int launch_tc_fwd(const float* Acm, const float* ascale, const double* shat, const double* antv,
                   const double* freqs, const int* units, int nunits, const int* items, int nitems,
                   const int* pair_bl, int ldp, int na, int nbl, int nfreq, long long S, int conj,
@@ -636,6 +700,24 @@ int b200rime_tcfringe_fwd_f32(const float* Acm, const float* ascale, const doubl
     return b200rime::launch_tc_fwd(Acm, ascale, shat, antv, freqs, units, nunits, items, nitems,
                                    pair_bl, ldp, na, nbl, nfreq, S, conj, Vpart,
                                    (cudaStream_t)stream);
+}
+int b200rime_tc_pack_cotangent_f32(const float* G, long long ldb, const int* pair_bl, int ldp,
+                                   int nt, int nf, int na, int nm_pad, int lower_only,
+                                   const float* hscale, void* Hq, void* stream) {
+    using namespace b200rime;
+    if (nt <= 0 || nf <= 0 || na <= 0) return 0;
+    if (nm_pad % TC_KS || nm_pad < na) return set_error("tc_pack_cotangent: nm_pad must be na rounded up to 16");
+    if (G == nullptr || pair_bl == nullptr || hscale == nullptr || Hq == nullptr)
+        return set_error("tc_pack_cotangent: null operand");
+    const int nfp = ((nf + TC_KC - 1) / TC_KC) * TC_KC;
+    const int nitem = (na + TC_M - 1) / TC_M, nstage = nm_pad / TC_KS;
+    const long long total = (long long)nt * nitem * nstage * TC_M * 2 * nfp;
+    const long long want = (total + 255) / 256;
+    const int grid = (int)(want < 148LL * 64 ? want : 148LL * 64);
+    tc_pack_cotangent_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(G), ldb, pair_bl, ldp, nt, nf, nfp, na, nitem, nstage,
+        lower_only, hscale, static_cast<unsigned char*>(Hq));
+    return check_launch("tc_pack_cotangent");
 }
 int b200rime_tc_rows(void) { return b200rime::TC_M; }
 int b200rime_tc_cols_max(void) { return b200rime::TC_NMAX; }

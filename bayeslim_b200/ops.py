@@ -865,36 +865,17 @@ class TcTiling:
         operands M = (-Hi ; Hr) / P = (Hr ; Hi):
         [nt][Nfp][item][stage of 16 m][hi | lo][3 halves][16 row groups][2 k groups][8 rows][8 k]."""
         nbl, nt, nf = G.shape
-        Gq = G.permute(1, 2, 0)                                    # (nt, nf, nbl)
-        H = torch.zeros(nt, nfp, self.apad, self.nm_pad, dtype=torch.complex64, device=G.device)
-        Hv = H[:, :nf]
-        if lower_only:
-            if len(self.jgt):
-                Hv[:, :, self.j[self.jgt], self.i[self.jgt]] = 2 * Gq.index_select(2, self.jgt)
-            if len(self.igt):
-                Hv[:, :, self.i[self.igt], self.j[self.igt]] = 2 * Gq.index_select(2, self.igt).conj()
-        else:
-            Hv[:, :, self.j, self.i] = Gq
-            if len(self.cross):
-                Hv[:, :, self.i[self.cross], self.j[self.cross]] = Gq.index_select(2, self.cross).conj()
-        if len(self.auto):
-            Hv[:, :, self.i[self.auto], self.i[self.auto]] = \
-                (2 * Gq.index_select(2, self.auto).real).to(G.dtype)
-        Hr = torch.view_as_real(H)                                  # (nt, nfp, apad, nm, 2)
-        amax = Hr.abs().amax().clamp_min(1e-30)
+        if G.stride(2) != 1 or G.stride(1) != nf:
+            G = G.contiguous()
+        # max |H| <= 2 max(|Re G|, |Im G|) when entries are doubled (autos, lower triangle)
+        dbl = 2.0 if (lower_only or len(self.auto)) else 1.0
+        amax = (torch.view_as_real(G).abs().amax() * dbl).clamp_min(1e-30)
         hscale = torch.exp2(14.0 - torch.floor(torch.log2(amax))).to(torch.float32).reshape(1)
-        Hr = Hr * hscale
-        hi = Hr.to(torch.float16)
-        lo = (Hr - hi.to(torch.float32)).to(torch.float16)
-        del Hr, H
-        # stacked B operands of tcfringe_bwd: the three-half buffer (-Hi ; Hr ; Hi), hi and lo parts
-        # (M = (-Hi ; Hr) = rows 0..255, P = (Hr ; Hi) = rows 128..383)
-        Q = torch.stack([-hi[..., 1], hi[..., 0], hi[..., 1],
-                         -lo[..., 1], lo[..., 0], lo[..., 1]], dim=2)              # (nt,nfp,6,a,m)
-        del hi, lo
-        Q = Q.reshape(nt, nfp, 6, self.nitem_bwd, 16, 8, self.nm_pad // 16, 2, 8)
-        Q = Q.permute(0, 1, 3, 6, 2, 4, 7, 5, 8).contiguous()
-        return Q, hscale
+        Hq = torch.empty(nt, nfp, self.nitem_bwd, self.nm_pad // 16, 6, 16, 2, 8, 8,
+                         dtype=torch.float16, device=G.device)
+        _call("tc_pack_cotangent", "f32", G, G.stride(0), self.pair_bl, self.ldp, nt, nf, self.na,
+              self.nm_pad, int(lower_only), hscale, Hq)
+        return Hq, hscale
 
 
 def tc_scale(A):

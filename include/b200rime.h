@@ -341,6 +341,16 @@ int b200rime_tcfringe_bwd_f32(const void* Hq, const float* hscale, const float* 
                               const int* mrange, int nfreq, long long S, int conj, float* dAcm,
                               float* drpart, b200rime_stream_t stream);
 
+/* Cotangent operand of tcfringe_bwd straight from the autograd cotangent G (complex64, element
+ * (baseline b, time t, channel k) at G[2 * (b * ldb + t * nf + k)]; ldb in complex elements):
+ * builds H through the antenna-pair table of tcfringe_fwd (lower_only: the doubled lower
+ * triangle), multiplies by hscale (device float [1], a power of two with max|H| hscale < 2^15),
+ * splits into float16 hi + lo and writes Hq in the layout above.  One pass; replaces the
+ * index_put / scale / split / stack / permute chain over a (Nt, Nfp, Na, Na) complex matrix. */
+int b200rime_tc_pack_cotangent_f32(const float* G, long long ldb, const int* pair_bl, int ldp,
+                                   int nt, int nf, int na, int nm_pad, int lower_only,
+                                   const float* hscale, void* Hq, b200rime_stream_t stream);
+
 /* ---- spherical-harmonic forward model on the tensor cores -----
  * AlmModel.forward_alm (sph_harm.py:1289-1373: einsum "...i,ij->...j" of the coefficients with the
  * Ylm matrix) behind YlmResponse.forward / set_beam_cache (beam_model.py:1166-1250), and its

@@ -327,6 +327,42 @@ def tcfringe_bwd(sfx, Hq, hscale, Acm, shat, antv, freqs, units, nunits, nitem, 
             drpart[u, :nfreq, 0, :, :3] = (sgn * 2 * math.pi / C * g).to(drpart.dtype)
 
 
+def tc_pack_cotangent(sfx, G, ldb, pair_bl, ldp, nt, nf, na, nm_pad, lower_only, hscale, Hq):
+    """Contract of b200rime_tc_pack_cotangent_f32, restated with dense torch operations (the
+    construction the package used before the fused kernel)."""
+    M = _lib.TC_ROWS
+    nitem = -(-na // M)
+    nfp = Hq.shape[1]
+    assert G.is_complex() and G.stride(2) == 1 and G.stride(1) == nf and G.stride(0) == ldb
+    Gq = G.permute(1, 2, 0).to(torch.complex64)                  # (nt, nf, nbl)
+    H = torch.zeros(nt, nfp, nitem * M, nm_pad, dtype=torch.complex64)
+    P = pair_bl.cpu().numpy()
+    xs, ys = np.nonzero(P[:na, :na] >= 0)
+    for x, y in zip(xs, ys):
+        ent = int(P[x, y])
+        g = Gq[:, :, ent >> 1]
+        if x == y:
+            H[:, :nf, x, x] = (2 * g.real).to(torch.complex64)
+            continue
+        first, second = (y, x) if ent & 1 else (x, y)
+        # H[a][m] = G for (first, second) = (m, a), conj(G) for (a, m)
+        if lower_only:
+            if second > first:
+                H[:, :nf, second, first] = 2 * g
+            else:
+                H[:, :nf, first, second] = 2 * g.conj()
+        else:
+            H[:, :nf, second, first] = g
+            H[:, :nf, first, second] = g.conj()
+    Hr = torch.view_as_real(H) * float(hscale[0])
+    assert float(Hr.abs().max()) < 2.0 ** 15
+    hi = Hr.to(torch.float16)
+    lo = (Hr - hi.to(torch.float32)).to(torch.float16)
+    Q = torch.stack([-hi[..., 1], hi[..., 0], hi[..., 1], -lo[..., 1], lo[..., 0], lo[..., 1]], dim=2)
+    Q = Q.reshape(nt, nfp, 6, nitem, 16, 8, nm_pad // 16, 2, 8).permute(0, 1, 3, 6, 2, 4, 7, 5, 8)
+    Hq.copy_(Q)
+
+
 def antfringe_bwd(sfx, Hp, A, shat, antv, freqs, units, nunits, na, na_pad, nm_pad, nfreq, S, conj,
                   dApart, drpart):
     assert na_pad - _lib.ANT_TILE < na <= na_pad
@@ -446,7 +482,7 @@ _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
               tcfringe_fwd=tcfringe_fwd, tcfringe_bwd=tcfringe_bwd,
               apply_cal=apply_cal, apply_cal_bwd_gains=apply_cal_bwd_gains,
               jones_sandwich=jones_sandwich, jones_sandwich_bwd=jones_sandwich_bwd)
-_TABLE_LATE = ('cgemm_pack_a', 'cgemm_pack_b', 'cgemm')
+_TABLE_LATE = ('cgemm_pack_a', 'cgemm_pack_b', 'cgemm', 'tc_pack_cotangent')
 
 
 # ----------------------------------------------------------------------------- a_lm -> map

@@ -847,11 +847,17 @@ def test_graphed_step_replays_the_eager_step(name):
 
     l0, g0 = eager()
     step = ba.rime_model.GraphedStep(rime, loss_fn, params)
+    # antenna-position gradients pass through torch's index_select backward (atomic adds: not
+    # bitwise reproducible run to run, graph or not); everything else is
+    def same(a, b, key):
+        return relmax(a, b) < 1e-6 if key == "antvecs" else torch.equal(a, b)
+
+    keys = list(gkeys)
     l1 = step()
     torch.cuda.synchronize()
     assert torch.equal(l1, l0)
-    for p, ref in zip(params, g0):
-        assert torch.equal(p.grad, ref)
+    for p, ref, key in zip(params, g0, keys):
+        assert same(p.grad, ref, key), key
     for k, gk in gkeys.items():
         assert relmax(leaves[k].grad, g[gk]) < 5e-5
     with torch.no_grad():
@@ -860,8 +866,8 @@ def test_graphed_step_replays_the_eager_step(name):
     grads2 = [p.grad.clone() for p in params]
     l3, g3 = eager()
     assert torch.equal(l2, l3)
-    for a, b in zip(grads2, g3):
-        assert torch.equal(a, b)
+    for a, b, key in zip(grads2, g3, keys):
+        assert same(a, b, key), key
     assert float((l2 - l0).abs()) > 0
 
 
