@@ -902,3 +902,29 @@ def test_model_on_a_non_current_device():
     out = ops.alm_forward(p, ops.AlmPlan(Y))
     assert relmax(out, p.cpu().to(torch.complex128) @ Y.cpu().to(torch.complex128)) < 1e-5
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.skipif(DOUBLE, reason="compares the CUDA kernel with the dense restatement")
+@pytest.mark.parametrize("lower_only", [False, True])
+def test_cotangent_pack_kernel_equals_dense_construction(lower_only):
+    """b200rime_tc_pack_cotangent_f32 against the dense torch construction it replaced (kept as
+    the CPU test double): bit-exact float16 operands, for a baseline list with both orientations,
+    auto-correlations, missing pairs, ragged antenna / channel counts and a time sub-range."""
+    from tests import cpu_double
+    rng = np.random.default_rng(5)
+    na, nt_all, nf = 150, 3, 70
+    pairs = [(i, j) for i in range(na) for j in range(i, na) if rng.random() < 0.6]
+    pairs = [(j, i) if rng.random() < 0.3 else (i, j) for i, j in pairs]
+    i_idx, j_idx = [p[0] for p in pairs], [p[1] for p in pairs]
+    tc = ops.TcTiling(i_idx, j_idx, na, 'cuda')
+    assert tc.usable and len(tc.auto) > 0 and len(tc.igt) > 0
+    G = torch.complex(torch.randn(len(pairs), nt_all, nf), torch.randn(len(pairs), nt_all, nf)).cuda()
+    nfp = ops.nchunks(nf, torch.float32) * _lib.KC["f32"]
+    Gs = G[:, 1:3]                                           # a time sub-range: strided view
+    Hq, hscale = tc.cotangent_operand(Gs, nfp, lower_only=lower_only)
+    ref = torch.empty(Hq.shape, dtype=torch.float16)
+    Gc = Gs.cpu().contiguous()
+    cpu_double.tc_pack_cotangent("f32", Gc, Gc.stride(0), tc.pair_bl.cpu(), tc.ldp, 2, nf, na, tc.nm_pad,
+                                 int(lower_only), hscale.cpu(), ref)
+    assert torch.equal(Hq.cpu().view(torch.int16), ref.view(torch.int16))
+    assert float(Hq.abs().max()) >= 2.0 ** 13          # the scale uses the float16 range
