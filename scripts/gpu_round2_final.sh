@@ -16,6 +16,8 @@ run c3
 run c3_fwd --pass fwd --no-cpu-baseline
 run ref_c3 --impl reference
 run c1 --workload c1 --steps 5 --warmup 3 --no-cpu-baseline
+run c1_graph --workload c1 --steps 20 --warmup 3 --no-cpu-baseline --graph
+run refgpu_c3 --impl reference-gpu
 run c2 --workload c2 --steps 3 --warmup 3 --no-cpu-baseline
 run c4 --workload c4 --steps 2 --warmup 3 --no-cpu-baseline
 run c5 --workload c5 --steps 2 --warmup 3 --no-cpu-baseline

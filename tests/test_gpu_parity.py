@@ -928,3 +928,74 @@ def test_cotangent_pack_kernel_equals_dense_construction(lower_only):
                                  int(lower_only), hscale.cpu(), ref)
     assert torch.equal(Hq.cpu().view(torch.int16), ref.view(torch.int16))
     assert float(Hq.abs().max()) >= 2.0 ** 13          # the scale uses the float16 range
+
+
+def test_c5_minibatch_grid_on_tensor_core_kernels_vs_oracle():
+    """BASELINE config 5 family (reduced): HERA-350, all cross baselines in two block-aligned
+    baseline groups x single-time groups = the reference's minibatch grid (rime_model.py:253-289).
+    Every minibatch stays on the tensor-core kernels; visibilities of each minibatch match the
+    fp64 oracle on a baseline / channel subset; gradients accumulated over the grid equal the
+    gradients of the same model run as ONE batch (minibatch invariance, reference
+    tests/test_rime.py:49-51) and match oracle autograd for a sparse cotangent."""
+    if DOUBLE:
+        pytest.skip("needs the GPU")
+    nf, nt = 96, 2
+    rime = workloads.pixel_interp(16, nf, nt, DEV, torch.float32, bl_groups=True, time_groups=True)
+    one = workloads.pixel_interp(16, nf, nt, DEV, torch.float32)
+    dev = torch.device(DEV, torch.cuda.current_device())
+    assert rime.Nbatch == 2 * nt and one.Nbatch == 1
+    nbl_all = len(one.sim_bls)
+    row = {bl: k for k, bl in enumerate(one.sim_bls)}
+    gen = torch.Generator().manual_seed(3)
+    V1 = one().data
+    G = torch.zeros(V1.shape, dtype=torch.complex64, device=V1.device)
+    gb = sorted(np.random.default_rng(1).choice(nbl_all, 6, replace=False).tolist())
+    gf = list(range(3, nf, 16))
+    gbt, gft = torch.as_tensor(gb, device=V1.device), torch.as_tensor(gf, device=V1.device)
+    shp = (1, 1, len(gb), nt, len(gf))
+    G_sub = torch.complex(torch.randn(shp, generator=gen, dtype=torch.float64),
+                          torch.randn(shp, generator=gen, dtype=torch.float64))
+    G[0, 0, gbt[:, None, None], torch.arange(nt, device=V1.device)[None, :, None], gft[None, None, :]] = \
+        G_sub[0, 0].to(V1.device, torch.complex64)
+    torch.sum(G.real * V1.real + G.imag * V1.imag).backward()
+    Vgrid = torch.zeros_like(V1)
+    seen = 0
+    for b in range(rime.Nbatch):
+        rime.batch_idx = b
+        assert rime._tc_tiling(dev) is not None, "minibatch %d left the tensor-core kernels" % b
+        vd = rime()
+        rows = torch.as_tensor([row[bl] for bl in rime.sim_bls], device=V1.device)
+        tsel = [int(np.argmin(np.abs(np.asarray(one.sim_times) - t))) for t in rime.sim_times]
+        assert len(tsel) == 1
+        Vgrid[:, :, rows, tsel[0]] = vd.data[:, :, :, 0].detach()
+        Gb = G[:, :, rows][:, :, :, tsel]
+        torch.sum(Gb.real * vd.data.real + Gb.imag * vd.data.imag).backward()
+        seen += len(rows)
+    assert seen == nbl_all * nt
+    assert relmax(Vgrid, V1, "c5_grid/V_vs_one_batch") < 2e-6
+    assert relmax(rime.sky.params.grad, one.sky.params.grad, "c5_grid/dsky_vs_one_batch") < 5e-6
+    assert relmax(rime.beam.params.grad, one.beam.params.grad, "c5_grid/dbeam_vs_one_batch") < 5e-6
+    # fp64 oracle on the cotangent's support
+    zenaz = [(za[0].cpu().double(), za[1].cpu().double()) for za in workloads.zenaz_of(one)]
+    fi = torch.as_tensor(gf)
+    freqs = one.array.freqs.detach().cpu().double()[fi]
+    antvecs = one.array.antvecs.detach().cpu().double()
+    sp = one.sky.params.detach().cpu().double()[:, :, fi].requires_grad_(True)
+    bp = one.beam.params.detach().cpu().double()[:, :, :, fi].requires_grad_(True)
+    bls = [one.sim_bls[i] for i in gb]
+    blvecs = orc.get_blvecs(antvecs, one.array.ants, bls)
+    bmap = orc.pixel_response_forward(bp, powerbeam=True)
+    tg, pg = one.beam.R.theta_grid.cpu().double(), one.beam.R.phi_grid.cpu().double()
+
+    def beam_fn(z, a):
+        inds, wgts = orc.rect_interp_weights(tg, pg, z, a, 'linear')
+        return orc.interp_map(bmap, inds, wgts)
+
+    Vo = orc.rime_forward(sp * float(one.sky.px_area), zenaz, beam_fn, bls, blvecs, freqs, fov=180.0)
+    oc.real_loss(Vo, G_sub).backward()
+    sub = Vgrid[0, 0][gbt][:, :, gft].cpu().to(torch.complex128)
+    err = float((sub - Vo[0, 0].detach()).abs().max()) / float(V1.abs().max())
+    ERRLOG["c5_grid/V_vs_oracle"] = err
+    assert err < 1e-5
+    assert relmax(rime.sky.params.grad[:, :, gf], sp.grad, "c5_grid/dsky_vs_oracle") < 5e-5
+    assert relmax(rime.beam.params.grad[:, :, :, gf], bp.grad, "c5_grid/dbeam_vs_oracle") < 5e-5
