@@ -65,6 +65,7 @@ _ANT_SIGS = {
     "tcfringe_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _L, _I, _P, _P, _P],
 }
 _ANT_SIGS.update({
+    "build_interp_bwd_t": [_P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _L, _L, _P, _L, _P, _P],
     "tc_pack_cotangent": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "cgemm_pack_a": [_P, _P, _L, _L, _I, _I, _P, _I, _P, _P],
     "cgemm_pack_b": [_P, _P, _L, _L, _I, _I, _P, _I, _P, _P],

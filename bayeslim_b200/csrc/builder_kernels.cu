@@ -355,6 +355,74 @@ build_interp_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ bmap, lo
     }
 }
 
+// Backward of build_interp_t for float32 bilinear tables from the CHANNEL-MAJOR beam map: like the
+// forward, a half-warp owns a source and a lane four channels, so the neighbour reads and the
+// cotangent read are 16-byte loads of fully used lines; the sky tile comes in and the two outputs
+// (row-major over sources) go out through shared-memory transposes.
+//   dIs[f*ldd + s] = B[f][s] dA[f][s]      dBI[f*ldd + s] = sky[f][cut[s]] dA[f][s]
+__global__ void __launch_bounds__(BUILD_THREADS)
+build_interp_bwd_t_kernel(const float* __restrict__ dA, const float* __restrict__ bmapT,
+                          long long ldt, const int* __restrict__ inds,
+                          const float* __restrict__ wgts, const float* __restrict__ sky,
+                          long long lds, const int* __restrict__ cut, int nfreq, int ns,
+                          long long soff, long long S, float* __restrict__ dBI, long long ldd,
+                          float* __restrict__ dIs) {
+    constexpr int KC = Cfg<float>::KC;
+    constexpr int ROWS = BUILD_THREADS / 32, SPW = TS / ROWS;
+    static_assert(KC == 64, "a half-warp covers the 64 channels of a chunk");
+    __shared__ float tI[KC][TS + 1], o1[KC][TS + 1], o2[KC][TS + 1];
+    __shared__ int spix[TS];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int chunk = blockIdx.y;
+    {
+        const int s = blockIdx.x * TS + tx;
+        const int pix = (s < ns) ? cut[s] : -1;
+        if (ty == 0) spix[tx] = pix;
+#pragma unroll
+        for (int i = 0; i < KC / ROWS; ++i) {
+            const int k = ty + i * ROWS, f = chunk * KC + k;
+            tI[k][tx] = (pix >= 0 && f < nfreq) ? sky[(size_t)f * lds + pix] : 0.f;
+        }
+    }
+    __syncthreads();
+    const float* g0 = dA + ((size_t)chunk * (size_t)S + (size_t)soff + (size_t)blockIdx.x * TS) * KC;
+    const float* bcol = bmapT + (size_t)chunk * KC;
+    const int half = tx >> 4, c4 = (tx & 15) * 4;
+#pragma unroll
+    for (int j = 0; j < SPW / 2; ++j) {
+        const int sl = ty * SPW + 2 * j + half;
+        const int s = blockIdx.x * TS + sl;
+        const bool live = spix[sl] >= 0;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f), g = b;
+        if (live) {
+            g = __ldg(reinterpret_cast<const float4*>(g0 + (size_t)sl * KC + c4));
+            if (dIs != nullptr) {
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const int ix = __ldg(inds + (size_t)s * 4 + n);
+                    const float w = __ldg(wgts + (size_t)s * 4 + n);
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(bcol + (size_t)ix * ldt + c4));
+                    b.x += v.x * w, b.y += v.y * w, b.z += v.z * w, b.w += v.w * w;
+                }
+            }
+        }
+        o1[c4][sl] = b.x * g.x, o1[c4 + 1][sl] = b.y * g.y;
+        o1[c4 + 2][sl] = b.z * g.z, o1[c4 + 3][sl] = b.w * g.w;
+        o2[c4][sl] = tI[c4][sl] * g.x, o2[c4 + 1][sl] = tI[c4 + 1][sl] * g.y;
+        o2[c4 + 2][sl] = tI[c4 + 2][sl] * g.z, o2[c4 + 3][sl] = tI[c4 + 3][sl] * g.w;
+    }
+    __syncthreads();
+    const int s = blockIdx.x * TS + tx;
+    if (s >= ns) return;
+#pragma unroll
+    for (int i = 0; i < KC / ROWS; ++i) {
+        const int k = ty + i * ROWS, f = chunk * KC + k;
+        if (f >= nfreq) break;
+        if (dIs != nullptr) dIs[(size_t)f * ldd + s] = o1[k][tx];
+        if (dBI != nullptr) dBI[(size_t)f * ldd + s] = o2[k][tx];
+    }
+}
+
 // dbmap[f][p] += sum_j val[j] * dBI[f][col[j]] over the CSR row of pixel p
 template <typename T>
 __global__ void __launch_bounds__(BUILD_THREADS)
@@ -903,6 +971,23 @@ int b200rime_build_interp_bwd_f64(const double* dA, const double* bmap, long lon
                                   void* stream) {
     return launch_build_interp_bwd<double>(dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, ns,
                                            soff, S, dsky, dBI, ldd, dIs, ST(stream));
+}
+int b200rime_build_interp_bwd_t_f32(const float* dA, const float* bmapT, long long ldt,
+                                    const int* inds, const float* wgts, const float* sky,
+                                    long long lds, const int* cut, int nfreq, int ns, long long soff,
+                                    long long S, float* dBI, long long ldd, float* dIs,
+                                    void* stream) {
+    using namespace b200rime;
+    if (ns <= 0 || nfreq <= 0) return 0;
+    if (soff % TS) return set_error("build_interp_bwd_t: bad offset");
+    if (dA == nullptr || bmapT == nullptr || sky == nullptr || inds == nullptr || wgts == nullptr)
+        return set_error("build_interp_bwd_t: null operand");
+    if (ldt < (long long)nchunks<float>(nfreq) * Cfg<float>::KC)
+        return set_error("build_interp_bwd_t: needs a channel-major beam map padded to whole chunks");
+    dim3 grid((ns + TS - 1) / TS, nchunks<float>(nfreq));
+    build_interp_bwd_t_kernel<<<grid, BUILD_THREADS, 0, ST(stream)>>>(
+        dA, bmapT, ldt, inds, wgts, sky, lds, cut, nfreq, ns, soff, S, dBI, ldd, dIs);
+    return check_launch("build_interp_bwd_t");
 }
 int b200rime_interp_transpose_f32(const float* dBI, long long ldd, const int* rowptr,
                                   const int* col, const float* val, int npix, int nfreq,

@@ -305,6 +305,7 @@ class _BuildInterp(torch.autograd.Function):
         kc = _lib.KC[sfx]
         S = max(geom.S, 1)
         A = torch.empty(1, nchunks(nfreq, dtype), S, kc, dtype=dtype, device=ref.device)
+        ctx.bT = None
         if geom.S > 0 and bmap is not None:
             # channel-major copy of the beam map (zero padded to whole chunks): neighbour reads
             # become full 128-byte lines instead of 32 scattered pixels per load
@@ -314,6 +315,8 @@ class _BuildInterp(torch.autograd.Function):
             _call("build_interp_t", sfx, bT, nfp, tab.inds, tab.wgts, tab.nnn, sky,
                   sky.shape[1] if sky is not None else 0, tab.cut, nfreq, geom.S, geom.S, 0,
                   geom.S, A[0])
+            if sfx == "f32" and tab.nnn == 4 and sky is not None:
+                ctx.bT = bT             # 0.13 GB at C3: kept for the channel-major backward
         elif geom.S > 0:
             _call("build_interp", sfx, None, 0, tab.inds, tab.wgts, tab.nnn, sky, sky.shape[1],
                   tab.cut, nfreq, geom.S, geom.S, 0, geom.S, A[0])
@@ -337,9 +340,13 @@ class _BuildInterp(torch.autograd.Function):
             S = geom.S
             dIs = torch.empty(nfreq, S, dtype=dA.dtype, device=dA.device) if need_sky else None
             dBI = torch.empty(nfreq, S, dtype=dA.dtype, device=dA.device) if need_beam else None
-            _call("build_interp_bwd", sfx, dA[0], bmap, bmap.shape[1] if bmap is not None else 0,
-                  tab.inds, tab.wgts, tab.nnn, sky, sky.shape[1] if sky is not None else 0, tab.cut,
-                  nfreq, S, 0, S, None, dBI, S, dIs)
+            if ctx.bT is not None:
+                _call("build_interp_bwd_t", sfx, dA[0], ctx.bT, ctx.bT.shape[1], tab.inds, tab.wgts,
+                      sky, sky.shape[1], tab.cut, nfreq, S, 0, S, dBI, S, dIs)
+            else:
+                _call("build_interp_bwd", sfx, dA[0], bmap, bmap.shape[1] if bmap is not None else 0,
+                      tab.inds, tab.wgts, tab.nnn, sky, sky.shape[1] if sky is not None else 0,
+                      tab.cut, nfreq, S, 0, S, None, dBI, S, dIs)
             if need_sky:
                 _call("gather_times", sfx, dIs, S, tab.pos, geom.nt, tab.npix_sky, nfreq, dsky,
                       sky.shape[1])
@@ -865,6 +872,8 @@ class TcTiling:
         operands M = (-Hi ; Hr) / P = (Hr ; Hi):
         [nt][Nfp][item][stage of 16 m][hi | lo][3 halves][16 row groups][2 k groups][8 rows][8 k]."""
         nbl, nt, nf = G.shape
+        if G.dtype != torch.complex64:
+            G = G.to(torch.complex64)
         if G.stride(2) != 1 or G.stride(1) != nf:
             G = G.contiguous()
         # max |H| <= 2 max(|Re G|, |Im G|) when entries are doubled (autos, lower triangle)

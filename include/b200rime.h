@@ -179,6 +179,13 @@ int b200rime_build_interp_f64(const double* bmap, long long ldb, const int* inds
  * b200rime_interp_transpose_* then gathers dBI into the beam map through the CSR transpose of
  * (inds, wgts):  dbmap[f*ldb + p] += sum_{j in [rowptr[p], rowptr[p+1])} val[j] *
  * dBI[f*ldd + col[j]]   -- one owner per (f, p), no atomics. */
+/* float32, bilinear (4 neighbours) form of the backward from the channel-major beam map of
+ * build_interp_t (16-byte neighbour and cotangent reads; dIs / dBI as above, each optional). */
+int b200rime_build_interp_bwd_t_f32(const float* dA, const float* bmapT, long long ldt,
+                                    const int* inds, const float* wgts, const float* sky,
+                                    long long lds, const int* cut, int nfreq, int ns, long long soff,
+                                    long long S, float* dBI, long long ldd, float* dIs,
+                                    b200rime_stream_t stream);
 int b200rime_build_interp_bwd_f32(const float* dA, const float* bmap, long long ldb,
                                   const int* inds, const float* wgts, int nnn, const float* sky,
                                   long long lds, const int* cut, int nfreq, int ns, long long soff,

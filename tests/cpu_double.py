@@ -164,6 +164,12 @@ def build_interp_bwd(sfx, dA, bmap, ldb, inds, wgts, nnn, sky, lds, cut, nfreq, 
         dBI[:, :ns] = I * g
 
 
+def build_interp_bwd_t(sfx, dA, bmapT, ldt, inds, wgts, sky, lds, cut, nfreq, ns, soff, S, dBI, ldd,
+                       dIs):
+    build_interp_bwd(sfx, dA, bmapT.t()[:nfreq], 0, inds, wgts, 4, sky, lds, cut, nfreq, ns, soff,
+                     S, None, dBI, ldd, dIs)
+
+
 def gather_times(sfx, dIs, ldd, pos, nt, npix, nfreq, dsky, lds):
     for t in range(nt):
         p = pos[t].long()
@@ -482,7 +488,7 @@ _TABLE = dict(fringe_sum_fwd=fringe_sum_fwd, reduce_units=reduce_units,
               tcfringe_fwd=tcfringe_fwd, tcfringe_bwd=tcfringe_bwd,
               apply_cal=apply_cal, apply_cal_bwd_gains=apply_cal_bwd_gains,
               jones_sandwich=jones_sandwich, jones_sandwich_bwd=jones_sandwich_bwd)
-_TABLE_LATE = ('cgemm_pack_a', 'cgemm_pack_b', 'cgemm', 'tc_pack_cotangent')
+_TABLE_LATE = ('cgemm_pack_a', 'cgemm_pack_b', 'cgemm', 'tc_pack_cotangent', 'build_interp_bwd_t')
 
 
 # ----------------------------------------------------------------------------- a_lm -> map

@@ -918,7 +918,9 @@ def test_cotangent_pack_kernel_equals_dense_construction(lower_only):
     i_idx, j_idx = [p[0] for p in pairs], [p[1] for p in pairs]
     tc = ops.TcTiling(i_idx, j_idx, na, 'cuda')
     assert tc.usable and len(tc.auto) > 0 and len(tc.igt) > 0
-    G = torch.complex(torch.randn(len(pairs), nt_all, nf), torch.randn(len(pairs), nt_all, nf)).cuda()
+    gen = torch.Generator().manual_seed(8)
+    G = torch.complex(torch.randn(len(pairs), nt_all, nf, generator=gen, dtype=torch.float32),
+                      torch.randn(len(pairs), nt_all, nf, generator=gen, dtype=torch.float32)).cuda()
     nfp = ops.nchunks(nf, torch.float32) * _lib.KC["f32"]
     Gs = G[:, 1:3]                                           # a time sub-range: strided view
     Hq, hscale = tc.cotangent_operand(Gs, nfp, lower_only=lower_only)
