@@ -175,16 +175,20 @@ class PixelSky(SkyBase):
 
 
 class PixelSkyResponse:
-    """Spatial ('pixel' | 'linear' via spat_LM) and frequency ('channel' | 'linear' | 'powerlaw')
-    parameterisation of a PixelSky (sky_model.py:510-732).  'alm' / 'bessel' modes need the
-    spherical-harmonic stack, which is outside the RIME path."""
+    """Spatial ('pixel' | 'linear' via spat_LM | 'alm': spat_LM is a sph_harm.AlmModel, the a_lm ->
+    pixel product runs on the CUDA spherical-harmonic GEMM) and frequency ('channel' | 'linear' |
+    'powerlaw') parameterisation of a PixelSky (sky_model.py:510-732).  The 'bessel' frequency
+    mode needs the spherical Fourier-Bessel stack and the cosmology module, which are outside
+    the RIME path."""
 
     def __init__(self, freqs, comp_params=False, spatial_mode='pixel', freq_mode='channel',
                  device=None, transform_order=0, cosmo=None, spat_LM=None, freq_LM=None, f0=None,
                  gln=None, kbins=None, log=False, real_output=True, abs_output=False, LM=None,
                  sky0=None):
-        if spatial_mode == 'alm' or freq_mode == 'bessel':
-            raise NotImplementedError("alm / bessel sky parameterisations are out of scope")
+        if freq_mode == 'bessel':
+            raise NotImplementedError("the spherical Fourier-Bessel sky parameterisation is out of scope")
+        if spatial_mode in ('alm', 'linear'):
+            assert spat_LM is not None, "spatial_mode '%s' needs spat_LM" % spatial_mode
         self.freqs = freqs
         self.comp_params = comp_params
         self.Nfreqs = len(freqs)

@@ -273,6 +273,41 @@ def gold_rime_ylm():
          grad_antvecs=array.antvecs.grad, fov=180.0)
 
 
+def gold_rime_alm_sky():
+    """Spherical-harmonic sky (sky_model.py:510-732, spatial_mode='alm'): PixelSky whose pixel
+    intensities are a_lm coefficients forward-modelled by an AlmModel (sph_harm.py:1289-1373),
+    complex coefficients in 2-real form, sky0 offset; Airy beam; gradients to the a_lm and antvecs."""
+    rng = np.random.default_rng(51)
+    freqs = torch.linspace(100e6, 200e6, 6)
+    times = np.linspace(2458148.15, 2458148.25, 2)
+    ants, vecs, array = hera_array(2, freqs, set_param=True)
+    bls = [(0, 1), (0, 2), (0, 3), (1, 5), (2, 6), (0, 6), (3, 4)]
+    ra, dec, px_area, sparams = healpix_sky(4, freqs, rng)
+    angs = torch.as_tensor(np.stack([ra, dec]))
+    l, m = ba.sph_harm.gen_lm(5, real_field=True)
+    A = ba.sph_harm.AlmModel(l, m, real_output=False, default_kw=dict(high_prec=False))
+    A.setup_Ylm(90.0 - dec, ra, generate=True)
+    g = torch.Generator().manual_seed(9)
+    p = 0.3 * torch.randn(1, 1, len(freqs), len(l), 2, generator=g) \
+        / (1.0 + torch.as_tensor(l, dtype=torch.float64))[:, None]
+    R = ba.sky_model.PixelSkyResponse(freqs, comp_params=True, spatial_mode='alm', spat_LM=A,
+                                      freq_mode='channel', sky0=sparams.clone())
+    sky = ba.sky_model.PixelSky(p.clone(), angs, px_area, R=R, parameter=True)
+    beam = ba.beam_model.PixelBeam(torch.ones(1, 1, 1, 1, 1) * 14.0, freqs,
+                                   R=ba.beam_model.AiryResponse(powerbeam=True), pol='e',
+                                   powerbeam=True, fov=180, parameter=False)
+    tel = ba.telescope_model.TelescopeModel(LOC)
+    rime = ba.rime_model.RIME(sky, tel, beam, array, bls, times, freqs)
+    zen_az = inject_geometry(rime, sky.name, ra, dec, rime.sim_times)
+    vd = rime()
+    G = cotangent(vd.data.shape, 105)
+    backward_with(vd.data, G)
+    save("rime_alm_sky", antvecs=vecs, ants=ants, bls=bls, freqs=freqs, times=times, ra=ra, dec=dec,
+         zen_az=zen_az, sky_params=p, sky0=sparams, px_area=px_area, l=l, m=m,
+         Ylm_sample=A.Ylm[:, ::17], alm_mult=A.alm_mult, vis=vd.data, G=G,
+         grad_sky=sky.params.grad, grad_antvecs=array.antvecs.grad, fov=180.0)
+
+
 def healpix_sky(nside, freqs, rng, dec_max=59.27852):
     theta, phi = orc.healpix_pix2ang(nside)
     dec = np.pi / 2 - theta
@@ -709,6 +744,7 @@ if __name__ == "__main__":
     gold_rime_pixel_interp()
     gold_alm()
     gold_rime_ylm()
+    gold_rime_alm_sky()
     gold_rime_pointing()
     gold_rime_batched()
     gold_rime_2pol()

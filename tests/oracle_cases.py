@@ -126,6 +126,26 @@ def oracle_ylm(g, dtype=torch.float64):
     return V, dict(sky=sky_params, beam=beam_params, antvecs=antvecs), beam_cache
 
 
+def oracle_alm_sky(g, dtype=torch.float64):
+    """rime_alm_sky fixture: a_lm --AlmModel--> pixel sky (+ sky0) x px_area --Airy beam--> RIME."""
+    antvecs = tt(g["antvecs"], dtype, grad=True)
+    sky_params = tt(g["sky_params"], dtype, grad=True)
+    freqs = tt(g["freqs"], dtype)
+    ants = [int(a) for a in g["ants"]]
+    bls = bl_list(g["bls"])
+    blvecs = orc.get_blvecs(antvecs, ants, bls)
+    Ylm = torch.as_tensor(orc.sph_harm_matrix(g["l"], g["m"], np.radians(90.0 - g["dec"]),
+                                              np.radians(g["ra"])))
+    # PixelSkyResponse.__call__ (sky_model.py:674-701): spatial transform, .real, + sky0
+    sky = orc.alm_forward(sky_params, Ylm, tt(g["alm_mult"], dtype), real_output=True)
+    sky = (sky + tt(g["sky0"], dtype)) * float(g["px_area"])
+    zenaz = [(tt(za[0], dtype), tt(za[1], dtype)) for za in g["zen_az"]]
+    D = torch.ones(1, 1, 1, 1, 1, dtype=dtype) * 14.0
+    beam_fn = lambda z, a: orc.airy_response(D, z, a, freqs, powerbeam=True)
+    V = orc.rime_forward(sky, zenaz, beam_fn, bls, blvecs, freqs, fov=float(g["fov"]))
+    return V, dict(sky=sky_params, antvecs=antvecs), Ylm
+
+
 def oracle_2pol(g, dtype=torch.float64):
     antvecs = tt(g["antvecs"], dtype)
     sky_params = tt(g["sky_params"], dtype, grad=True)

@@ -185,6 +185,14 @@ def test_rime_ylm_vs_reference():
     _check(V, leaves, g, dict(sky="grad_sky", beam="grad_beam", antvecs="grad_antvecs"))
 
 
+def test_rime_alm_sky_vs_reference():
+    """PixelSkyResponse(spatial_mode='alm') through the RIME (sky_model.py:510-732)."""
+    g = oc.load("rime_alm_sky")
+    V, leaves, Ylm = oc.oracle_alm_sky(g)
+    assert np.abs(Ylm.numpy()[:, ::17] - g["Ylm_sample"]).max() < 1e-13
+    _check(V, leaves, g, dict(sky="grad_sky", antvecs="grad_antvecs"))
+
+
 def test_rime_pixel_interp_vs_reference():
     g = oc.load("rime_pixel_interp")
     V, leaves = oc.oracle_pixel_interp(g)
