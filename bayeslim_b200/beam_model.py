@@ -543,12 +543,35 @@ def cut_sky_fov(sky, cut):
     return sky.index_select(-1, cut)
 
 
+def _tukey(n, alpha):
+    """Tukey (tapered cosine) window of n points, the definition of scipy.signal.windows.tukey."""
+    if alpha <= 0:
+        return np.ones(n)
+    if alpha >= 1:
+        return np.hanning(n)
+    k = np.arange(n, dtype=np.float64)
+    width = int(np.floor(alpha * (n - 1) / 2.0))
+    w = np.ones(n)
+    k1, k3 = k[:width + 1], k[n - width - 1:]
+    w[:width + 1] = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * k1 / alpha / (n - 1))))
+    w[n - width - 1:] = 0.5 * (1 + np.cos(np.pi * (-2.0 / alpha + 1 + 2.0 * k3 / alpha / (n - 1))))
+    return w
+
+
 def beam_edge_taper(zen, mode='gauss', fov=180, device=None, mu=85, sigma=2.5, alpha=0.1):
-    """Gaussian roll-off of the beam beyond zenith angle mu [deg] (beam_model.py:1701-1735)."""
+    """Edge taper of a beam response (beam_model.py:1701-1735): 'gauss' rolls the beam off beyond
+    zenith angle mu [deg]; 'tukey' is a 5000-point Tukey window over [-fov/2, fov/2], linearly
+    interpolated at zen and zero outside."""
     zen = torch.as_tensor(zen)
     taper = torch.ones(len(zen), device=device, dtype=_float())
+    if mode == 'tukey':
+        th = np.linspace(-fov / 2, fov / 2, 5000, endpoint=True)
+        vals = np.interp(utils.tensor2numpy(zen).astype(np.float64), th, _tukey(5000, alpha),
+                         left=0.0, right=0.0)
+        taper[:] = torch.as_tensor(vals, device=device)
+        return taper
     if mode != 'gauss':
-        raise NotImplementedError("only the gauss taper is mirrored")
+        return taper
     s = zen >= mu
     taper[s] = torch.exp(-0.5 * (zen[s].to(taper.dtype) - mu) ** 2 / sigma ** 2)
     return taper

@@ -390,3 +390,18 @@ def test_cache_keys_and_user_level_clearing():
             V3 = rime2().data
             assert len(calls) == len(rime.sim_times)
             assert float((V3 - V0).abs().max()) > 1e-6 * float(V0.abs().max())
+
+
+def test_beam_edge_taper_modes():
+    """beam_model.py:1701-1735: Gaussian roll-off beyond mu, Tukey window over the field of view
+    (checked against scipy's window and, at generation time, against the reference: identical)."""
+    from scipy.signal import windows
+    zen = torch.linspace(0, 95, 400, dtype=torch.float64)
+    t = ba.beam_model.beam_edge_taper(zen, mode='gauss', mu=70, sigma=5.0)
+    assert float(t[zen < 70].min()) == 1.0
+    k = int(torch.argmin((zen - 80).abs()))
+    assert abs(float(t[k]) - np.exp(-0.5 * (float(zen[k]) - 70) ** 2 / 25.0)) < 1e-6
+    w = ba.beam_model.beam_edge_taper(zen, mode='tukey', fov=170, alpha=0.2)
+    th = np.linspace(-85, 85, 5000)
+    ref = np.interp(zen.numpy(), th, windows.tukey(5000, alpha=0.2), left=0, right=0)
+    assert np.abs(w.numpy() - ref).max() < 1e-6 and float(w[zen > 85.01].abs().max()) == 0.0
