@@ -46,6 +46,8 @@ def test_no_cpu_path():
         rime()
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.fringe_sum(torch.zeros(1, 1, 128, 32), torch.zeros(2, 3), None, torch.zeros(4), 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ba.rime_model.GraphedStep(rime, lambda vd: vd.data.abs().sum(), [rime.sky.params])
 
 
 @pytest.mark.parametrize("name", list(mc.CASES))
