@@ -1,10 +1,7 @@
 #!/bin/bash
-# final tree check: full GPU suite, smoke, default bench
+# what the driver runs at round end: GPU test suite (-x), smoke, default bench
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?"; tail -n 3 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-echo "smoke exit $?"; tail -n 2 gpurun_out/smoke.log
-timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-echo "bench default exit $?"; cut -c1-260 gpurun_out/bench_default.json
+timeout 1500 python -m pytest tests/ -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log | cut -c1-200
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log | cut -c1-300
+timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; head -c 300 gpurun_out/bench_default.json
