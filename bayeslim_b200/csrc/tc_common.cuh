@@ -12,6 +12,12 @@ namespace b200rime {
 #ifndef B200_TC_PROBE
 #define B200_TC_PROBE 0            // timing probes (wrong results): 1 no sine / cosine, 2 no MMAs, 4 no generation
 #endif
+#ifndef B200_TC_UNROLL_FWD
+#define B200_TC_UNROLL_FWD 1       // unroll the two 8-source halves of a stage in the generating loop
+#endif
+#ifndef B200_TC_UNROLL_BWD
+#define B200_TC_UNROLL_BWD 0
+#endif
 #ifndef B200_TC_FLUSH
 #define B200_TC_FLUSH 4            // stages (of 16 sources) per TMEM accumulation chain
 #endif

@@ -1,11 +1,11 @@
 #!/bin/bash
-# timing (and parity) of the tensor-core forward kernel for every library variant
+# timing (and parity) of the tensor-core kernels for every library variant against the shipped build
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 : > gpurun_out/tc_variants.jsonl
-for so in bayeslim_b200/csrc/variants/lib_tcv*.so; do
+for so in bayeslim_b200/csrc/libb200rime.so bayeslim_b200/csrc/variants/lib_tcv*.so bayeslim_b200/csrc/libb200rime.so; do
   echo "== $so" >> gpurun_out/tc_variants.jsonl
   B200RIME_LIB=$PWD/$so timeout 200 python scripts/tc_probe.py time >> gpurun_out/tc_variants.jsonl 2>> gpurun_out/tc_variants.err
-  echo "$so exit $?"
+  B200RIME_LIB=$PWD/$so timeout 300 python scripts/tc_probe.py bwd 2>> gpurun_out/tc_variants.err | tail -2 >> gpurun_out/tc_variants.jsonl
 done
-cat gpurun_out/tc_variants.jsonl
+tail -2 gpurun_out/tc_variants.err
