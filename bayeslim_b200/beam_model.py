@@ -11,14 +11,13 @@ path does not go through ``apply_beam`` / ``PixInterp.interp`` / ``airy_disk``: 
 model state (params, p0, response type, interpolation tables) and evaluates the beam inside
 the fused CUDA builders (ops.build_interp / ops.build_airy), see rime_model.RIME.
 """
-import copy
 import math
 
 import numpy as np
 import torch
 
 from . import utils, sph_harm
-from .utils import _float, _cfloat, D2R
+from .utils import _float, D2R
 
 C_LIGHT = 2.99792458e8
 

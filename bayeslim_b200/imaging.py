@@ -19,8 +19,8 @@ Not mirrored: the dense (Npix, Npix) PSF matrix (``contract=None``), ``deconvolv
 import numpy as np
 import torch
 
-from . import ops, telescope_model, utils
-from .dataset import VisData, MapData
+from . import ops, telescope_model
+from .dataset import MapData
 
 
 class VisMapper:
@@ -289,12 +289,3 @@ class VisMapper:
             out *= D
         return out
 
-
-def make_map(v, w, A):
-    """torch form for a materialised A (imaging.py:717-736); VisMapper.make_map does not use it."""
-    return torch.einsum('vfp,...vf->...fp', A, v * w).real
-
-
-def compute_Am(A, m):
-    """torch form for a materialised A (imaging.py:755-774)."""
-    return torch.einsum("vfp,...fp->...vf", A.conj(), m)

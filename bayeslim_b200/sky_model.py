@@ -8,7 +8,6 @@ MapData exactly as the reference does (rime_model.py:306).
 import torch
 
 from . import utils, dataset
-from .utils import _float, _cfloat
 
 
 class SkyBase(utils.Module):
