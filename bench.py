@@ -428,7 +428,7 @@ def main():
         if rank != 0:
             return
         gpu = args.impl == "reference-gpu"
-        steps = max(1, min(args.steps, 5))
+        steps = 5 if not gpu else max(1, min(args.steps, 5))   # CPU arm: always 5 timed steps of ~10 s
         warm = max(1, min(args.warmup, 1))
         try:
             r = reference_arm(args.workload, steps, warm, mode=args.mode,
